@@ -1,0 +1,300 @@
+"""Python host of the C ABI with the SAME five entry points, argument order and return tuples as the
+reference's pybind module ``diff_gaussian_rasterization._C`` (reference: ext.cpp:15-23,
+rasterize_points.cu:35-432), so the reference's own ``__init__.py`` could be run against it unchanged.
+
+torch is used here only for what the task calls plumbing: device memory (tensors from the caching
+allocator), the current stream and the device guard.  All arithmetic happens in libhsraster.so.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import weakref
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+# -- behaviour switches ------------------------------------------------------------------------------
+# 'ref'   : reproduce the reference's observable semantic backward (quirk Q1):
+#           semantic channels do not contribute to dL/dalpha.
+# 'exact' : the mathematically intended gradient.
+SEM_ALPHA_GRAD = os.environ.get("HS_SEM_ALPHA_GRAD", "ref")
+NO_CULL = os.environ.get("HS_NO_CULL", "0") == "1"
+
+_contig_cache: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
+
+
+def _small_contig(t: torch.Tensor) -> torch.Tensor:
+    """Contiguous float32 version of a small camera tensor, cached per tensor object + version
+    (the [1,4,4] matrices of utils/recon_helpers.py:8-13 are transposed views and are reused every frame)."""
+    if t.is_contiguous() and t.dtype == torch.float32:
+        return t
+    hit = _contig_cache.get(t)
+    if hit is not None and hit[0] == t._version:
+        return hit[1]
+    c = t.contiguous().float()
+    _contig_cache[t] = (t._version, c)
+    return c
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    if t is None or t.numel() == 0:
+        return None
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _f32c(t: torch.Tensor, name: str, device) -> torch.Tensor:
+    if t.numel() == 0:
+        return t
+    if t.device != device:
+        raise RuntimeError(f"{name} must live on {device}, got {t.device}")
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"{name} must be float32, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _camera(background, scale_modifier, viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height, image_width,
+            campos, prefiltered, debug):
+    keep = (_small_contig(viewmatrix), _small_contig(projmatrix), _small_contig(background),
+            _small_contig(campos) if campos is not None and campos.numel() else None)
+    cam = _lib.HsCamera(int(image_height), int(image_width), float(tan_fovx), float(tan_fovy), float(scale_modifier),
+                        keep[0].data_ptr(), keep[1].data_ptr(), keep[2].data_ptr(),
+                        keep[3].data_ptr() if keep[3] is not None else None, int(bool(prefiltered)), int(bool(debug)))
+    return cam, keep
+
+
+def _forward(background, means3D, colors, semantics, opacity, scales, rotations, scale_modifier, cov3D_precomp,
+             viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height, image_width, sh, degree, campos, prefiltered,
+             debug, semantic: bool):
+    lib = _lib.load()
+    if means3D.dim() != 2 or means3D.size(1) != 3:
+        raise RuntimeError("means3D must have dimensions (num_points, 3)")   # rasterize_points.cu:266-268
+    if not means3D.is_cuda:
+        raise RuntimeError("hier_slam_b200 rasterizer is CUDA-only (no CPU fallback): means3D must be a CUDA tensor")
+    device = means3D.device
+    P = means3D.size(0)
+    H, W = int(image_height), int(image_width)
+    S = int(semantics.size(1)) if (semantic and semantics.numel() > 0) else 0
+    if semantic and semantics.numel() > 0 and (semantics.dim() != 2 or semantics.size(0) != P):
+        raise RuntimeError("semantics_precomp must have dimensions (num_points, S)")
+    if not lib.hs_supports_semantic_channels(S):
+        raise RuntimeError(f"semantic channel count S={S} is not instantiated in libhsraster (built: 0,16,26,74,102)")
+    if colors.numel() == 0 and P > 0:
+        raise RuntimeError("only precomputed colours are supported (the spherical-harmonics colour path of the "
+                           "reference, forward.cu:20-71, is never used by Hier-SLAM and is not implemented)")
+    fopt = dict(dtype=torch.float32, device=device)
+    with torch.cuda.device(device):
+        stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+        radii = torch.empty(P, dtype=torch.int32, device=device)
+        byte = dict(dtype=torch.uint8, device=device)
+        if P == 0:
+            # reference: outputs are zero-filled and the rasterizer is not run (rasterize_points.cu:277-292)
+            z = lambda c: torch.zeros(c, H, W, **fopt)
+            empty = torch.empty(0, **byte)
+            outs = (z(3), z(S) if semantic else None, z(1), z(1), z(1), z(1))
+            return 0, outs, radii, empty, empty, empty
+        means3D_c = _f32c(means3D, "means3D", device)
+        colors_c = _f32c(colors, "colors_precomp", device)
+        sem_c = _f32c(semantics, "semantics_precomp", device) if S else None
+        opac_c = _f32c(opacity, "opacities", device)
+        scales_c = _f32c(scales, "scales", device)
+        rot_c = _f32c(rotations, "rotations", device)
+        cov_c = _f32c(cov3D_precomp, "cov3D_precomp", device)
+        cam, keep = _camera(background, scale_modifier, viewmatrix, projmatrix, tan_fovx, tan_fovy, H, W, campos,
+                            prefiltered, debug)
+        geom_bytes = lib.hs_geom_state_bytes(P)
+        geomBuffer = torch.empty(geom_bytes, **byte)
+        R = ctypes.c_int(0)
+        _lib.check(lib.hs_forward_geometry(ctypes.byref(cam), P, _ptr(means3D_c), _ptr(opac_c), _ptr(scales_c),
+                                           _ptr(rot_c), _ptr(cov_c), _ptr(radii), _ptr(geomBuffer), geom_bytes,
+                                           ctypes.byref(R), stream), "hs_forward_geometry")
+        num_rendered = int(R.value)
+        bin_bytes = lib.hs_binning_state_bytes(num_rendered)
+        binningBuffer = torch.empty(bin_bytes, **byte)
+        img_bytes = lib.hs_image_state_bytes(H, W)
+        imgBuffer = torch.empty(img_bytes, **byte)
+        out_color = torch.empty(3, H, W, **fopt)
+        out_sem = torch.empty(S, H, W, **fopt) if semantic else None
+        out_depth = torch.empty(1, H, W, **fopt)
+        out_median = torch.empty(1, H, W, **fopt)
+        out_opacity = torch.empty(1, H, W, **fopt)
+        out_mask = None if semantic else torch.empty(1, H, W, **fopt)
+        flags = _lib.HS_NO_CULL if NO_CULL else 0
+        _lib.check(lib.hs_forward_render(ctypes.byref(cam), P, S, num_rendered, _ptr(colors_c), _ptr(sem_c),
+                                         _ptr(radii), _ptr(geomBuffer), _ptr(binningBuffer), bin_bytes,
+                                         _ptr(imgBuffer), img_bytes, _ptr(out_color), _ptr(out_sem), _ptr(out_depth),
+                                         _ptr(out_median), _ptr(out_opacity), _ptr(out_mask), flags, stream),
+                   "hs_forward_render")
+        del keep
+    return num_rendered, (out_color, out_sem, out_depth, out_median, out_opacity, out_mask), radii, geomBuffer, \
+        binningBuffer, imgBuffer
+
+
+def rasterize_gaussians_semantic(background, means3D, colors, semantics, opacity, scales, rotations, scale_modifier,
+                                 cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height,
+                                 image_width, sh, degree, campos, prefiltered, debug):
+    """reference: RasterizeGaussiansCUDA_semantic, rasterize_points.cu:240-336."""
+    n, o, radii, gb, bb, ib = _forward(background, means3D, colors, semantics, opacity, scales, rotations,
+                                       scale_modifier, cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy,
+                                       image_height, image_width, sh, degree, campos, prefiltered, debug, True)
+    return n, o[0], o[1], o[2], o[3], o[4], radii, gb, bb, ib
+
+
+def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp,
+                        viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height, image_width, sh, degree, campos,
+                        prefiltered, debug):
+    """reference: RasterizeGaussiansCUDA, rasterize_points.cu:35-117 (returns out_mask before radii)."""
+    n, o, radii, gb, bb, ib = _forward(background, means3D, colors, torch.empty(0), opacity, scales, rotations,
+                                       scale_modifier, cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy,
+                                       image_height, image_width, sh, degree, campos, prefiltered, debug, False)
+    return n, o[0], o[2], o[3], o[4], o[5], radii, gb, bb, ib
+
+
+def _backward(background, means3D, radii, colors, semantics, scales, rotations, scale_modifier, cov3D_precomp,
+              viewmatrix, projmatrix, tan_fovx, tan_fovy, dL_dout_color, dL_dout_semantic, dL_dout_depth,
+              dL_dout_median_depth, dL_dout_final_opacity, sh, degree, campos, geomBuffer, R, binningBuffer,
+              imageBuffer, debug, H: int, W: int, semantic: bool):
+    lib = _lib.load()
+    device = means3D.device
+    P = means3D.size(0)
+    S = int(semantics.size(1)) if (semantic and semantics is not None and semantics.numel() > 0) else 0
+    M = sh.size(1) if (sh is not None and sh.numel() != 0) else 0
+    fopt = dict(dtype=torch.float32, device=device)
+    with torch.cuda.device(device):
+        # atomically accumulated outputs: ONE zero fill
+        nacc = 3 + 4 + 1 + 3 + S + 1
+        acc = torch.zeros(P * nacc, **fopt)
+        o = 0
+
+        def take(cols):
+            nonlocal o
+            v = acc[o:o + P * cols]
+            o += P * cols
+            return v
+        dL_dconic = take(4).view(P, 2, 2)       # first: read back as float4 (needs 16-B alignment)
+        dL_dsemantics = take(S).view(P, S)
+        dL_dmeans2D = take(3).view(P, 3)
+        dL_dcolors = take(3).view(P, 3)
+        dL_dopacity = take(1).view(P, 1)
+        dL_ddepths = take(1).view(P, 1)
+        dL_dmeans3D = torch.empty(P, 3, **fopt)
+        dL_dcov3D = torch.empty(P, 6, **fopt)
+        have_scales = scales is not None and scales.numel() > 0
+        dL_dscales = torch.empty(P, 3, **fopt) if have_scales else torch.zeros(P, 3, **fopt)
+        dL_drotations = torch.empty(P, 4, **fopt) if have_scales else torch.zeros(P, 4, **fopt)
+        dL_dsh = torch.zeros(P, M, 3, **fopt)
+        if P != 0:
+            stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+            cam, keep = _camera(background, scale_modifier, viewmatrix, projmatrix, tan_fovx, tan_fovy, H, W, campos,
+                                False, debug)
+            g = lambda t, name: None if t is None else _f32c(t, name, device)
+            gc, gs, gd, gm, go = (g(dL_dout_color, "dL_dout_color"), g(dL_dout_semantic, "dL_dout_semantic"),
+                                  g(dL_dout_depth, "dL_dout_depth"), g(dL_dout_median_depth, "dL_dout_median_depth"),
+                                  g(dL_dout_final_opacity, "dL_dout_final_opacity"))
+            means3D_c = _f32c(means3D, "means3D", device)
+            colors_c = _f32c(colors, "colors_precomp", device)
+            sem_c = _f32c(semantics, "semantics_precomp", device) if S else None
+            scales_c = _f32c(scales, "scales", device) if have_scales else None
+            rot_c = _f32c(rotations, "rotations", device) if have_scales else None
+            cov_c = _f32c(cov3D_precomp, "cov3D_precomp", device) if cov3D_precomp is not None else None
+            flags = _lib.HS_SEM_ALPHA_EXACT if SEM_ALPHA_GRAD == "exact" else 0
+            _lib.check(lib.hs_backward(
+                ctypes.byref(cam), P, S, int(R), _ptr(means3D_c), _ptr(radii), _ptr(colors_c), _ptr(sem_c),
+                _ptr(scales_c), _ptr(rot_c), _ptr(cov_c), _ptr(geomBuffer), _ptr(binningBuffer), _ptr(imageBuffer),
+                _ptr(gc), _ptr(gs), _ptr(gd), _ptr(gm), _ptr(go), _ptr(dL_dmeans2D), _ptr(dL_dconic),
+                _ptr(dL_dopacity), _ptr(dL_dcolors), _ptr(dL_dsemantics), _ptr(dL_ddepths), _ptr(dL_dmeans3D),
+                _ptr(dL_dcov3D), _ptr(dL_dscales) if have_scales else None,
+                _ptr(dL_drotations) if have_scales else None, flags, stream), "hs_backward")
+            del keep
+    return dL_dmeans2D, dL_dcolors, dL_dsemantics, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations
+
+
+def _hw(image_buffer_hint, grads, H, W):
+    for gten in grads:
+        if gten is not None:
+            return int(gten.size(1)), int(gten.size(2))
+    if H is None or W is None:
+        raise RuntimeError("image size unknown: all upstream gradients are None; pass image_height/image_width")
+    return int(H), int(W)
+
+
+def rasterize_gaussians_backward_semantic(background, means3D, radii, colors, semantics, scales, rotations,
+                                          scale_modifier, cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy,
+                                          dL_dout_color, dL_dout_semantic, dL_dout_depth, dL_dout_median_depth,
+                                          dL_dout_final_opacity, sh, degree, campos, geomBuffer, R, binningBuffer,
+                                          imageBuffer, debug, image_height=None, image_width=None):
+    """reference: RasterizeGaussiansBackwardCUDA_semantic, rasterize_points.cu:339-432.  H and W are taken from
+    dL_dout_color like the reference does (:369-370); the two optional trailing arguments supply them when the
+    caller passes None for unmaterialised gradients."""
+    H, W = _hw(imageBuffer, (dL_dout_color, dL_dout_semantic, dL_dout_depth, dL_dout_median_depth,
+                             dL_dout_final_opacity), image_height, image_width)
+    return _backward(background, means3D, radii, colors, semantics, scales, rotations, scale_modifier, cov3D_precomp,
+                     viewmatrix, projmatrix, tan_fovx, tan_fovy, dL_dout_color, dL_dout_semantic, dL_dout_depth,
+                     dL_dout_median_depth, dL_dout_final_opacity, sh, degree, campos, geomBuffer, R, binningBuffer,
+                     imageBuffer, debug, H, W, True)
+
+
+def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rotations, scale_modifier, cov3D_precomp,
+                                 viewmatrix, projmatrix, tan_fovx, tan_fovy, dL_dout_color, dL_dout_depth,
+                                 dL_dout_median_depth, dL_dout_final_opacity, sh, degree, campos, geomBuffer, R,
+                                 binningBuffer, imageBuffer, debug, image_height=None, image_width=None):
+    """reference: RasterizeGaussiansBackwardCUDA, rasterize_points.cu:119-215.
+    Returns (dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations)."""
+    H, W = _hw(imageBuffer, (dL_dout_color, dL_dout_depth, dL_dout_median_depth, dL_dout_final_opacity),
+               image_height, image_width)
+    r = _backward(background, means3D, radii, colors, None, scales, rotations, scale_modifier, cov3D_precomp,
+                  viewmatrix, projmatrix, tan_fovx, tan_fovy, dL_dout_color, None, dL_dout_depth,
+                  dL_dout_median_depth, dL_dout_final_opacity, sh, degree, campos, geomBuffer, R, binningBuffer,
+                  imageBuffer, debug, H, W, False)
+    return r[0], r[1], r[3], r[4], r[5], r[6], r[7], r[8]
+
+
+def mark_visible(means3D, viewmatrix, projmatrix):
+    """reference: markVisible, rasterize_points.cu:217-236."""
+    lib = _lib.load()
+    if not means3D.is_cuda:
+        raise RuntimeError("hier_slam_b200 rasterizer is CUDA-only: means3D must be a CUDA tensor")
+    P = means3D.size(0)
+    present = torch.zeros(P, dtype=torch.bool, device=means3D.device)
+    if P != 0:
+        with torch.cuda.device(means3D.device):
+            stream = ctypes.c_void_p(torch.cuda.current_stream(means3D.device).cuda_stream)
+            m = _f32c(means3D, "means3D", means3D.device)
+            v, pm = _small_contig(viewmatrix), _small_contig(projmatrix)
+            _lib.check(lib.hs_mark_visible(P, _ptr(m), _ptr(v), _ptr(pm), _ptr(present), stream), "hs_mark_visible")
+    return present
+
+
+# ---- test / debugging aid: typed views into the opaque state buffers --------------------------------------
+def state_views(P: int, H: int, W: int, R: int, geomBuffer, binningBuffer, imgBuffer):
+    lib = _lib.load()
+    tiles = ((W + 15) // 16) * ((H + 15) // 16)
+    N = H * W
+
+    def view(buf, off, n, dtype):
+        esz = torch.empty((), dtype=dtype).element_size()
+        return buf[off:off + n * esz].view(dtype)
+    out = {}
+    if P > 0:
+        off = (ctypes.c_size_t * 5)()
+        lib.hs_geom_state_layout(P, off)
+        out["depths"] = view(geomBuffer, off[0], P, torch.float32)
+        out["means2D"] = view(geomBuffer, off[1], 2 * P, torch.float32).view(P, 2)
+        out["conic_opacity"] = view(geomBuffer, off[2], 4 * P, torch.float32).view(P, 4)
+        out["tiles_touched"] = view(geomBuffer, off[3], P, torch.int32)
+        out["point_offsets"] = view(geomBuffer, off[4], P, torch.int32)
+    off = (ctypes.c_size_t * 3)()
+    lib.hs_image_state_layout(H, W, off)
+    out["final_T"] = view(imgBuffer, off[0], N, torch.float32)
+    out["n_contrib"] = view(imgBuffer, off[1], N, torch.int32)
+    out["ranges"] = view(imgBuffer, off[2], 2 * tiles, torch.int32).view(tiles, 2)
+    if R > 0:
+        off = (ctypes.c_size_t * 4)()
+        lib.hs_binning_state_layout(R, off)
+        out["point_list"] = view(binningBuffer, off[0], R, torch.int32)
+        out["point_list_unsorted"] = view(binningBuffer, off[1], R, torch.int32)
+        out["keys"] = view(binningBuffer, off[2], R, torch.int64)
+        out["keys_unsorted"] = view(binningBuffer, off[3], R, torch.int64)
+    return out

@@ -1,0 +1,243 @@
+// Binning: offsets scan, (tile | depth) key duplication, key sort, tile ranges, and the opaque state-buffer
+// layouts.  Reference behaviour: cuda_rasterizer/rasterizer_impl.cu:70-138 (duplicateWithKeys,
+// identifyTileRanges), :544-585 (scan, sort, memset) and :155-194 (state chunks).
+//
+// Parity contract: unsorted keys/values, sorted keys, point_list and ranges are bit-exact with the reference
+// (stable ascending sort on key bits [0, 32 + getHigherMsb(tiles)) keeps equal keys in Gaussian order).
+#include "hs_common.cuh"
+#include <cub/cub.cuh>
+#include <stdarg.h>
+#include <mutex>
+#include <string>
+
+namespace hs {
+
+static thread_local std::string g_last_error;
+void count_lib_call();
+void set_error(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+}
+const char* last_error() { return g_last_error.c_str(); }
+
+// ---- profiling / launch accounting ---------------------------------------------------------------------
+static bool g_prof_on = false;
+static cudaEvent_t g_ev[2 * ST_COUNT];
+static bool g_ev_used[ST_COUNT];
+static bool g_ev_created = false;
+static long long g_launches = 0;      // kernels written in this library
+static long long g_lib_calls = 0;     // CUB device-wide primitives (scan, sort)
+void count_launch(int n) { g_launches += n; }
+void count_lib_call() { g_lib_calls += 1; }
+long long launches() { return g_launches; }
+long long lib_calls() { return g_lib_calls; }
+void prof_enable(bool on) {
+    if (on && !g_ev_created) {
+        for (int i = 0; i < 2 * ST_COUNT; i++) cudaEventCreate(&g_ev[i]);
+        g_ev_created = true;
+    }
+    for (int i = 0; i < ST_COUNT; i++) g_ev_used[i] = false;
+    g_prof_on = on;
+}
+void prof_begin(int stage, cudaStream_t stream) {
+    if (g_prof_on) cudaEventRecord(g_ev[2 * stage], stream);
+}
+void prof_end(int stage, cudaStream_t stream) {
+    if (g_prof_on) {
+        cudaEventRecord(g_ev[2 * stage + 1], stream);
+        g_ev_used[stage] = true;
+    }
+}
+int prof_read(float* ms) {
+    for (int i = 0; i < ST_COUNT; i++) {
+        ms[i] = -1.f;
+        if (g_ev_created && g_ev_used[i]) {
+            if (cudaEventSynchronize(g_ev[2 * i + 1]) != cudaSuccess) return 2;
+            if (cudaEventElapsedTime(&ms[i], g_ev[2 * i], g_ev[2 * i + 1]) != cudaSuccess) return 2;
+        }
+    }
+    return 0;
+}
+
+// ---- state layouts ------------------------------------------------------------------------------------
+template <typename T>
+static void carve(char*& p, T*& ptr, size_t count) {
+    size_t off = align_up(reinterpret_cast<size_t>(p));
+    ptr = reinterpret_cast<T*>(off);
+    p = reinterpret_cast<char*>(ptr + count);
+}
+
+int geom_view(char* base, size_t P, GeomView* v) {
+    char* p = base;
+    carve(p, v->depths, P);
+    carve(p, v->means2D, P);
+    carve(p, v->conic_opacity, P);
+    carve(p, v->tiles_touched, P);
+    carve(p, v->point_offsets, P);
+    v->scan_temp_bytes = 0;
+    if (P > 0) {
+        HS_CUDA_OK(cub::DeviceScan::InclusiveSum(nullptr, v->scan_temp_bytes, v->tiles_touched, v->point_offsets, (int)P));
+    }
+    carve(p, v->scan_temp, v->scan_temp_bytes);
+    v->total_bytes = (size_t)(p - base) + HS_ALIGN;
+    return 0;
+}
+
+int image_view(char* base, size_t N, size_t tiles, ImageView* v) {
+    char* p = base;
+    carve(p, v->final_T, N);
+    carve(p, v->n_contrib, N);
+    carve(p, v->ranges, tiles);
+    v->total_bytes = (size_t)(p - base) + HS_ALIGN;
+    return 0;
+}
+
+int binning_view(char* base, size_t R, BinningView* v) {
+    char* p = base;
+    carve(p, v->point_list, R);
+    carve(p, v->point_list_unsorted, R);
+    carve(p, v->keys, R);
+    carve(p, v->keys_unsorted, R);
+    v->sort_temp_bytes = 0;
+    if (R > 0) {
+        HS_CUDA_OK(cub::DeviceRadixSort::SortPairs(nullptr, v->sort_temp_bytes, v->keys_unsorted, v->keys,
+                                                   v->point_list_unsorted, v->point_list, (int)R));
+    }
+    carve(p, v->sort_temp, v->sort_temp_bytes);
+    v->total_bytes = (size_t)(p - base) + HS_ALIGN;
+    return 0;
+}
+
+int launch_scan(int P, const GeomView& g, cudaStream_t stream, bool debug) {
+    if (P <= 0) return 0;
+    size_t tb = g.scan_temp_bytes;
+    prof_begin(ST_SCAN, stream);
+    HS_CUDA_OK(cub::DeviceScan::InclusiveSum(g.scan_temp, tb, g.tiles_touched, g.point_offsets, P, stream));
+    prof_end(ST_SCAN, stream);
+    count_lib_call();
+    HS_CUDA_OK(cudaGetLastError());
+    if (debug) HS_CUDA_OK(cudaStreamSynchronize(stream));
+    return 0;
+}
+
+// rasterizer_impl.cu:35-50
+static uint32_t higher_msb(uint32_t n) {
+    uint32_t msb = sizeof(n) * 4;
+    uint32_t step = msb;
+    while (step > 1) {
+        step /= 2;
+        if (n >> msb) msb += step;
+        else msb -= step;
+    }
+    if (n >> msb) msb++;
+    return msb;
+}
+
+__device__ __forceinline__ void get_rect_dev(const float2 p, int max_radius, uint2& rect_min, uint2& rect_max,
+                                             unsigned gx, unsigned gy) {  // auxiliary.h:46-56
+    rect_min = {min(gx, (unsigned)max((int)0, (int)((p.x - max_radius) / HS_TILE_X))),
+                min(gy, (unsigned)max((int)0, (int)((p.y - max_radius) / HS_TILE_Y)))};
+    rect_max = {min(gx, (unsigned)max((int)0, (int)((p.x + max_radius + HS_TILE_X - 1) / HS_TILE_X))),
+                min(gy, (unsigned)max((int)0, (int)((p.y + max_radius + HS_TILE_Y - 1) / HS_TILE_Y)))};
+}
+
+// One thread per Gaussian like the reference, but a Gaussian that covers many tiles is expanded by its
+// whole warp (coalesced 8-byte / 4-byte stores) instead of by one serial thread.  Output order is identical:
+// instance n of Gaussian idx sits at offsets[idx-1] + n, y-major / x-minor inside the rect.
+__global__ void __launch_bounds__(256) duplicate_kernel(int P, const float2* __restrict__ points_xy,
+                                                        const float* __restrict__ depths,
+                                                        const uint32_t* __restrict__ offsets,
+                                                        uint64_t* __restrict__ keys_unsorted,
+                                                        uint32_t* __restrict__ values_unsorted,
+                                                        const int* __restrict__ radii, unsigned gx, unsigned gy) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    uint32_t off = 0, w = 0, count = 0, dbits = 0;
+    uint2 rmin = {0, 0}, rmax = {0, 0};
+    if (idx < P && radii[idx] > 0) {
+        off = (idx == 0) ? 0 : offsets[idx - 1];
+        get_rect_dev(points_xy[idx], radii[idx], rmin, rmax, gx, gy);
+        w = rmax.x - rmin.x;
+        count = w * (rmax.y - rmin.y);
+        dbits = __float_as_uint(depths[idx]);
+    }
+    const uint32_t kSmall = 4;
+    if (count > 0 && count <= kSmall) {
+        for (uint32_t n = 0; n < count; n++) {
+            uint32_t y = rmin.y + n / w, x = rmin.x + n % w;
+            uint64_t key = y * gx + x;
+            key <<= 32;
+            key |= dbits;
+            keys_unsorted[off + n] = key;
+            values_unsorted[off + n] = idx;
+        }
+    }
+    unsigned big = __ballot_sync(0xffffffffu, count > kSmall);
+    while (big) {
+        const int src = __ffs(big) - 1;
+        big &= big - 1;
+        const uint32_t s_off = __shfl_sync(0xffffffffu, off, src);
+        const uint32_t s_w = __shfl_sync(0xffffffffu, w, src);
+        const uint32_t s_count = __shfl_sync(0xffffffffu, count, src);
+        const uint32_t s_db = __shfl_sync(0xffffffffu, dbits, src);
+        const uint32_t s_x0 = __shfl_sync(0xffffffffu, rmin.x, src);
+        const uint32_t s_y0 = __shfl_sync(0xffffffffu, rmin.y, src);
+        const uint32_t s_idx = (blockIdx.x * blockDim.x + (threadIdx.x & ~31)) + src;
+        for (uint32_t n = lane; n < s_count; n += 32) {
+            uint32_t y = s_y0 + n / s_w, x = s_x0 + n % s_w;
+            uint64_t key = y * gx + x;
+            key <<= 32;
+            key |= s_db;
+            keys_unsorted[s_off + n] = key;
+            values_unsorted[s_off + n] = s_idx;
+        }
+    }
+}
+
+// rasterizer_impl.cu:116-138
+__global__ void tile_ranges_kernel(int L, const uint64_t* __restrict__ keys, uint2* __restrict__ ranges) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= L) return;
+    const uint32_t currtile = keys[idx] >> 32;
+    if (idx == 0) ranges[currtile].x = 0;
+    else {
+        const uint32_t prevtile = keys[idx - 1] >> 32;
+        if (currtile != prevtile) {
+            ranges[prevtile].y = idx;
+            ranges[currtile].x = idx;
+        }
+    }
+    if (idx == L - 1) ranges[currtile].y = L;
+}
+
+int launch_binning(int P, int R, const Camera& cam, const int* radii, const GeomView& g, const BinningView& b,
+                   const ImageView& img, cudaStream_t stream, bool debug) {
+    const int tiles = cam.grid_x * cam.grid_y;
+    HS_CUDA_OK(cudaMemsetAsync(img.ranges, 0, sizeof(uint2) * (size_t)tiles, stream));
+    if (P <= 0 || R <= 0) return 0;
+    prof_begin(ST_DUPLICATE, stream);
+    duplicate_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, g.means2D, g.depths, g.point_offsets, b.keys_unsorted,
+                                                         b.point_list_unsorted, radii, cam.grid_x, cam.grid_y);
+    prof_end(ST_DUPLICATE, stream);
+    HS_LAUNCH_OK(stream, debug);
+    const int bit = (int)higher_msb((uint32_t)tiles);
+    size_t tb = b.sort_temp_bytes;
+    prof_begin(ST_SORT, stream);
+    HS_CUDA_OK(cub::DeviceRadixSort::SortPairs(b.sort_temp, tb, b.keys_unsorted, b.keys, b.point_list_unsorted,
+                                               b.point_list, R, 0, 32 + bit, stream));
+    prof_end(ST_SORT, stream);
+    count_lib_call();
+    HS_CUDA_OK(cudaGetLastError());
+    if (debug) HS_CUDA_OK(cudaStreamSynchronize(stream));
+    prof_begin(ST_RANGES, stream);
+    tile_ranges_kernel<<<(R + 255) / 256, 256, 0, stream>>>(R, b.keys, img.ranges);
+    prof_end(ST_RANGES, stream);
+    HS_LAUNCH_OK(stream, debug);
+    return 0;
+}
+
+}  // namespace hs

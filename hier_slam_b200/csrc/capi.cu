@@ -1,0 +1,254 @@
+// extern "C" entry points of libhsraster (see include/hs_raster.h for the contract).
+#include "../../include/hs_raster.h"
+#include "hs_common.cuh"
+
+namespace hs {
+const char* last_error();
+void prof_enable(bool on);
+int prof_read(float* ms);
+long long launches();
+long long lib_calls();
+}
+
+using namespace hs;
+
+static int make_camera(const hs_camera* c, Camera* cam) {
+    if (c == nullptr) {
+        set_error("hs_camera is NULL");
+        return 1;
+    }
+    if (c->image_width <= 0 || c->image_height <= 0) {
+        set_error("invalid image size %dx%d", c->image_width, c->image_height);
+        return 1;
+    }
+    cam->W = c->image_width;
+    cam->H = c->image_height;
+    cam->tanfovx = c->tanfovx;
+    cam->tanfovy = c->tanfovy;
+    // reference: rasterizer_impl.cu:489-490
+    cam->focal_y = c->image_height / (2.0f * c->tanfovy);
+    cam->focal_x = c->image_width / (2.0f * c->tanfovx);
+    cam->scale_modifier = c->scale_modifier;
+    cam->view = c->viewmatrix;
+    cam->proj = c->projmatrix;
+    cam->grid_x = (c->image_width + HS_TILE_X - 1) / HS_TILE_X;
+    cam->grid_y = (c->image_height + HS_TILE_Y - 1) / HS_TILE_Y;
+    return 0;
+}
+
+static int* pinned_int() {
+    static thread_local int* p = nullptr;
+    if (p == nullptr) {
+        if (cudaHostAlloc((void**)&p, 64, cudaHostAllocDefault) != cudaSuccess) p = nullptr;
+    }
+    return p;
+}
+
+extern "C" {
+
+int hs_abi_version(void) { return HS_RASTER_ABI_VERSION; }
+const char* hs_last_error(void) { return hs::last_error(); }
+
+int hs_supports_semantic_channels(int S) { return S == 0 || S == 16 || S == 26 || S == 74 || S == 102; }
+
+size_t hs_geom_state_bytes(int P) {
+    GeomView v;
+    if (geom_view(nullptr, (size_t)(P > 0 ? P : 0), &v)) return 0;
+    return v.total_bytes;
+}
+size_t hs_image_state_bytes(int H, int W) {
+    ImageView v;
+    const size_t tiles = (size_t)((W + HS_TILE_X - 1) / HS_TILE_X) * ((H + HS_TILE_Y - 1) / HS_TILE_Y);
+    image_view(nullptr, (size_t)H * W, tiles, &v);
+    return v.total_bytes;
+}
+size_t hs_binning_state_bytes(int R) {
+    BinningView v;
+    if (binning_view(nullptr, (size_t)(R > 0 ? R : 0), &v)) return 0;
+    return v.total_bytes;
+}
+
+int hs_geom_state_layout(int P, size_t off[5]) {
+    GeomView v;
+    if (geom_view(nullptr, (size_t)P, &v)) return 2;
+    off[0] = (size_t)v.depths;
+    off[1] = (size_t)v.means2D;
+    off[2] = (size_t)v.conic_opacity;
+    off[3] = (size_t)v.tiles_touched;
+    off[4] = (size_t)v.point_offsets;
+    return 0;
+}
+int hs_image_state_layout(int H, int W, size_t off[3]) {
+    ImageView v;
+    const size_t tiles = (size_t)((W + HS_TILE_X - 1) / HS_TILE_X) * ((H + HS_TILE_Y - 1) / HS_TILE_Y);
+    image_view(nullptr, (size_t)H * W, tiles, &v);
+    off[0] = (size_t)v.final_T;
+    off[1] = (size_t)v.n_contrib;
+    off[2] = (size_t)v.ranges;
+    return 0;
+}
+int hs_binning_state_layout(int R, size_t off[4]) {
+    BinningView v;
+    if (binning_view(nullptr, (size_t)R, &v)) return 2;
+    off[0] = (size_t)v.point_list;
+    off[1] = (size_t)v.point_list_unsorted;
+    off[2] = (size_t)v.keys;
+    off[3] = (size_t)v.keys_unsorted;
+    return 0;
+}
+
+int hs_forward_geometry(const hs_camera* c, int P, const float* means3D, const float* opacities,
+                        const float* scales, const float* rotations, const float* cov3D_precomp, int* radii,
+                        void* geom_state, size_t geom_state_bytes, int* num_rendered, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    Camera cam;
+    if (make_camera(c, &cam)) return 1;
+    if (num_rendered == nullptr) {
+        set_error("num_rendered is NULL");
+        return 1;
+    }
+    *num_rendered = 0;
+    if (P <= 0) return 0;
+    if (means3D == nullptr || opacities == nullptr || radii == nullptr || geom_state == nullptr) {
+        set_error("hs_forward_geometry: NULL argument");
+        return 1;
+    }
+    if (cov3D_precomp == nullptr && (scales == nullptr || rotations == nullptr)) {
+        set_error("provide either scales+rotations or cov3D_precomp");
+        return 1;
+    }
+    if ((reinterpret_cast<uintptr_t>(geom_state) & (HS_ALIGN - 1)) != 0) {
+        set_error("geom_state must be %d-byte aligned", HS_ALIGN);
+        return 1;
+    }
+    GeomView g;
+    if (geom_view((char*)geom_state, (size_t)P, &g)) return 2;
+    if (g.total_bytes > geom_state_bytes + HS_ALIGN) {
+        set_error("geom_state too small: %zu < %zu", geom_state_bytes, g.total_bytes);
+        return 1;
+    }
+    const bool debug = c->debug != 0;
+    int rc = launch_preprocess(P, means3D, scales, rotations, opacities, cov3D_precomp, cam, radii, g, stream, debug);
+    if (rc) return rc;
+    rc = launch_scan(P, g, stream, debug);
+    if (rc) return rc;
+    int* host = pinned_int();
+    if (host == nullptr) {
+        set_error("cudaHostAlloc failed");
+        return 2;
+    }
+    HS_CUDA_OK(cudaMemcpyAsync(host, g.point_offsets + (P - 1), sizeof(int), cudaMemcpyDeviceToHost, stream));
+    HS_CUDA_OK(cudaStreamSynchronize(stream));
+    *num_rendered = *host;
+    return 0;
+}
+
+int hs_forward_render(const hs_camera* c, int P, int S, int R, const float* colors, const float* semantics,
+                      const int* radii, void* geom_state, void* binning_state, size_t binning_state_bytes,
+                      void* image_state, size_t image_state_bytes, float* out_color, float* out_semantic,
+                      float* out_depth, float* out_median_depth, float* out_opacity, float* out_mask, int flags,
+                      void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    Camera cam;
+    if (make_camera(c, &cam)) return 1;
+    if (!hs_supports_semantic_channels(S)) {
+        set_error("semantic channel count S=%d is not instantiated (built: 0,16,26,74,102)", S);
+        return 3;
+    }
+    if (image_state == nullptr || out_color == nullptr || out_depth == nullptr || out_median_depth == nullptr ||
+        out_opacity == nullptr || (S > 0 && out_semantic == nullptr)) {
+        set_error("hs_forward_render: NULL output");
+        return 1;
+    }
+    const size_t N = (size_t)cam.W * cam.H;
+    const size_t tiles = (size_t)cam.grid_x * cam.grid_y;
+    ImageView img;
+    image_view((char*)image_state, N, tiles, &img);
+    if (img.total_bytes > image_state_bytes + HS_ALIGN) {
+        set_error("image_state too small");
+        return 1;
+    }
+    GeomView g;
+    BinningView b;
+    if (P > 0) {
+        if (geom_view((char*)geom_state, (size_t)P, &g)) return 2;
+    } else {
+        g = GeomView{};
+    }
+    if (R > 0) {
+        if (binning_state == nullptr) {
+            set_error("binning_state is NULL");
+            return 1;
+        }
+        if (binning_view((char*)binning_state, (size_t)R, &b)) return 2;
+        if (b.total_bytes > binning_state_bytes + HS_ALIGN) {
+            set_error("binning_state too small: %zu < %zu", binning_state_bytes, b.total_bytes);
+            return 1;
+        }
+        if (colors == nullptr || (S > 0 && semantics == nullptr)) {
+            set_error("colors / semantics must be provided (precomputed colours are the only supported colour path)");
+            return 1;
+        }
+    } else {
+        b = BinningView{};
+    }
+    const bool debug = c->debug != 0;
+    int rc = launch_binning(P, R, cam, radii, g, b, img, stream, debug);
+    if (rc) return rc;
+    return launch_blend_forward(S, cam, g, b, img, colors, semantics, out_color, out_semantic, out_depth,
+                                out_median_depth, out_opacity, out_mask, flags, stream, debug);
+}
+
+int hs_backward(const hs_camera* c, int P, int S, int R, const float* means3D, const int* radii,
+                const float* colors, const float* semantics, const float* scales, const float* rotations,
+                const float* cov3D_precomp, const void* geom_state, const void* binning_state,
+                const void* image_state, const float* dL_dout_color, const float* dL_dout_semantic,
+                const float* dL_dout_depth, const float* dL_dout_median_depth, const float* dL_dout_opacity,
+                float* dL_dmeans2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolors, float* dL_dsemantics,
+                float* dL_ddepths, float* dL_dmeans3D, float* dL_dcov3D, float* dL_dscales, float* dL_drotations,
+                int flags, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    Camera cam;
+    if (make_camera(c, &cam)) return 1;
+    if (P <= 0) return 0;
+    if (!hs_supports_semantic_channels(S)) {
+        set_error("semantic channel count S=%d is not instantiated (built: 0,16,26,74,102)", S);
+        return 3;
+    }
+    const size_t N = (size_t)cam.W * cam.H;
+    const size_t tiles = (size_t)cam.grid_x * cam.grid_y;
+    GeomView g;
+    ImageView img;
+    BinningView b = BinningView{};
+    if (geom_view((char*)geom_state, (size_t)P, &g)) return 2;
+    image_view((char*)image_state, N, tiles, &img);
+    const bool debug = c->debug != 0;
+    int rc = 0;
+    if (R > 0) {
+        if (binning_view((char*)binning_state, (size_t)R, &b)) return 2;
+        int kflags = 0;
+        if (flags & HS_SEM_ALPHA_EXACT) kflags |= HS_FLAG_SEM_ALPHA_EXACT;
+        rc = launch_blend_backward(S, cam, g, b, img, c->bg, colors, semantics, dL_dout_color, dL_dout_semantic,
+                                   dL_dout_depth, dL_dout_median_depth, dL_dout_opacity, dL_dmeans2D, dL_dconic,
+                                   dL_dopacity, dL_dcolors, dL_dsemantics, dL_ddepths, kflags, stream, debug);
+        if (rc) return rc;
+    }
+    return launch_geom_backward(P, means3D, radii, scales, rotations, cov3D_precomp, cam, dL_dmeans2D, dL_dconic,
+                                dL_ddepths, dL_dmeans3D, dL_dcov3D, cov3D_precomp ? nullptr : dL_dscales,
+                                cov3D_precomp ? nullptr : dL_drotations, stream, debug);
+}
+
+int hs_profile_enable(int on) {
+    prof_enable(on != 0);
+    return 0;
+}
+int hs_profile_read(float ms[8]) { return prof_read(ms); }
+long long hs_kernel_launch_count(void) { return launches(); }
+long long hs_library_call_count(void) { return lib_calls(); }
+
+int hs_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                    unsigned char* present, void* stream_) {
+    return launch_mark_visible(P, means3D, viewmatrix, projmatrix, (bool*)present, (cudaStream_t)stream_, false);
+}
+
+}  // extern "C"

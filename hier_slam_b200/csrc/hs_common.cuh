@@ -1,0 +1,118 @@
+// Internal header of libhsraster (sm_100a).  Not part of the public C ABI (see include/hs_raster.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <stdio.h>
+
+#define HS_TILE_X 16          // reference: cuda_rasterizer/config.h:16  (BLOCK_X)
+#define HS_TILE_Y 16          // reference: cuda_rasterizer/config.h:17  (BLOCK_Y)
+#define HS_TILE_PIX 256
+#define HS_ALIGN 256          // every array inside an opaque state buffer is 256-B aligned
+
+namespace hs {
+
+void set_error(const char* fmt, ...);
+
+// ---- optional per-stage timing with CUDA events on the launching stream (hs_profile_enable / hs_profile_read)
+enum Stage : int {
+    ST_PREPROCESS = 0, ST_SCAN, ST_DUPLICATE, ST_SORT, ST_RANGES, ST_BLEND_FWD, ST_BLEND_BWD, ST_GEOM_BWD, ST_COUNT
+};
+void prof_begin(int stage, cudaStream_t stream);
+void prof_end(int stage, cudaStream_t stream);
+void count_launch(int n = 1);
+
+#define HS_CUDA_OK(expr)                                                                     \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess) {                                                             \
+            hs::set_error("%s failed at %s:%d: %s", #expr, __FILE__, __LINE__,               \
+                          cudaGetErrorString(_e));                                           \
+            return 2;                                                                        \
+        }                                                                                    \
+    } while (0)
+
+// After every launch: always check the launch itself; with debug additionally synchronise the
+// stream and surface execution errors (mirrors CHECK_CUDA, cuda_rasterizer/auxiliary.h:166-173).
+#define HS_LAUNCH_OK(stream, debug)                                                          \
+    do {                                                                                     \
+        hs::count_launch();                                                                  \
+        HS_CUDA_OK(cudaGetLastError());                                                      \
+        if (debug) HS_CUDA_OK(cudaStreamSynchronize(stream));                                \
+    } while (0)
+
+static inline size_t align_up(size_t x) { return (x + HS_ALIGN - 1) & ~(size_t)(HS_ALIGN - 1); }
+
+// ---- opaque state buffers (our private layout; the three buffers mirror geomBuffer / binningBuffer /
+//      imgBuffer of RAST/rasterize_points.cu:285-291 in role, not in layout) ------------------------------
+struct GeomView {
+    float* depths;            // f32[P]   view-space z
+    float2* means2D;          // float2[P] pixel centre
+    float4* conic_opacity;    // float4[P] (conic.x, conic.y, conic.z, opacity)
+    uint32_t* tiles_touched;  // u32[P]
+    uint32_t* point_offsets;  // u32[P]   inclusive scan of tiles_touched
+    char* scan_temp;          // CUB scan temp
+    size_t scan_temp_bytes;
+    size_t total_bytes;
+};
+struct ImageView {
+    float* final_T;           // f32[N]
+    uint32_t* n_contrib;      // u32[N]
+    uint2* ranges;            // uint2[tiles]
+    size_t total_bytes;
+};
+struct BinningView {
+    uint32_t* point_list;          // u32[R] sorted Gaussian ids
+    uint32_t* point_list_unsorted; // u32[R]
+    uint64_t* keys;                // u64[R] sorted (tile << 32 | depth bits)
+    uint64_t* keys_unsorted;       // u64[R]
+    char* sort_temp;
+    size_t sort_temp_bytes;
+    size_t total_bytes;
+};
+
+int geom_view(char* base, size_t P, GeomView* v);
+int image_view(char* base, size_t N, size_t tiles, ImageView* v);
+int binning_view(char* base, size_t R, BinningView* v);
+
+// ---- kernels' host launchers (defined in the .cu files) ----------------------------------------------
+struct Camera {
+    int W, H;
+    float tanfovx, tanfovy, focal_x, focal_y, scale_modifier;
+    const float* view;   // device, 16 floats, m[4*c+r]
+    const float* proj;   // device, 16 floats
+    int grid_x, grid_y;
+};
+
+int launch_preprocess(int P, const float* means3D, const float* scales, const float* rotations,
+                      const float* opacities, const float* cov3D_precomp, const Camera& cam, int* radii,
+                      const GeomView& g, cudaStream_t stream, bool debug);
+int launch_scan(int P, const GeomView& g, cudaStream_t stream, bool debug);
+int launch_binning(int P, int R, const Camera& cam, const int* radii, const GeomView& g, const BinningView& b,
+                   const ImageView& img, cudaStream_t stream, bool debug);
+int launch_blend_forward(int S, const Camera& cam, const GeomView& g, const BinningView& b, const ImageView& img,
+                         const float* colors, const float* semantics, float* out_color, float* out_semantic,
+                         float* out_depth, float* out_median, float* out_opacity, float* out_mask, int flags,
+                         cudaStream_t stream, bool debug);
+int launch_blend_backward(int S, const Camera& cam, const GeomView& g, const BinningView& b, const ImageView& img,
+                          const float* bg, const float* colors, const float* semantics, const float* dL_color,
+                          const float* dL_sem, const float* dL_depth, const float* dL_median,
+                          const float* dL_opacity, float* dL_dmean2D, float* dL_dconic, float* dL_dopacity,
+                          float* dL_dcolors, float* dL_dsemantics, float* dL_ddepths, int flags,
+                          cudaStream_t stream, bool debug);
+int launch_geom_backward(int P, const float* means3D, const int* radii, const float* scales,
+                         const float* rotations, const float* cov3D_precomp, const Camera& cam,
+                         const float* dL_dmean2D, const float* dL_dconic, const float* dL_ddepths,
+                         float* dL_dmeans3D, float* dL_dcov3D, float* dL_dscales, float* dL_drots,
+                         cudaStream_t stream, bool debug);
+int launch_mark_visible(int P, const float* means3D, const float* view, const float* proj, bool* present,
+                        cudaStream_t stream, bool debug);
+
+// flags shared by the blend kernels
+enum : int {
+    HS_FLAG_SEM_ALPHA_EXACT = 1,   // semantic channels contribute to dL/dalpha (reference quirk Q1 off)
+    HS_FLAG_NO_CULL = 2,           // disable the conservative per-warp footprint test
+    HS_FLAG_BWD_SHUFFLE = 4,       // backward: plain warp-shuffle reduction instead of the default path
+};
+
+}  // namespace hs

@@ -1,0 +1,411 @@
+// Per-Gaussian kernels: forward preprocess (EWA projection, near cull, tile-overlap count), the fused
+// per-Gaussian backward, and markVisible.
+//
+// Parity contract: radii, tiles_touched, depths, means2D and conic_opacity must be BIT-EXACT with the
+// reference build (they define the sort keys and tile lists).  The arithmetic below therefore keeps the
+// reference's expression shapes (reference: cuda_rasterizer/forward.cu:74-256, auxiliary.h:41-164 and the
+// GLM 0.9.9.9 mat3 operators it instantiates) so that nvcc's FMA contraction produces the same sequence
+// of roundings; no fast-math anywhere.  What is new is the data movement: [P,3] inputs are staged through
+// shared memory with 128-bit coalesced loads, the two 4x4 matrices are read once per block, and the
+// cov3D array is never written (the backward recomputes it from scale/rotation).
+#include "hs_common.cuh"
+
+namespace hs {
+
+// Column-major 3x3 (m[c][r]) with exactly the operator formulas of glm/detail/type_mat3x3.inl:486-519.
+struct M3 {
+    float m[3][3];
+};
+__device__ __forceinline__ M3 m3_mul(const M3& a, const M3& b) {
+    M3 r;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        r.m[c][0] = a.m[0][0] * b.m[c][0] + a.m[1][0] * b.m[c][1] + a.m[2][0] * b.m[c][2];
+        r.m[c][1] = a.m[0][1] * b.m[c][0] + a.m[1][1] * b.m[c][1] + a.m[2][1] * b.m[c][2];
+        r.m[c][2] = a.m[0][2] * b.m[c][0] + a.m[1][2] * b.m[c][1] + a.m[2][2] * b.m[c][2];
+    }
+    return r;
+}
+__device__ __forceinline__ M3 m3_transpose(const M3& a) {
+    M3 r;
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+#pragma unroll
+        for (int q = 0; q < 3; q++) r.m[c][q] = a.m[q][c];
+    return r;
+}
+// glm::mat3(x0..x8): column-major constructor
+__device__ __forceinline__ M3 m3_make(float x0, float x1, float x2, float x3, float x4, float x5, float x6,
+                                       float x7, float x8) {
+    M3 r;
+    r.m[0][0] = x0; r.m[0][1] = x1; r.m[0][2] = x2;
+    r.m[1][0] = x3; r.m[1][1] = x4; r.m[1][2] = x5;
+    r.m[2][0] = x6; r.m[2][1] = x7; r.m[2][2] = x8;
+    return r;
+}
+
+__device__ __forceinline__ float3 xform4x3(const float3& p, const float* m) {  // auxiliary.h:58-66
+    float3 t = {m[0] * p.x + m[4] * p.y + m[8] * p.z + m[12], m[1] * p.x + m[5] * p.y + m[9] * p.z + m[13],
+                m[2] * p.x + m[6] * p.y + m[10] * p.z + m[14]};
+    return t;
+}
+__device__ __forceinline__ float4 xform4x4(const float3& p, const float* m) {  // auxiliary.h:68-77
+    float4 t = {m[0] * p.x + m[4] * p.y + m[8] * p.z + m[12], m[1] * p.x + m[5] * p.y + m[9] * p.z + m[13],
+                m[2] * p.x + m[6] * p.y + m[10] * p.z + m[14], m[3] * p.x + m[7] * p.y + m[11] * p.z + m[15]};
+    return t;
+}
+
+// forward.cu:118-152 — Sigma = (S R)^T (S R); the quaternion is used as given.
+__device__ __forceinline__ void cov3d_from_scale_rot(const float3 scale, float mod, const float4 rot, float* cov3D) {
+    M3 S = m3_make(1.0f, 0.0f, 0.0f, 0.0f, 1.0f, 0.0f, 0.0f, 0.0f, 1.0f);
+    S.m[0][0] = mod * scale.x;
+    S.m[1][1] = mod * scale.y;
+    S.m[2][2] = mod * scale.z;
+    float r = rot.x, x = rot.y, y = rot.z, z = rot.w;
+    M3 R = m3_make(1.f - 2.f * (y * y + z * z), 2.f * (x * y - r * z), 2.f * (x * z + r * y),
+                   2.f * (x * y + r * z), 1.f - 2.f * (x * x + z * z), 2.f * (y * z - r * x),
+                   2.f * (x * z - r * y), 2.f * (y * z + r * x), 1.f - 2.f * (x * x + y * y));
+    M3 M = m3_mul(S, R);
+    M3 Sigma = m3_mul(m3_transpose(M), M);
+    cov3D[0] = Sigma.m[0][0];
+    cov3D[1] = Sigma.m[0][1];
+    cov3D[2] = Sigma.m[0][2];
+    cov3D[3] = Sigma.m[1][1];
+    cov3D[4] = Sigma.m[1][2];
+    cov3D[5] = Sigma.m[2][2];
+}
+
+// forward.cu:74-113
+__device__ __forceinline__ float3 cov2d_forward(const float3& mean, float focal_x, float focal_y, float tan_fovx,
+                                                float tan_fovy, const float* cov3D, const float* viewmatrix) {
+    float3 t = xform4x3(mean, viewmatrix);
+    const float limx = 1.3f * tan_fovx;
+    const float limy = 1.3f * tan_fovy;
+    const float txtz = t.x / t.z;
+    const float tytz = t.y / t.z;
+    t.x = min(limx, max(-limx, txtz)) * t.z;
+    t.y = min(limy, max(-limy, tytz)) * t.z;
+    M3 J = m3_make(focal_x / t.z, 0.0f, -(focal_x * t.x) / (t.z * t.z), 0.0f, focal_y / t.z,
+                   -(focal_y * t.y) / (t.z * t.z), 0, 0, 0);
+    M3 W = m3_make(viewmatrix[0], viewmatrix[4], viewmatrix[8], viewmatrix[1], viewmatrix[5], viewmatrix[9],
+                   viewmatrix[2], viewmatrix[6], viewmatrix[10]);
+    M3 T = m3_mul(W, J);
+    M3 Vrk = m3_make(cov3D[0], cov3D[1], cov3D[2], cov3D[1], cov3D[3], cov3D[4], cov3D[2], cov3D[4], cov3D[5]);
+    M3 cov = m3_mul(m3_mul(m3_transpose(T), m3_transpose(Vrk)), T);
+    cov.m[0][0] += 0.3f;
+    cov.m[1][1] += 0.3f;
+    return {float(cov.m[0][0]), float(cov.m[0][1]), float(cov.m[1][1])};
+}
+
+__device__ __forceinline__ float ndc2pix(float v, int S) {  // auxiliary.h:41-44 (FP64 on purpose)
+    return ((v + 1.0) * S - 1.0) * 0.5;
+}
+
+__device__ __forceinline__ void get_rect(const float2 p, int max_radius, uint2& rect_min, uint2& rect_max,
+                                         unsigned gx, unsigned gy) {  // auxiliary.h:46-56
+    rect_min = {min(gx, (unsigned)max((int)0, (int)((p.x - max_radius) / HS_TILE_X))),
+                min(gy, (unsigned)max((int)0, (int)((p.y - max_radius) / HS_TILE_Y)))};
+    rect_max = {min(gx, (unsigned)max((int)0, (int)((p.x + max_radius + HS_TILE_X - 1) / HS_TILE_X))),
+                min(gy, (unsigned)max((int)0, (int)((p.y + max_radius + HS_TILE_Y - 1) / HS_TILE_Y)))};
+}
+
+// Stage `n3` consecutive floats (a [n,3] slab) into shared memory with 128-bit loads when aligned.
+__device__ __forceinline__ void stage_slab(float* dst, const float* __restrict__ src, int n3) {
+    if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+        const int n4 = n3 >> 2;
+        for (int i = threadIdx.x; i < n4; i += blockDim.x)
+            reinterpret_cast<float4*>(dst)[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
+        for (int i = (n4 << 2) + threadIdx.x; i < n3; i += blockDim.x) dst[i] = __ldg(src + i);
+    } else {
+        for (int i = threadIdx.x; i < n3; i += blockDim.x) dst[i] = __ldg(src + i);
+    }
+}
+
+__global__ void __launch_bounds__(256) preprocess_kernel(int P, const float* __restrict__ means3D,
+                                                         const float* __restrict__ scales,
+                                                         const float4* __restrict__ rotations,
+                                                         const float* __restrict__ opacities,
+                                                         const float* __restrict__ cov3D_precomp, Camera cam,
+                                                         int* __restrict__ radii, float* __restrict__ depths,
+                                                         float2* __restrict__ means2D,
+                                                         float4* __restrict__ conic_opacity,
+                                                         uint32_t* __restrict__ tiles_touched) {
+    __shared__ __align__(16) float s_means[256 * 3];
+    __shared__ __align__(16) float s_scales[256 * 3];
+    __shared__ float s_view[16];
+    __shared__ float s_proj[16];
+    const int base = blockIdx.x * 256;
+    const int n = min(256, P - base);
+    stage_slab(s_means, means3D + (size_t)base * 3, n * 3);
+    if (cov3D_precomp == nullptr) stage_slab(s_scales, scales + (size_t)base * 3, n * 3);
+    if (threadIdx.x < 16) s_view[threadIdx.x] = __ldg(cam.view + threadIdx.x);
+    else if (threadIdx.x < 32) s_proj[threadIdx.x - 16] = __ldg(cam.proj + threadIdx.x - 16);
+    __syncthreads();
+    const int idx = base + threadIdx.x;
+    if (idx >= P) return;
+
+    int my_radii = 0;
+    uint32_t my_tiles = 0;
+    float my_depth = 0.f;
+    float2 my_xy = {0.f, 0.f};
+    float4 my_co = {0.f, 0.f, 0.f, 0.f};
+    do {
+        const float3 p_orig = {s_means[3 * threadIdx.x], s_means[3 * threadIdx.x + 1], s_means[3 * threadIdx.x + 2]};
+        // in_frustum (auxiliary.h:139-164): only the near-plane test is live
+        float4 p_hom = xform4x4(p_orig, s_proj);
+        float p_w = 1.0f / (p_hom.w + 0.0000001f);
+        float3 p_proj = {p_hom.x * p_w, p_hom.y * p_w, p_hom.z * p_w};
+        float3 p_view = xform4x3(p_orig, s_view);
+        if (p_view.z <= 0.2f) break;
+
+        float cov3D[6];
+        if (cov3D_precomp != nullptr) {
+#pragma unroll
+            for (int k = 0; k < 6; k++) cov3D[k] = __ldg(cov3D_precomp + (size_t)idx * 6 + k);
+        } else {
+            const float3 sc = {s_scales[3 * threadIdx.x], s_scales[3 * threadIdx.x + 1], s_scales[3 * threadIdx.x + 2]};
+            cov3d_from_scale_rot(sc, cam.scale_modifier, __ldg(rotations + idx), cov3D);
+        }
+        float3 cov = cov2d_forward(p_orig, cam.focal_x, cam.focal_y, cam.tanfovx, cam.tanfovy, cov3D, s_view);
+
+        float det = (cov.x * cov.z - cov.y * cov.y);
+        if (det == 0.0f) break;
+        float det_inv = 1.f / det;
+        float3 conic = {cov.z * det_inv, -cov.y * det_inv, cov.x * det_inv};
+
+        float mid = 0.5f * (cov.x + cov.z);
+        float lambda1 = mid + sqrt(max(0.1f, mid * mid - det));
+        float lambda2 = mid - sqrt(max(0.1f, mid * mid - det));
+        float my_radius = ceil(3.f * sqrt(max(lambda1, lambda2)));
+        float2 point_image = {ndc2pix(p_proj.x, cam.W), ndc2pix(p_proj.y, cam.H)};
+        uint2 rect_min, rect_max;
+        get_rect(point_image, my_radius, rect_min, rect_max, cam.grid_x, cam.grid_y);
+        if ((rect_max.x - rect_min.x) * (rect_max.y - rect_min.y) == 0) break;
+
+        my_depth = p_view.z;
+        my_radii = my_radius;
+        my_xy = point_image;
+        my_co = {conic.x, conic.y, conic.z, __ldg(opacities + idx)};
+        my_tiles = (rect_max.y - rect_min.y) * (rect_max.x - rect_min.x);
+    } while (0);
+    // Unlike the reference (which leaves stale bytes for culled Gaussians) every field is written, so the
+    // state buffers never need a memset and can come from torch.empty.
+    radii[idx] = my_radii;
+    tiles_touched[idx] = my_tiles;
+    depths[idx] = my_depth;
+    means2D[idx] = my_xy;
+    conic_opacity[idx] = my_co;
+}
+
+int launch_preprocess(int P, const float* means3D, const float* scales, const float* rotations,
+                      const float* opacities, const float* cov3D_precomp, const Camera& cam, int* radii,
+                      const GeomView& g, cudaStream_t stream, bool debug) {
+    if (P <= 0) return 0;
+    prof_begin(ST_PREPROCESS, stream);
+    preprocess_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, means3D, scales, (const float4*)rotations, opacities,
+                                                          cov3D_precomp, cam, radii, g.depths, g.means2D,
+                                                          g.conic_opacity, g.tiles_touched);
+    prof_end(ST_PREPROCESS, stream);
+    HS_LAUNCH_OK(stream, debug);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// markVisible (reference: rasterizer_impl.cu:54-66,141-153)
+// ------------------------------------------------------------------------------------------------------
+__global__ void mark_visible_kernel(int P, const float* __restrict__ means3D, const float* __restrict__ view,
+                                    bool* __restrict__ present) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P) return;
+    float3 p = {means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]};
+    float3 pv = xform4x3(p, view);
+    present[idx] = !(pv.z <= 0.2f);
+}
+int launch_mark_visible(int P, const float* means3D, const float* view, const float* proj, bool* present,
+                        cudaStream_t stream, bool debug) {
+    (void)proj;
+    if (P <= 0) return 0;
+    mark_visible_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, means3D, view, present);
+    HS_LAUNCH_OK(stream, debug);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Per-Gaussian backward: computeCov2DCUDA + preprocessCUDA(bwd) + computeCov3D(bwd) fused into one pass
+// (reference: cuda_rasterizer/backward.cu:144-274, 278-341, 346-412).  Every output row is written
+// (zeros for culled Gaussians), so the output tensors need no memset.
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) geom_backward_kernel(
+    int P, const float* __restrict__ means3D, const int* __restrict__ radii, const float* __restrict__ scales,
+    const float4* __restrict__ rotations, const float* __restrict__ cov3D_precomp, Camera cam,
+    const float* __restrict__ dL_dmean2D, const float4* __restrict__ dL_dconic, const float* __restrict__ dL_ddepths,
+    float* __restrict__ dL_dmeans3D, float* __restrict__ dL_dcov3D, float* __restrict__ dL_dscales,
+    float4* __restrict__ dL_drots) {
+    __shared__ float s_view[16];
+    __shared__ float s_proj[16];
+    if (threadIdx.x < 16) s_view[threadIdx.x] = __ldg(cam.view + threadIdx.x);
+    else if (threadIdx.x < 32) s_proj[threadIdx.x - 16] = __ldg(cam.proj + threadIdx.x - 16);
+    __syncthreads();
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    if (idx >= P) return;
+    const bool has_scales = (cov3D_precomp == nullptr);
+    float3 g_mean = {0.f, 0.f, 0.f};
+    float g_cov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float3 g_scale = {0.f, 0.f, 0.f};
+    float4 g_rot = {0.f, 0.f, 0.f, 0.f};
+    if (radii[idx] > 0) {
+        const float3 mean = {means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]};
+        float cov3D[6];
+        float3 sc = {0.f, 0.f, 0.f};
+        float4 rot = {0.f, 0.f, 0.f, 0.f};
+        if (has_scales) {
+            sc = {scales[3 * idx], scales[3 * idx + 1], scales[3 * idx + 2]};
+            rot = __ldg(rotations + idx);
+            cov3d_from_scale_rot(sc, cam.scale_modifier, rot, cov3D);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 6; k++) cov3D[k] = __ldg(cov3D_precomp + (size_t)idx * 6 + k);
+        }
+        // ---- conic -> cov2D -> cov3D / mean (backward.cu:144-274)
+        const float4 dc4 = __ldg(dL_dconic + idx);
+        const float3 dL_dcon = {dc4.x, dc4.y, dc4.w};
+        const float h_x = cam.focal_x, h_y = cam.focal_y;
+        float3 t = xform4x3(mean, s_view);
+        const float limx = 1.3f * cam.tanfovx;
+        const float limy = 1.3f * cam.tanfovy;
+        const float txtz = t.x / t.z;
+        const float tytz = t.y / t.z;
+        t.x = min(limx, max(-limx, txtz)) * t.z;
+        t.y = min(limy, max(-limy, tytz)) * t.z;
+        const float x_grad_mul = txtz < -limx || txtz > limx ? 0 : 1;
+        const float y_grad_mul = tytz < -limy || tytz > limy ? 0 : 1;
+        M3 J = m3_make(h_x / t.z, 0.0f, -(h_x * t.x) / (t.z * t.z), 0.0f, h_y / t.z, -(h_y * t.y) / (t.z * t.z), 0, 0, 0);
+        M3 W = m3_make(s_view[0], s_view[4], s_view[8], s_view[1], s_view[5], s_view[9], s_view[2], s_view[6], s_view[10]);
+        M3 Vrk = m3_make(cov3D[0], cov3D[1], cov3D[2], cov3D[1], cov3D[3], cov3D[4], cov3D[2], cov3D[4], cov3D[5]);
+        M3 T = m3_mul(W, J);
+        M3 cov2D = m3_mul(m3_mul(m3_transpose(T), m3_transpose(Vrk)), T);
+        float a = cov2D.m[0][0] += 0.3f;
+        float b = cov2D.m[0][1];
+        float c = cov2D.m[1][1] += 0.3f;
+        float denom = a * c - b * b;
+        float dL_da = 0, dL_db = 0, dL_dc = 0;
+        float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
+        if (denom2inv != 0) {
+            dL_da = denom2inv * (-c * c * dL_dcon.x + 2 * b * c * dL_dcon.y + (denom - a * c) * dL_dcon.z);
+            dL_dc = denom2inv * (-a * a * dL_dcon.z + 2 * a * b * dL_dcon.y + (denom - a * c) * dL_dcon.x);
+            dL_db = denom2inv * 2 * (b * c * dL_dcon.x - (denom + 2 * b * b) * dL_dcon.y + a * b * dL_dcon.z);
+            g_cov[0] = (T.m[0][0] * T.m[0][0] * dL_da + T.m[0][0] * T.m[1][0] * dL_db + T.m[1][0] * T.m[1][0] * dL_dc);
+            g_cov[3] = (T.m[0][1] * T.m[0][1] * dL_da + T.m[0][1] * T.m[1][1] * dL_db + T.m[1][1] * T.m[1][1] * dL_dc);
+            g_cov[5] = (T.m[0][2] * T.m[0][2] * dL_da + T.m[0][2] * T.m[1][2] * dL_db + T.m[1][2] * T.m[1][2] * dL_dc);
+            g_cov[1] = 2 * T.m[0][0] * T.m[0][1] * dL_da + (T.m[0][0] * T.m[1][1] + T.m[0][1] * T.m[1][0]) * dL_db + 2 * T.m[1][0] * T.m[1][1] * dL_dc;
+            g_cov[2] = 2 * T.m[0][0] * T.m[0][2] * dL_da + (T.m[0][0] * T.m[1][2] + T.m[0][2] * T.m[1][0]) * dL_db + 2 * T.m[1][0] * T.m[1][2] * dL_dc;
+            g_cov[4] = 2 * T.m[0][2] * T.m[0][1] * dL_da + (T.m[0][1] * T.m[1][2] + T.m[0][2] * T.m[1][1]) * dL_db + 2 * T.m[1][1] * T.m[1][2] * dL_dc;
+        }
+        float dL_dT00 = 2 * (T.m[0][0] * Vrk.m[0][0] + T.m[0][1] * Vrk.m[0][1] + T.m[0][2] * Vrk.m[0][2]) * dL_da +
+                        (T.m[1][0] * Vrk.m[0][0] + T.m[1][1] * Vrk.m[0][1] + T.m[1][2] * Vrk.m[0][2]) * dL_db;
+        float dL_dT01 = 2 * (T.m[0][0] * Vrk.m[1][0] + T.m[0][1] * Vrk.m[1][1] + T.m[0][2] * Vrk.m[1][2]) * dL_da +
+                        (T.m[1][0] * Vrk.m[1][0] + T.m[1][1] * Vrk.m[1][1] + T.m[1][2] * Vrk.m[1][2]) * dL_db;
+        float dL_dT02 = 2 * (T.m[0][0] * Vrk.m[2][0] + T.m[0][1] * Vrk.m[2][1] + T.m[0][2] * Vrk.m[2][2]) * dL_da +
+                        (T.m[1][0] * Vrk.m[2][0] + T.m[1][1] * Vrk.m[2][1] + T.m[1][2] * Vrk.m[2][2]) * dL_db;
+        float dL_dT10 = 2 * (T.m[1][0] * Vrk.m[0][0] + T.m[1][1] * Vrk.m[0][1] + T.m[1][2] * Vrk.m[0][2]) * dL_dc +
+                        (T.m[0][0] * Vrk.m[0][0] + T.m[0][1] * Vrk.m[0][1] + T.m[0][2] * Vrk.m[0][2]) * dL_db;
+        float dL_dT11 = 2 * (T.m[1][0] * Vrk.m[1][0] + T.m[1][1] * Vrk.m[1][1] + T.m[1][2] * Vrk.m[1][2]) * dL_dc +
+                        (T.m[0][0] * Vrk.m[1][0] + T.m[0][1] * Vrk.m[1][1] + T.m[0][2] * Vrk.m[1][2]) * dL_db;
+        float dL_dT12 = 2 * (T.m[1][0] * Vrk.m[2][0] + T.m[1][1] * Vrk.m[2][1] + T.m[1][2] * Vrk.m[2][2]) * dL_dc +
+                        (T.m[0][0] * Vrk.m[2][0] + T.m[0][1] * Vrk.m[2][1] + T.m[0][2] * Vrk.m[2][2]) * dL_db;
+        float dL_dJ00 = W.m[0][0] * dL_dT00 + W.m[0][1] * dL_dT01 + W.m[0][2] * dL_dT02;
+        float dL_dJ02 = W.m[2][0] * dL_dT00 + W.m[2][1] * dL_dT01 + W.m[2][2] * dL_dT02;
+        float dL_dJ11 = W.m[1][0] * dL_dT10 + W.m[1][1] * dL_dT11 + W.m[1][2] * dL_dT12;
+        float dL_dJ12 = W.m[2][0] * dL_dT10 + W.m[2][1] * dL_dT11 + W.m[2][2] * dL_dT12;
+        float tz = 1.f / t.z;
+        float tz2 = tz * tz;
+        float tz3 = tz2 * tz;
+        float dL_dtx = x_grad_mul * -h_x * tz2 * dL_dJ02;
+        float dL_dty = y_grad_mul * -h_y * tz2 * dL_dJ12;
+        float dL_dtz = -h_x * tz2 * dL_dJ00 - h_y * tz2 * dL_dJ11 + (2 * h_x * t.x) * tz3 * dL_dJ02 + (2 * h_y * t.y) * tz3 * dL_dJ12;
+        // transformVec4x3Transpose (auxiliary.h:89-97)
+        g_mean = {s_view[0] * dL_dtx + s_view[1] * dL_dty + s_view[2] * dL_dtz,
+                  s_view[4] * dL_dtx + s_view[5] * dL_dty + s_view[6] * dL_dtz,
+                  s_view[8] * dL_dtx + s_view[9] * dL_dty + s_view[10] * dL_dtz};
+
+        // ---- mean2D path through the projection (backward.cu:368-389)
+        const float* proj = s_proj;
+        const float3 m = mean;
+        float4 m_hom = xform4x4(m, proj);
+        float m_w = 1.0f / (m_hom.w + 0.0000001f);
+        const float g2x = dL_dmean2D[3 * idx], g2y = dL_dmean2D[3 * idx + 1];
+        float mul1 = (proj[0] * m.x + proj[4] * m.y + proj[8] * m.z + proj[12]) * m_w * m_w;
+        float mul2 = (proj[1] * m.x + proj[5] * m.y + proj[9] * m.z + proj[13]) * m_w * m_w;
+        g_mean.x += (proj[0] * m_w - proj[3] * mul1) * g2x + (proj[1] * m_w - proj[3] * mul2) * g2y;
+        g_mean.y += (proj[4] * m_w - proj[7] * mul1) * g2x + (proj[5] * m_w - proj[7] * mul2) * g2y;
+        g_mean.z += (proj[8] * m_w - proj[11] * mul1) * g2x + (proj[9] * m_w - proj[11] * mul2) * g2y;
+        // ---- depth path through the view matrix (backward.cu:391-406)
+        const float* view = s_view;
+        const float gd = dL_ddepths[idx];
+        float mul3 = view[2] * m.x + view[6] * m.y + view[10] * m.z + view[14];
+        g_mean.x += (view[2] - view[3] * mul3) * gd;
+        g_mean.y += (view[6] - view[7] * mul3) * gd;
+        g_mean.z += (view[10] - view[11] * mul3) * gd;
+
+        // ---- cov3D -> scale / rotation (backward.cu:278-341)
+        if (has_scales) {
+            float r = rot.x, x = rot.y, y = rot.z, z = rot.w;
+            M3 R = m3_make(1.f - 2.f * (y * y + z * z), 2.f * (x * y - r * z), 2.f * (x * z + r * y),
+                           2.f * (x * y + r * z), 1.f - 2.f * (x * x + z * z), 2.f * (y * z - r * x),
+                           2.f * (x * z - r * y), 2.f * (y * z + r * x), 1.f - 2.f * (x * x + y * y));
+            const float3 s = {cam.scale_modifier * sc.x, cam.scale_modifier * sc.y, cam.scale_modifier * sc.z};
+            M3 S = m3_make(s.x, 0.f, 0.f, 0.f, s.y, 0.f, 0.f, 0.f, s.z);
+            M3 M = m3_mul(S, R);
+            M3 dSig = m3_make(g_cov[0], 0.5f * g_cov[1], 0.5f * g_cov[2], 0.5f * g_cov[1], g_cov[3], 0.5f * g_cov[4],
+                              0.5f * g_cov[2], 0.5f * g_cov[4], g_cov[5]);
+            M3 dM = m3_mul(M, dSig);
+#pragma unroll
+            for (int cc = 0; cc < 3; cc++)
+#pragma unroll
+                for (int q = 0; q < 3; q++) dM.m[cc][q] *= 2.0f;
+            M3 Rt = m3_transpose(R);
+            M3 dMt = m3_transpose(dM);
+            g_scale.x = Rt.m[0][0] * dMt.m[0][0] + Rt.m[0][1] * dMt.m[0][1] + Rt.m[0][2] * dMt.m[0][2];
+            g_scale.y = Rt.m[1][0] * dMt.m[1][0] + Rt.m[1][1] * dMt.m[1][1] + Rt.m[1][2] * dMt.m[1][2];
+            g_scale.z = Rt.m[2][0] * dMt.m[2][0] + Rt.m[2][1] * dMt.m[2][1] + Rt.m[2][2] * dMt.m[2][2];
+#pragma unroll
+            for (int q = 0; q < 3; q++) {
+                dMt.m[0][q] *= s.x;
+                dMt.m[1][q] *= s.y;
+                dMt.m[2][q] *= s.z;
+            }
+            g_rot.x = 2 * z * (dMt.m[0][1] - dMt.m[1][0]) + 2 * y * (dMt.m[2][0] - dMt.m[0][2]) + 2 * x * (dMt.m[1][2] - dMt.m[2][1]);
+            g_rot.y = 2 * y * (dMt.m[1][0] + dMt.m[0][1]) + 2 * z * (dMt.m[2][0] + dMt.m[0][2]) + 2 * r * (dMt.m[1][2] - dMt.m[2][1]) - 4 * x * (dMt.m[2][2] + dMt.m[1][1]);
+            g_rot.z = 2 * x * (dMt.m[1][0] + dMt.m[0][1]) + 2 * r * (dMt.m[2][0] - dMt.m[0][2]) + 2 * z * (dMt.m[1][2] + dMt.m[2][1]) - 4 * y * (dMt.m[2][2] + dMt.m[0][0]);
+            g_rot.w = 2 * r * (dMt.m[0][1] - dMt.m[1][0]) + 2 * x * (dMt.m[2][0] + dMt.m[0][2]) + 2 * y * (dMt.m[1][2] + dMt.m[2][1]) - 4 * z * (dMt.m[1][1] + dMt.m[0][0]);
+        }
+    }
+    dL_dmeans3D[3 * idx] = g_mean.x;
+    dL_dmeans3D[3 * idx + 1] = g_mean.y;
+    dL_dmeans3D[3 * idx + 2] = g_mean.z;
+#pragma unroll
+    for (int k = 0; k < 6; k++) dL_dcov3D[(size_t)idx * 6 + k] = g_cov[k];
+    if (dL_dscales != nullptr) {
+        dL_dscales[3 * idx] = g_scale.x;
+        dL_dscales[3 * idx + 1] = g_scale.y;
+        dL_dscales[3 * idx + 2] = g_scale.z;
+        dL_drots[idx] = g_rot;
+    }
+}
+
+int launch_geom_backward(int P, const float* means3D, const int* radii, const float* scales,
+                         const float* rotations, const float* cov3D_precomp, const Camera& cam,
+                         const float* dL_dmean2D, const float* dL_dconic, const float* dL_ddepths,
+                         float* dL_dmeans3D, float* dL_dcov3D, float* dL_dscales, float* dL_drots,
+                         cudaStream_t stream, bool debug) {
+    if (P <= 0) return 0;
+    prof_begin(ST_GEOM_BWD, stream);
+    geom_backward_kernel<<<(P + 255) / 256, 256, 0, stream>>>(
+        P, means3D, radii, scales, (const float4*)rotations, cov3D_precomp, cam, dL_dmean2D,
+        (const float4*)dL_dconic, dL_ddepths, dL_dmeans3D, dL_dcov3D, dL_dscales, (float4*)dL_drots);
+    prof_end(ST_GEOM_BWD, stream);
+    HS_LAUNCH_OK(stream, debug);
+    return 0;
+}
+
+}  // namespace hs

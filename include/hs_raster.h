@@ -1,0 +1,124 @@
+/* libhsraster — C ABI of the Blackwell-native differentiable Gaussian rasterizer (Hier-SLAM render hot path).
+ *
+ * This is the drop-in boundary for the reference's PyTorch extension `diff_gaussian_rasterization._C`
+ * (reference: hierslam-diff-gaussian-rasterization-w-depth/ext.cpp:15-23, rasterize_points.h:18-125).
+ * Everything is plain pointers and sizes: all `const float*` / `float*` arguments are DEVICE pointers to
+ * contiguous float32 arrays on the current CUDA device unless stated otherwise; `stream` is a cudaStream_t
+ * passed as void*.  No torch types, no CPU fallback.  Every function returns 0 on success, non-zero on error
+ * (then hs_last_error() describes it).  With cam->debug != 0 every kernel launch is followed by a stream
+ * synchronisation and an error check (reference: CHECK_CUDA, cuda_rasterizer/auxiliary.h:166-173).
+ *
+ * The caller owns all memory (in the Python host: torch tensors, so the caching allocator and stream
+ * semantics of torch apply).  The three opaque state buffers play the role of the reference's geomBuffer /
+ * binningBuffer / imgBuffer (rasterize_points.cu:285-291): they are produced by the forward call and must be
+ * handed unchanged to hs_backward.
+ *
+ * Mapping to the reference entry points:
+ *   rasterize_gaussians_semantic  (rasterize_points.cu:240-336)  -> hs_forward_geometry + hs_forward_render (S > 0)
+ *   rasterize_gaussians           (rasterize_points.cu:35-117)   -> same with S = 0 and out_mask != NULL
+ *   rasterize_gaussians_backward_semantic (:339-432) / rasterize_gaussians_backward (:119-215) -> hs_backward
+ *   mark_visible                  (rasterize_points.cu:217-236)  -> hs_mark_visible
+ * The forward is split in two calls because the size of the binning buffer (num_rendered tile instances) is
+ * only known after the per-Gaussian pass; the reference resolves this with a resize callback into torch
+ * (rasterize_points.cu:27-33), a plain C ABI resolves it by returning num_rendered to the caller.
+ */
+#ifndef HS_RASTER_H_
+#define HS_RASTER_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HS_RASTER_ABI_VERSION 1
+
+/* flags (bit-or) */
+#define HS_SEM_ALPHA_EXACT 1 /* backward: semantic channels contribute to dL/dalpha (the mathematically intended
+                                gradient).  Default (0) reproduces the reference, whose kernel reads the semantic
+                                feature from a never-written scratch buffer (backward.cu:834, rasterizer_impl.cu:673). */
+#define HS_NO_CULL 2         /* forward: disable the conservative per-warp footprint test (results are identical) */
+
+/* Mirror of GaussianRasterizationSettings (diff_gaussian_rasterization/__init__.py:161-173). */
+typedef struct hs_camera {
+    int image_height;
+    int image_width;
+    float tanfovx;
+    float tanfovy;
+    float scale_modifier;
+    const float* viewmatrix; /* device, 16 floats: world-to-camera, transposed ([1,4,4] made contiguous)      */
+    const float* projmatrix; /* device, 16 floats: full projection, transposed                                */
+    const float* bg;         /* device, 3 floats                                                              */
+    const float* campos;     /* device, 3 floats (only used by the SH colour path, which is not implemented)   */
+    int prefiltered;
+    int debug;
+} hs_camera;
+
+int hs_abi_version(void);
+const char* hs_last_error(void);
+/* 1 if kernels for S semantic channels are instantiated in this build (S = 0 is the non-semantic variant). */
+int hs_supports_semantic_channels(int S);
+
+/* Sizes of the opaque state buffers (bytes).  Require a CUDA device (temp-storage queries). */
+size_t hs_geom_state_bytes(int P);
+size_t hs_image_state_bytes(int image_height, int image_width);
+size_t hs_binning_state_bytes(int num_rendered);
+
+/* Stage 1 of the forward: per-Gaussian projection / cull / tile count + offsets scan.
+ * Writes radii[P] (int32, device), fills geom_state, and returns the number of (Gaussian, tile) instances in
+ * *num_rendered (HOST pointer).  Synchronises `stream` once (the only host sync of a forward+backward).
+ * scales/rotations may be NULL iff cov3D_precomp is given, and vice versa. */
+int hs_forward_geometry(const hs_camera* cam, int P, const float* means3D, const float* opacities,
+                        const float* scales, const float* rotations, const float* cov3D_precomp, int* radii,
+                        void* geom_state, size_t geom_state_bytes, int* num_rendered, void* stream);
+
+/* Stage 2 of the forward: key duplication, sort, tile ranges, alpha compositing.
+ * Outputs (device): out_color[3,H,W], out_semantic[S,H,W] (S > 0), out_depth[1,H,W], out_median_depth[1,H,W],
+ * out_opacity[1,H,W], out_mask[1,H,W] (may be NULL; only written when S == 0).  No output needs initialisation. */
+int hs_forward_render(const hs_camera* cam, int P, int S, int num_rendered, const float* colors,
+                      const float* semantics, const int* radii, void* geom_state, void* binning_state,
+                      size_t binning_state_bytes, void* image_state, size_t image_state_bytes, float* out_color,
+                      float* out_semantic, float* out_depth, float* out_median_depth, float* out_opacity,
+                      float* out_mask, int flags, void* stream);
+
+/* Backward.  Upstream gradients may be NULL (treated as zero and never read).
+ * Accumulated outputs — MUST be zero-initialised by the caller: dL_dmeans2D[P,3], dL_dconic[P,4],
+ * dL_dopacity[P], dL_dcolors[P,3], dL_dsemantics[P,S], dL_ddepths[P].
+ * Plain outputs — fully written: dL_dmeans3D[P,3], dL_dcov3D[P,6], dL_dscales[P,3], dL_drotations[P,4]
+ * (the last two may be NULL when cov3D_precomp is used). */
+int hs_backward(const hs_camera* cam, int P, int S, int num_rendered, const float* means3D, const int* radii,
+                const float* colors, const float* semantics, const float* scales, const float* rotations,
+                const float* cov3D_precomp, const void* geom_state, const void* binning_state,
+                const void* image_state, const float* dL_dout_color, const float* dL_dout_semantic,
+                const float* dL_dout_depth, const float* dL_dout_median_depth, const float* dL_dout_opacity,
+                float* dL_dmeans2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolors, float* dL_dsemantics,
+                float* dL_ddepths, float* dL_dmeans3D, float* dL_dcov3D, float* dL_dscales, float* dL_drotations,
+                int flags, void* stream);
+
+/* present[P] (bool, device) = view-space z > 0.2 (reference: rasterizer_impl.cu:54-66). */
+int hs_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                    unsigned char* present, void* stream);
+
+/* Measurement aids.  hs_profile_enable(1) makes every subsequent call record CUDA events around each kernel
+ * on the launching stream; hs_profile_read() waits for them and returns the elapsed milliseconds of the most
+ * recent launch of each stage (-1 = not run): [preprocess, scan, duplicate, sort, ranges, blend_fwd, blend_bwd,
+ * geom_bwd].  hs_kernel_launch_count() = kernels of this library launched so far; hs_library_call_count() =
+ * CUB device-wide primitives (scan, radix sort) called so far. */
+int hs_profile_enable(int on);
+int hs_profile_read(float ms[8]);
+long long hs_kernel_launch_count(void);
+long long hs_library_call_count(void);
+
+/* Test / debugging aid: byte offsets of the arrays inside the opaque state buffers.
+ *   geom    : [depths f32[P], means2D f32[2P], conic_opacity f32[4P], tiles_touched u32[P], point_offsets u32[P]]
+ *   image   : [final_T f32[N], n_contrib u32[N], ranges u32[2*tiles]]
+ *   binning : [point_list u32[R], point_list_unsorted u32[R], keys u64[R], keys_unsorted u64[R]] */
+int hs_geom_state_layout(int P, size_t offsets[5]);
+int hs_image_state_layout(int image_height, int image_width, size_t offsets[3]);
+int hs_binning_state_layout(int num_rendered, size_t offsets[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HS_RASTER_H_ */

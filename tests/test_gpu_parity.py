@@ -1,0 +1,295 @@
+"""GPU parity tests (-m gpu): the new sm_100a path, called through the C ABI (hier_slam_b200._C -> ctypes ->
+libhsraster.so), against
+  (1) the golden fixtures made by the reference CUDA extension (tests/golden/*.npz),
+  (2) the CPU oracle on small seeded scenes,
+  (3) the reference CUDA extension itself when oracle/_ref travelled to the box (bit-exact lists / keys / radii),
+  (4) size-independent properties at the full BASELINE.json size (1200x680, 300K Gaussians).
+Tolerances are the north_star's: radii / keys / tile lists bit-exact; images 1e-5 abs + 1e-4 rel;
+gradients 1e-3 relative (norm-wise: the reference's atomics are order-nondeterministic).
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import parity_tools as pt
+from hier_slam_b200.scene import CONFIGS, camera_matrices, make_scene, upstream_grads
+from oracle import raster_oracle as O
+from oracle import ref_loader
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+FIXTURES = sorted(glob.glob(os.path.join(GOLDEN, "*.npz")))
+IMG_ATOL, IMG_RTOL, GRAD_RTOL = 1e-5, 1e-4, 1e-3
+
+
+def new_impl():
+    from hier_slam_b200 import _C, _lib
+    from hier_slam_b200.rasterizer import GaussianRasterizationSettings
+    _lib.load()  # raises if the CUDA library is missing: no fallback
+    return _C, GaussianRasterizationSettings
+
+
+def assert_images_close(a, b, what):
+    mx, viol = pt.image_err(a, b, IMG_ATOL, IMG_RTOL)
+    assert viol == 0, f"{what}: {viol} pixels outside {IMG_ATOL}+{IMG_RTOL}*|ref| (max abs err {mx:.3e})"
+
+
+def assert_grads_close(a, b, what, tol=GRAD_RTOL):
+    nrm, mx = pt.grad_err(a, b)
+    assert nrm < tol, f"{what}: norm-wise relative error {nrm:.3e} (max/max|ref| {mx:.3e})"
+
+
+@pytest.mark.skipif(not FIXTURES, reason="no golden fixtures committed yet")
+@pytest.mark.parametrize("path", FIXTURES, ids=[os.path.basename(p) for p in FIXTURES])
+def test_against_reference_golden(path):
+    C, Settings = new_impl()
+    z = np.load(path)
+    cfg = CONFIGS[str(z["scene_key"])]
+    S = int(z["S"])
+    scene = make_scene(cfg, int(z["scene_seed"]), num_semantic=S, device="cuda")
+    settings = pt.make_settings(Settings, cfg)
+    T = lambda k: torch.from_numpy(z[k]).cuda()
+    f = pt.run_forward(C, settings, scene)
+    P, H, W = scene["means3D"].shape[0], cfg.height, cfg.width
+    sv = C.state_views(P, H, W, f["R"], f["geomBuffer"], f["binningBuffer"], f["imgBuffer"])
+    # bit-exact: radii, per-Gaussian state, keys, lists, ranges, n_contrib
+    assert f["R"] == int(z["num_rendered"])
+    assert torch.equal(f["radii"], T("radii"))
+    vis = f["radii"] > 0
+    for k in ("depths", "means2D", "conic_opacity"):
+        assert pt.bits_equal(sv[k][vis], T("st_" + k)[vis]) == 0, k
+    assert torch.equal(sv["tiles_touched"], T("st_tiles_touched"))
+    for k in ("keys_unsorted", "point_list_unsorted", "keys", "point_list", "ranges", "n_contrib"):
+        assert torch.equal(sv[k], T("st_" + k)), k
+    assert pt.bits_equal(sv["final_T"], T("st_final_T")) == 0
+    for k in ("color", "semantic", "depth", "median_depth", "final_opacity"):
+        assert_images_close(f[k], T(k), k)
+    ug = upstream_grads(cfg, int(z["grad_seed"]), num_semantic=S, device="cuda")
+    if not int(z["all_grads"]):
+        ug["semantic"] = ug["median_depth"] = ug["final_opacity"] = None
+    g = pt.run_backward(C, settings, scene, f, ug, materialize=False)
+    for k, rk in (("means3D", "d_means3D"), ("means2D", "d_means2D"), ("colors", "d_colors"),
+                  ("semantics", "d_semantics"), ("opacities", "d_opacities"), ("scales", "d_scales"),
+                  ("rotations", "d_rotations"), ("cov3D", "d_cov3D")):
+        assert_grads_close(g[k], T(rk), k)
+
+
+@pytest.mark.parametrize("key,S,semantic", [("tiny", 26, True), ("small", 26, True), ("tiny", 16, True),
+                                            ("small", 74, True), ("tiny", 102, True), ("small", 0, False)])
+def test_against_cpu_oracle(key, S, semantic):
+    C, Settings = new_impl()
+    cfg = CONFIGS[key]
+    cpu = make_scene(cfg, 3, num_semantic=max(S, 1))
+    if not semantic:
+        cpu.pop("semantics_precomp")
+    scene = {k: v.cuda() for k, v in cpu.items()}
+    settings = pt.make_settings(Settings, cfg)
+    f = pt.run_forward(C, settings, scene, semantic)
+    P, H, W = cpu["means3D"].shape[0], cfg.height, cfg.width
+    sv = {k: v.cpu() for k, v in C.state_views(P, H, W, f["R"], f["geomBuffer"], f["binningBuffer"],
+                                               f["imgBuffer"]).items()}
+    view, proj, campos, tfx, tfy = camera_matrices(cfg)
+    # oracle stages are fed with the GPU's own upstream state so that each stage is checked in isolation
+    geom = O.preprocess(cpu["means3D"], cpu["scales"], cpu["rotations"], cpu["opacities"], view, proj, W, H, tfx, tfy)
+    near_int = (geom["radius_prerounding"] - geom["radius_prerounding"].round()).abs() < 1e-3
+    assert int(((geom["radii"] != f["radii"].cpu()) & ~near_int).sum()) == 0
+    radii = f["radii"].cpu()
+    both = (radii > 0) & (geom["radii"] > 0)
+    assert float((geom["depths"][both] - sv["depths"][both]).abs().max()) < 1e-5
+    assert float((geom["means2D"][both] - sv["means2D"][both]).abs().max()) < 2e-3
+    keys_u, vals_u = O.duplicate_with_keys(sv["depths"], sv["means2D"], radii, W, H)
+    assert keys_u.numel() == f["R"]
+    assert torch.equal(keys_u, sv["keys_unsorted"]) and torch.equal(vals_u.int(), sv["point_list_unsorted"])
+    skeys, plist, ranges = O.sort_and_ranges(keys_u, vals_u, W, H)
+    assert torch.equal(skeys, sv["keys"]) and torch.equal(plist.int(), sv["point_list"])
+    assert torch.equal(ranges.int(), sv["ranges"])
+    ggeom = dict(means2D=sv["means2D"], conic_opacity=sv["conic_opacity"], depths=sv["depths"])
+    sem_cpu = cpu.get("semantics_precomp")
+    fo = O.blend_forward(ggeom, plist, ranges, cpu["colors_precomp"], sem_cpu, W, H)
+    nc_same = (fo["n_contrib"].int() == sv["n_contrib"])
+    assert int((~nc_same).sum()) <= max(2, int(1e-4 * W * H))
+    ok = nc_same.reshape(H, W)
+    names = [("color", "color"), ("depth", "depth"), ("median_depth", "median_depth"), ("opacity", "final_opacity")]
+    names += [("semantic", "semantic")] if semantic else [("mask", "mask")]
+    for ko, kn in names:
+        a, b = f[kn].cpu()[:, ok], fo[ko][:, ok]
+        assert int(((a - b).abs() > IMG_ATOL + IMG_RTOL * b.abs()).sum()) == 0, kn
+    # backward: oracle evaluated from the GPU forward state, all five upstream gradients, both Q1 modes
+    ugc = upstream_grads(cfg, 4, num_semantic=max(S, 1))
+    if not semantic:
+        ugc["semantic"] = None
+    ug = {k: (v.cuda() if v is not None else None) for k, v in ugc.items()}
+    st = dict(geom=dict(ggeom, cov3D=geom["cov3D"], radii=radii), point_list=plist, ranges=ranges,
+              final_T=sv["final_T"], n_contrib=sv["n_contrib"].long())
+    for mode in (("ref", "exact") if semantic else ("ref",)):
+        C.SEM_ALPHA_GRAD = mode
+        try:
+            g = pt.run_backward(C, settings, scene, f, ug, semantic, materialize=False)
+        finally:
+            C.SEM_ALPHA_GRAD = "ref"
+        go = O.rasterize_backward(st, torch.zeros(3), cpu["means3D"], cpu["colors_precomp"], sem_cpu, cpu["scales"],
+                                  cpu["rotations"], 1.0, None, view, proj, tfx, tfy, H, W, ugc["color"],
+                                  ugc["semantic"], ugc["depth"], ugc["median_depth"], ugc["final_opacity"],
+                                  sem_alpha_grad=mode)
+        pairs = [("means3D", "dL_dmeans3D"), ("means2D", "dL_dmean2D"), ("colors", "dL_dcolors"),
+                 ("opacities", "dL_dopacity"), ("scales", "dL_dscales"), ("rotations", "dL_drotations"),
+                 ("cov3D", "dL_dcov3D")] + ([("semantics", "dL_dsemantics")] if semantic else [])
+        for kn, ko in pairs:
+            assert_grads_close(g[kn].cpu(), go[ko].reshape(g[kn].shape), f"{kn} ({mode})")
+
+
+def _ref_or_skip(S):
+    ref = ref_loader.load_reference(S)
+    if ref is None:
+        pytest.skip(f"oracle/_ref/S{S} not available on this box")
+    return ref
+
+
+@pytest.mark.parametrize("key,P,S", [("c1", None, 26), ("c2", 60_000, 26), ("c4", 50_000, 16), ("c5", 50_000, 74)])
+def test_against_live_reference(key, P, S):
+    """Same inputs through the UNMODIFIED reference CUDA build: lists / keys / radii bit-exact, images and
+    gradients within the north_star tolerances."""
+    ref = _ref_or_skip(S)
+    C, Settings = new_impl()
+    cfg = CONFIGS[key]
+    scene = make_scene(cfg, 0, num_gaussians=P, num_semantic=S, device="cuda")
+    settings = pt.make_settings(Settings, cfg)
+    ug = upstream_grads(cfg, 1, num_semantic=S, device="cuda")
+    f, fr = pt.run_forward(C, settings, scene), pt.run_forward(ref._C, settings, scene)
+    Pn, H, W = scene["means3D"].shape[0], cfg.height, cfg.width
+    sv = C.state_views(Pn, H, W, f["R"], f["geomBuffer"], f["binningBuffer"], f["imgBuffer"])
+    sr = ref_loader.parse_ref_state(Pn, H, W, fr["R"], fr["geomBuffer"], fr["binningBuffer"], fr["imgBuffer"])
+    assert f["R"] == fr["R"]
+    assert torch.equal(f["radii"], fr["radii"])
+    vis = fr["radii"] > 0
+    for k in ("depths", "means2D", "conic_opacity"):
+        assert pt.bits_equal(sv[k][vis], sr[k][vis]) == 0, k
+    assert torch.equal(sv["tiles_touched"], sr["tiles_touched"])
+    for k in ("keys_unsorted", "point_list_unsorted", "keys", "point_list", "ranges", "n_contrib"):
+        assert torch.equal(sv[k], sr[k]), k
+    for k in ("color", "semantic", "depth", "median_depth", "final_opacity"):
+        assert_images_close(f[k], fr[k], k)
+    g = pt.run_backward(C, settings, scene, f, ug)
+    gr = pt.run_backward(ref._C, settings, scene, fr, ug)
+    for k in g:
+        assert_grads_close(g[k], gr[k], k)
+
+
+def test_nonsemantic_against_live_reference():
+    ref = _ref_or_skip(26)
+    C, Settings = new_impl()
+    cfg = CONFIGS["c1"]
+    scene = make_scene(cfg, 0, device="cuda")
+    scene.pop("semantics_precomp")
+    settings = pt.make_settings(Settings, cfg)
+    ug = upstream_grads(cfg, 1, device="cuda")
+    f, fr = pt.run_forward(C, settings, scene, False), pt.run_forward(ref._C, settings, scene, False)
+    assert f["R"] == fr["R"] and torch.equal(f["radii"], fr["radii"])
+    for k in ("color", "depth", "median_depth", "final_opacity", "mask"):
+        assert_images_close(f[k], fr[k], k)
+    g = pt.run_backward(C, settings, scene, f, ug, False)
+    gr = pt.run_backward(ref._C, settings, scene, fr, ug, False)
+    for k in g:
+        assert_grads_close(g[k], gr[k], k)
+
+
+def test_full_size_properties_c2():
+    """BASELINE.json config 2 at full size (1200x680, 300K Gaussians, S=26): properties that need no oracle."""
+    C, Settings = new_impl()
+    cfg = CONFIGS["c2"]
+    scene = make_scene(cfg, 0, device="cuda")
+    settings = pt.make_settings(Settings, cfg)
+    f = pt.run_forward(C, settings, scene)
+    P, H, W = cfg.num_gaussians, cfg.height, cfg.width
+    sv = C.state_views(P, H, W, f["R"], f["geomBuffer"], f["binningBuffer"], f["imgBuffer"])
+    keys = sv["keys"]
+    assert bool((keys[1:] >= keys[:-1]).all())                                   # sortedness
+    assert int(sv["tiles_touched"].long().sum()) == f["R"] == int(sv["point_offsets"][-1])
+    same = keys[1:] == keys[:-1]
+    assert bool((sv["point_list"][1:][same] > sv["point_list"][:-1][same]).all())  # stability
+    assert torch.equal(torch.sort(sv["point_list"].long())[0], torch.sort(sv["point_list_unsorted"].long())[0])
+    rg = sv["ranges"].long()
+    assert int((rg[:, 1] - rg[:, 0]).sum()) == f["R"]
+    tile_of = (keys >> 32)
+    nz = torch.nonzero(rg[:, 1] > rg[:, 0]).reshape(-1)
+    assert torch.equal(tile_of[rg[nz, 0]], nz) and torch.equal(tile_of[rg[nz, 1] - 1], nz)
+    # silhouette = 1 - final_T in [0, 1]; contributors never exceed the tile's list length
+    assert float(f["final_opacity"].min()) >= 0 and float(f["final_opacity"].max()) <= 1.0
+    assert pt.bits_equal((1 - sv["final_T"]).reshape(1, H, W), f["final_opacity"]) == 0
+    # footprint culling is exact: identical bits with and without it
+    C.NO_CULL = True
+    try:
+        f2 = pt.run_forward(C, settings, scene)
+    finally:
+        C.NO_CULL = False
+    for k in ("color", "semantic", "depth", "median_depth", "final_opacity"):
+        assert pt.bits_equal(f[k], f2[k]) == 0, k
+    # idempotence of the forward and linearity of the backward in the upstream gradient
+    f3 = pt.run_forward(C, settings, scene)
+    assert pt.bits_equal(f["color"], f3["color"]) == 0 and torch.equal(f["radii"], f3["radii"])
+    u1 = upstream_grads(cfg, 1, device="cuda")
+    u2 = upstream_grads(cfg, 2, device="cuda")
+    u12 = {k: 2.0 * u1[k] + u2[k] for k in u1}
+    g1, g2, g12 = (pt.run_backward(C, settings, scene, f, u) for u in (u1, u2, u12))
+    for k in g1:
+        assert_grads_close(g12[k], 2.0 * g1[k] + g2[k], f"linearity of {k}", tol=1e-4)
+    # None upstream gradients == zero upstream gradients
+    z = {k: (v if k in ("color", "depth") else None) for k, v in u1.items()}
+    zz = {k: (v if k in ("color", "depth") else torch.zeros_like(v)) for k, v in u1.items()}
+    ga, gb = pt.run_backward(C, settings, scene, f, z, materialize=False), pt.run_backward(C, settings, scene, f, zz)
+    for k in ga:
+        assert_grads_close(ga[k], gb[k], f"None-vs-zero {k}", tol=1e-5)
+
+
+def test_public_api_autograd_and_edge_cases():
+    """The reference's user-facing call pattern (utils/slam_helpers.py:195-219 + scripts/hierslam.py:896): nn.Module
+    call, 6-tuple, .backward() with a loss that ignores some outputs; empty input; non-contiguous means3D."""
+    import diff_gaussian_rasterization as dgr
+    cfg = CONFIGS["small"]
+    sc = make_scene(cfg, 5, device="cuda")
+    settings = pt.make_settings(dgr.GaussianRasterizationSettings, cfg)
+    pts4 = torch.cat([sc["means3D"], torch.ones_like(sc["means3D"][:, :1])], 1)
+    rel = torch.eye(4, device="cuda")
+    leaf = {k: v.clone().requires_grad_(True) for k, v in sc.items()}
+    means3D = (rel @ torch.cat([leaf["means3D"], torch.ones_like(pts4[:, :1])], 1).T).T[:, :3]   # non-contiguous view
+    assert not means3D.is_contiguous()
+    means2D = torch.zeros_like(leaf["means3D"], requires_grad=True) + 0
+    means2D.retain_grad()
+    out = dgr.GaussianRasterizer_semantic(raster_settings=settings)(
+        means3D=means3D, means2D=means2D, opacities=leaf["opacities"], colors_precomp=leaf["colors_precomp"],
+        scales=leaf["scales"], rotations=leaf["rotations"], semantics_precomp=leaf["semantics_precomp"])
+    color, radii, sem, depth, median, opacity = out
+    assert color.shape == (3, cfg.height, cfg.width) and sem.shape == (26, cfg.height, cfg.width)
+    assert radii.dtype == torch.int32 and radii.shape == (sc["means3D"].shape[0],)
+    loss = color.abs().sum() + depth.sum()          # tracking-style: semantic / median / silhouette unused
+    loss.backward()
+    for k in ("means3D", "opacities", "colors_precomp", "scales", "rotations"):
+        assert leaf[k].grad is not None and torch.isfinite(leaf[k].grad).all()
+    assert means2D.grad.shape == (sc["means3D"].shape[0], 3) and float(means2D.grad[:, 2].abs().max()) == 0
+    assert float(leaf["semantics_precomp"].grad.abs().max()) == 0
+    # markVisible
+    vis = dgr.GaussianRasterizer_semantic(settings).markVisible(sc["means3D"])
+    assert vis.dtype == torch.bool and torch.equal(vis, sc["means3D"][:, 2] > 0.2)
+    # empty scene: zero images, nothing rendered (reference: rasterize_points.cu:277-292)
+    e = {k: v[:0] for k, v in sc.items()}
+    o = dgr.GaussianRasterizer_semantic(settings)(means3D=e["means3D"], means2D=e["means3D"], opacities=e["opacities"],
+                                                  colors_precomp=e["colors_precomp"], scales=e["scales"],
+                                                  rotations=e["rotations"], semantics_precomp=e["semantics_precomp"])
+    assert float(o[0].abs().max()) == 0 and o[1].numel() == 0
+    # everything culled: background-free zeros and median default
+    far = dict(sc)
+    far["means3D"] = sc["means3D"] * torch.tensor([1.0, 1.0, -1.0], device="cuda")
+    o = dgr.GaussianRasterizer_semantic(settings)(means3D=far["means3D"], means2D=far["means3D"],
+                                                  opacities=far["opacities"], colors_precomp=far["colors_precomp"],
+                                                  scales=far["scales"], rotations=far["rotations"],
+                                                  semantics_precomp=far["semantics_precomp"])
+    assert int((o[1] > 0).sum()) <= int((far["means3D"][:, 2] > 0.2).sum())
+    # unsupported S is a loud error, not a fallback
+    with pytest.raises(RuntimeError, match="not instantiated"):
+        dgr.GaussianRasterizer_semantic(settings)(means3D=sc["means3D"], means2D=sc["means3D"],
+                                                  opacities=sc["opacities"], colors_precomp=sc["colors_precomp"],
+                                                  scales=sc["scales"], rotations=sc["rotations"],
+                                                  semantics_precomp=sc["semantics_precomp"][:, :5].contiguous())

@@ -1,0 +1,77 @@
+"""Host-side logic of the reference-facing API that needs no GPU: argument validation, error behaviour,
+the absence of any CPU fallback, scene determinism."""
+import pytest
+import torch
+
+import diff_gaussian_rasterization as dgr
+from hier_slam_b200.scene import CONFIGS, camera_matrices, keyframe_poses, make_scene, upstream_grads
+from oracle import raster_oracle as O
+
+
+def settings(cfg, device="cpu"):
+    view, proj, campos, tfx, tfy = camera_matrices(cfg)
+    return dgr.GaussianRasterizationSettings(cfg.height, cfg.width, tfx, tfy, torch.zeros(3), 1.0, view, proj, 0,
+                                             campos, False, False)
+
+
+def test_public_names_match_reference():
+    for name in ("GaussianRasterizationSettings", "GaussianRasterizer", "GaussianRasterizer_semantic",
+                 "rasterize_gaussians", "rasterize_gaussians_semantic", "_RasterizeGaussians",
+                 "_RasterizeGaussians_semantic", "cpu_deep_copy_tuple", "_C"):
+        assert hasattr(dgr, name)
+    for name in ("rasterize_gaussians", "rasterize_gaussians_backward", "mark_visible",
+                 "rasterize_gaussians_semantic", "rasterize_gaussians_backward_semantic"):
+        assert hasattr(dgr._C, name)            # reference: ext.cpp:15-23
+    assert dgr.GaussianRasterizationSettings._fields == (
+        "image_height", "image_width", "tanfovx", "tanfovy", "bg", "scale_modifier", "viewmatrix", "projmatrix",
+        "sh_degree", "campos", "prefiltered", "debug")
+
+
+def test_argument_validation_messages():
+    cfg = CONFIGS["tiny"]
+    sc = make_scene(cfg, 0)
+    for cls in (dgr.GaussianRasterizer, dgr.GaussianRasterizer_semantic):
+        r = cls(settings(cfg))
+        with pytest.raises(Exception, match="excatly one of either SHs or precomputed colors"):
+            r(means3D=sc["means3D"], means2D=sc["means3D"], opacities=sc["opacities"], scales=sc["scales"],
+              rotations=sc["rotations"])
+        with pytest.raises(Exception, match="exactly one of either scale/rotation pair"):
+            r(means3D=sc["means3D"], means2D=sc["means3D"], opacities=sc["opacities"],
+              colors_precomp=sc["colors_precomp"])
+        with pytest.raises(Exception, match="exactly one of either scale/rotation pair"):
+            r(means3D=sc["means3D"], means2D=sc["means3D"], opacities=sc["opacities"],
+              colors_precomp=sc["colors_precomp"], scales=sc["scales"], rotations=sc["rotations"],
+              cov3D_precomp=torch.zeros(sc["means3D"].shape[0], 6))
+
+
+def test_no_cpu_fallback():
+    cfg = CONFIGS["tiny"]
+    sc = make_scene(cfg, 0)
+    r = dgr.GaussianRasterizer_semantic(settings(cfg))
+    with pytest.raises(RuntimeError, match="CUDA-only"):
+        r(means3D=sc["means3D"], means2D=sc["means3D"], opacities=sc["opacities"],
+          colors_precomp=sc["colors_precomp"], scales=sc["scales"], rotations=sc["rotations"],
+          semantics_precomp=sc["semantics_precomp"])
+    with pytest.raises(RuntimeError, match="must have dimensions"):
+        dgr._C.rasterize_gaussians_semantic(torch.zeros(3), torch.zeros(5, 4), *([torch.zeros(1)] * 5), 1.0,
+                                            torch.zeros(0), torch.eye(4), torch.eye(4), 1.0, 1.0, 8, 8,
+                                            torch.zeros(0), 0, torch.zeros(3), False, False)
+
+
+def test_scene_generator_is_seeded():
+    cfg = CONFIGS["tiny"]
+    a, b, c = make_scene(cfg, 0), make_scene(cfg, 0), make_scene(cfg, 1)
+    for k in a:
+        assert torch.equal(a[k], b[k])
+    assert not torch.equal(a["means3D"], c["means3D"])
+    g = upstream_grads(cfg, 1)
+    assert g["semantic"].shape == (26, cfg.height, cfg.width)
+    assert keyframe_poses(3).shape == (3, 4, 4)
+    assert make_scene(CONFIGS["c4"], 0, num_gaussians=10)["semantics_precomp"].shape == (10, 16)
+
+
+def test_get_higher_msb_matches_documented_key_widths():
+    # 44 bits @1200x680 (3225 tiles), 43 @640x480 (1200), 41 @320x240 (300)
+    assert 32 + O.get_higher_msb(75 * 43) == 44
+    assert 32 + O.get_higher_msb(40 * 30) == 43
+    assert 32 + O.get_higher_msb(20 * 15) == 41
