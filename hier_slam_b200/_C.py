@@ -23,7 +23,7 @@ from . import _lib
 SEM_ALPHA_GRAD = os.environ.get("HS_SEM_ALPHA_GRAD", "ref")
 NO_CULL = os.environ.get("HS_NO_CULL", "0") == "1"
 
-_contig_cache: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
+_contig_cache: dict = {}   # id(tensor) -> (weakref(tensor), version, contiguous copy)
 
 
 def _small_contig(t: torch.Tensor) -> torch.Tensor:
@@ -31,11 +31,15 @@ def _small_contig(t: torch.Tensor) -> torch.Tensor:
     (the [1,4,4] matrices of utils/recon_helpers.py:8-13 are transposed views and are reused every frame)."""
     if t.is_contiguous() and t.dtype == torch.float32:
         return t
-    hit = _contig_cache.get(t)
-    if hit is not None and hit[0] == t._version:
-        return hit[1]
+    key = id(t)
+    hit = _contig_cache.get(key)
+    if hit is not None and hit[0]() is t and hit[1] == t._version:
+        return hit[2]
     c = t.contiguous().float()
-    _contig_cache[t] = (t._version, c)
+    if len(_contig_cache) > 256:
+        for k in [k for k, v in _contig_cache.items() if v[0]() is None]:
+            del _contig_cache[k]
+    _contig_cache[key] = (weakref.ref(t), t._version, c)
     return c
 
 

@@ -73,7 +73,7 @@ def load() -> ctypes.CDLL:
     lib.hs_binning_state_layout.argtypes = [c_int, POINTER(c_size_t)]
     lib.hs_binning_state_layout.restype = c_int
     lib.hs_profile_enable.argtypes = [c_int]
-    lib.hs_profile_read.argtypes = [POINTER(c_float)]
+    lib.hs_profile_read.argtypes = [POINTER(c_float), POINTER(c_int)]
     lib.hs_kernel_launch_count.restype = ctypes.c_longlong
     lib.hs_library_call_count.restype = ctypes.c_longlong
     if lib.hs_abi_version() != 1:
@@ -89,8 +89,9 @@ def check(rc: int, what: str) -> None:
 
 
 def profile_read() -> dict:
-    """Elapsed ms of the most recent launch of every stage (needs hs_profile_enable(1) before the calls)."""
+    """{stage: (total_ms, launches)} since the previous read (needs hs_profile_enable(1) before the calls)."""
     lib = load()
     ms = (c_float * 8)()
-    check(lib.hs_profile_read(ms), "hs_profile_read")
-    return {name: float(ms[i]) for i, name in enumerate(STAGES) if ms[i] >= 0}
+    cnt = (c_int * 8)()
+    check(lib.hs_profile_read(ms, cnt), "hs_profile_read")
+    return {name: (float(ms[i]), int(cnt[i])) for i, name in enumerate(STAGES) if cnt[i] > 0}

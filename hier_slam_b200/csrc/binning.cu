@@ -9,6 +9,7 @@
 #include <stdarg.h>
 #include <mutex>
 #include <string>
+#include <vector>
 
 namespace hs {
 
@@ -25,42 +26,70 @@ void set_error(const char* fmt, ...) {
 const char* last_error() { return g_last_error.c_str(); }
 
 // ---- profiling / launch accounting ---------------------------------------------------------------------
+// Every kernel launch made while profiling is on gets its own CUDA event pair on the launching stream;
+// hs_profile_read() waits for all of them and returns per-stage totals and counts, then recycles the events.
+struct ProfRec {
+    int stage;
+    cudaEvent_t e0, e1;
+};
 static bool g_prof_on = false;
-static cudaEvent_t g_ev[2 * ST_COUNT];
-static bool g_ev_used[ST_COUNT];
-static bool g_ev_created = false;
+static std::mutex g_prof_mu;
+static std::vector<ProfRec> g_recs;
+static std::vector<ProfRec> g_free;
+static thread_local int g_open = -1;
 static long long g_launches = 0;      // kernels written in this library
 static long long g_lib_calls = 0;     // CUB device-wide primitives (scan, sort)
 void count_launch(int n) { g_launches += n; }
 void count_lib_call() { g_lib_calls += 1; }
 long long launches() { return g_launches; }
 long long lib_calls() { return g_lib_calls; }
-void prof_enable(bool on) {
-    if (on && !g_ev_created) {
-        for (int i = 0; i < 2 * ST_COUNT; i++) cudaEventCreate(&g_ev[i]);
-        g_ev_created = true;
-    }
-    for (int i = 0; i < ST_COUNT; i++) g_ev_used[i] = false;
-    g_prof_on = on;
-}
+void prof_enable(bool on) { g_prof_on = on; }
 void prof_begin(int stage, cudaStream_t stream) {
-    if (g_prof_on) cudaEventRecord(g_ev[2 * stage], stream);
+    if (!g_prof_on) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    ProfRec r;
+    if (!g_free.empty()) {
+        r = g_free.back();
+        g_free.pop_back();
+    } else {
+        cudaEventCreate(&r.e0);
+        cudaEventCreate(&r.e1);
+    }
+    r.stage = stage;
+    cudaEventRecord(r.e0, stream);
+    g_recs.push_back(r);
+    g_open = (int)g_recs.size() - 1;
 }
 void prof_end(int stage, cudaStream_t stream) {
-    if (g_prof_on) {
-        cudaEventRecord(g_ev[2 * stage + 1], stream);
-        g_ev_used[stage] = true;
-    }
-}
-int prof_read(float* ms) {
-    for (int i = 0; i < ST_COUNT; i++) {
-        ms[i] = -1.f;
-        if (g_ev_created && g_ev_used[i]) {
-            if (cudaEventSynchronize(g_ev[2 * i + 1]) != cudaSuccess) return 2;
-            if (cudaEventElapsedTime(&ms[i], g_ev[2 * i], g_ev[2 * i + 1]) != cudaSuccess) return 2;
+    if (!g_prof_on) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (int i = (int)g_recs.size() - 1; i >= 0; i--) {
+        if (g_recs[i].stage == stage) {
+            cudaEventRecord(g_recs[i].e1, stream);
+            break;
         }
     }
-    return 0;
+}
+int prof_read(float* total_ms, int* count) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (int i = 0; i < ST_COUNT; i++) {
+        total_ms[i] = 0.f;
+        count[i] = 0;
+    }
+    int rc = 0;
+    for (auto& r : g_recs) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(r.e1) != cudaSuccess || cudaEventElapsedTime(&ms, r.e0, r.e1) != cudaSuccess) {
+            rc = 2;
+            cudaGetLastError();
+        } else {
+            total_ms[r.stage] += ms;
+            count[r.stage] += 1;
+        }
+        g_free.push_back(r);
+    }
+    g_recs.clear();
+    return rc;
 }
 
 // ---- state layouts ------------------------------------------------------------------------------------

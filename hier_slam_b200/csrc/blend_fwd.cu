@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(256) blend_forward_kernel(
             const float2 xy = s_xy[j];
             const float2 d = {xy.x - pixf.x, xy.y - pixf.y};
             const float4 con_o = s_co[j];
-            const float power = -0.5f * (con_o.x * d.x * d.x + con_o.z * d.y * d.y) - con_o.y * d.x * d.y;
+            const float power = gauss_power(d, con_o);
             if (power > 0.0f) continue;
             const float alpha = min(0.99f, con_o.w * exp(power));
             if (alpha < 1.0f / 255.0f) continue;

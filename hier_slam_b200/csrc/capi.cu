@@ -5,7 +5,7 @@
 namespace hs {
 const char* last_error();
 void prof_enable(bool on);
-int prof_read(float* ms);
+int prof_read(float* total_ms, int* count);
 long long launches();
 long long lib_calls();
 }
@@ -242,7 +242,7 @@ int hs_profile_enable(int on) {
     prof_enable(on != 0);
     return 0;
 }
-int hs_profile_read(float ms[8]) { return prof_read(ms); }
+int hs_profile_read(float total_ms[8], int count[8]) { return prof_read(total_ms, count); }
 long long hs_kernel_launch_count(void) { return launches(); }
 long long hs_library_call_count(void) { return lib_calls(); }
 

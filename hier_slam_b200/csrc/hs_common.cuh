@@ -108,6 +108,16 @@ int launch_geom_backward(int P, const float* means3D, const int* radii, const fl
 int launch_mark_visible(int P, const float* means3D, const float* view, const float* proj, bool* present,
                         cudaStream_t stream, bool debug);
 
+// power = -0.5 (A dx^2 + C dy^2) - B dx dy with the roundings of the reference's sm_100 SASS pinned
+// (forward.cu:490 / backward.cu:804: FMUL A*dx, C*dy, (C*dy)*dy, B*dx, (B*dx)*dy; FFMA dx*(A*dx)+..; FFMA *-0.5 - ..),
+// so that the alpha < 1/255 and T < 1e-4 decisions -- hence n_contrib and final_T -- agree bit for bit.
+#ifdef __CUDACC__
+__device__ __forceinline__ float gauss_power(const float2 d, const float4 con_o) {
+    const float q = __fmaf_rn(d.x, __fmul_rn(d.x, con_o.x), __fmul_rn(d.y, __fmul_rn(d.y, con_o.z)));
+    return __fmaf_rn(q, -0.5f, -__fmul_rn(d.y, __fmul_rn(d.x, con_o.y)));
+}
+#endif
+
 // flags shared by the blend kernels
 enum : int {
     HS_FLAG_SEM_ALPHA_EXACT = 1,   // semantic channels contribute to dL/dalpha (reference quirk Q1 off)

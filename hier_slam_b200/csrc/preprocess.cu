@@ -55,6 +55,23 @@ __device__ __forceinline__ float4 xform4x4(const float3& p, const float* m) {  /
     return t;
 }
 
+// Rotation matrix of forward.cu:135-139 (glm column-major constructor order).  The six mixed products are the
+// only place of the per-Gaussian pass where the PTX leaves a mul+add pair for ptxas to contract, and ptxas picks
+// the product to keep rounded by operand order -- which NVVM canonicalises differently in different kernels.
+// The roundings are therefore pinned with explicit intrinsics to what the reference's sm_100 SASS does
+// (FMUL r*z, r*x, x*z, y*y, z*z; every other product fused), so that cov3D -> conic stay bit-exact.
+__device__ __forceinline__ M3 quat_to_rot(float r, float x, float y, float z) {
+    const float rz = __fmul_rn(r, z), rx = __fmul_rn(r, x), xz = __fmul_rn(x, z);
+    const float yy = __fmul_rn(y, y), zz = __fmul_rn(z, z);
+    const float xy_m_rz = __fmaf_rn(x, y, -rz), xy_p_rz = __fmaf_rn(x, y, rz);
+    const float xz_p_ry = __fmaf_rn(r, y, xz), xz_m_ry = __fmaf_rn(-r, y, xz);
+    const float yz_m_rx = __fmaf_rn(y, z, -rx), yz_p_rx = __fmaf_rn(y, z, rx);
+    const float yy_p_zz = __fadd_rn(yy, zz), xx_p_zz = __fmaf_rn(x, x, zz), xx_p_yy = __fmaf_rn(x, x, yy);
+    return m3_make(__fsub_rn(1.f, __fadd_rn(yy_p_zz, yy_p_zz)), __fadd_rn(xy_m_rz, xy_m_rz), __fadd_rn(xz_p_ry, xz_p_ry),
+                   __fadd_rn(xy_p_rz, xy_p_rz), __fsub_rn(1.f, __fadd_rn(xx_p_zz, xx_p_zz)), __fadd_rn(yz_m_rx, yz_m_rx),
+                   __fadd_rn(xz_m_ry, xz_m_ry), __fadd_rn(yz_p_rx, yz_p_rx), __fsub_rn(1.f, __fadd_rn(xx_p_yy, xx_p_yy)));
+}
+
 // forward.cu:118-152 — Sigma = (S R)^T (S R); the quaternion is used as given.
 __device__ __forceinline__ void cov3d_from_scale_rot(const float3 scale, float mod, const float4 rot, float* cov3D) {
     M3 S = m3_make(1.0f, 0.0f, 0.0f, 0.0f, 1.0f, 0.0f, 0.0f, 0.0f, 1.0f);
@@ -62,9 +79,7 @@ __device__ __forceinline__ void cov3d_from_scale_rot(const float3 scale, float m
     S.m[1][1] = mod * scale.y;
     S.m[2][2] = mod * scale.z;
     float r = rot.x, x = rot.y, y = rot.z, z = rot.w;
-    M3 R = m3_make(1.f - 2.f * (y * y + z * z), 2.f * (x * y - r * z), 2.f * (x * z + r * y),
-                   2.f * (x * y + r * z), 1.f - 2.f * (x * x + z * z), 2.f * (y * z - r * x),
-                   2.f * (x * z - r * y), 2.f * (y * z + r * x), 1.f - 2.f * (x * x + y * y));
+    M3 R = quat_to_rot(r, x, y, z);
     M3 M = m3_mul(S, R);
     M3 Sigma = m3_mul(m3_transpose(M), M);
     cov3D[0] = Sigma.m[0][0];
@@ -168,14 +183,14 @@ __global__ void __launch_bounds__(256) preprocess_kernel(int P, const float* __r
         }
         float3 cov = cov2d_forward(p_orig, cam.focal_x, cam.focal_y, cam.tanfovx, cam.tanfovy, cov3D, s_view);
 
-        float det = (cov.x * cov.z - cov.y * cov.y);
+        float det = __fmaf_rn(cov.x, cov.z, -__fmul_rn(cov.y, cov.y));  // reference SASS: FMUL b*b ; FFMA a*c - bb
         if (det == 0.0f) break;
         float det_inv = 1.f / det;
         float3 conic = {cov.z * det_inv, -cov.y * det_inv, cov.x * det_inv};
 
         float mid = 0.5f * (cov.x + cov.z);
-        float lambda1 = mid + sqrt(max(0.1f, mid * mid - det));
-        float lambda2 = mid - sqrt(max(0.1f, mid * mid - det));
+        float lambda1 = mid + sqrt(max(0.1f, __fmaf_rn(mid, mid, -det)));
+        float lambda2 = mid - sqrt(max(0.1f, __fmaf_rn(mid, mid, -det)));
         float my_radius = ceil(3.f * sqrt(max(lambda1, lambda2)));
         float2 point_image = {ndc2pix(p_proj.x, cam.W), ndc2pix(p_proj.y, cam.H)};
         uint2 rect_min, rect_max;
@@ -350,9 +365,7 @@ __global__ void __launch_bounds__(256) geom_backward_kernel(
         // ---- cov3D -> scale / rotation (backward.cu:278-341)
         if (has_scales) {
             float r = rot.x, x = rot.y, y = rot.z, z = rot.w;
-            M3 R = m3_make(1.f - 2.f * (y * y + z * z), 2.f * (x * y - r * z), 2.f * (x * z + r * y),
-                           2.f * (x * y + r * z), 1.f - 2.f * (x * x + z * z), 2.f * (y * z - r * x),
-                           2.f * (x * z - r * y), 2.f * (y * z + r * x), 1.f - 2.f * (x * x + y * y));
+            M3 R = quat_to_rot(r, x, y, z);
             const float3 s = {cam.scale_modifier * sc.x, cam.scale_modifier * sc.y, cam.scale_modifier * sc.z};
             M3 S = m3_make(s.x, 0.f, 0.f, 0.f, s.y, 0.f, 0.f, 0.f, s.z);
             M3 M = m3_mul(S, R);

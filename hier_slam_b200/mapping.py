@@ -1,0 +1,77 @@
+"""Keyframe-parallel mapping across the GPUs of one box — a NEW capability: the reference
+optimises ONE randomly chosen keyframe per mapping iteration on one GPU (scripts/hierslam.py:1986-2059).
+
+Partitioning: one process per GPU (torchrun), the Gaussian set replicated, keyframe k of a K-keyframe batch
+rendered by rank k mod G.  Every rank accumulates the gradients of its keyframes directly into ONE flat fp32
+buffer (the leaves' ``.grad`` tensors are views into it, so autograd's accumulation *is* the pack step — there
+is no gather/concat copy), then a single ``all_reduce(SUM)`` over NCCL / NVLink combines the ranks.  The
+correctness criterion is: all-reduced gradient == sum of the K single-keyframe gradients (fp32 reassociation
+only); tests/test_mapping_gloo.py checks it with world_size 2 on CPU (gloo), tests/test_gpu_parity.py on GPU.
+
+Tracking (a sequential 40-100 iteration chain per frame) stays on one GPU: "replicas only".
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, Iterable, List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+
+class FlatParams:
+    """Named fp32 leaves carved out of one flat buffer, with gradients carved out of one flat gradient buffer."""
+
+    def __init__(self, tensors: Dict[str, torch.Tensor]):
+        self.names: List[str] = list(tensors)
+        self.shapes = {k: tuple(v.shape) for k, v in tensors.items()}
+        sizes = [v.numel() for v in tensors.values()]
+        # 64-float (256-B) aligned segments so every view can be consumed with vector loads
+        self.offsets = {}
+        off = 0
+        for k, n in zip(self.names, sizes):
+            self.offsets[k] = off
+            off += (n + 63) // 64 * 64
+        dev = next(iter(tensors.values())).device
+        self.flat = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.flat_grad = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.leaves: Dict[str, torch.Tensor] = {}
+        for k, v in tensors.items():
+            o, n = self.offsets[k], v.numel()
+            self.flat[o:o + n].copy_(v.detach().reshape(-1).float())
+            leaf = self.flat[o:o + n].view(self.shapes[k]).requires_grad_(True)
+            leaf.grad = self.flat_grad[o:o + n].view(self.shapes[k])
+            self.leaves[k] = leaf
+
+    def zero_grad(self) -> None:
+        self.flat_grad.zero_()
+
+    def grad_bytes(self) -> int:
+        return self.flat_grad.numel() * 4
+
+
+def keyframes_of_rank(num_keyframes: int, rank: int, world_size: int) -> List[int]:
+    """keyframe k -> rank k mod G."""
+    return list(range(rank, num_keyframes, world_size))
+
+
+def allreduce_gradients(params: FlatParams, group=None) -> None:
+    """ONE collective per mapping iteration on the flat gradient buffer (SUM, fp32)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(params.flat_grad, op=dist.ReduceOp.SUM, group=group)
+
+
+def mapping_iteration(params: FlatParams, keyframe_losses: Sequence[Callable[[Dict[str, torch.Tensor]], torch.Tensor]],
+                      rank: int = 0, world_size: int = 1, group=None) -> torch.Tensor:
+    """One data-parallel mapping iteration.
+
+    keyframe_losses[k](leaves) renders keyframe k from the shared Gaussian leaves and returns its scalar loss.
+    This rank evaluates keyframes k = rank, rank+G, ...; their gradients accumulate in params.flat_grad; the
+    buffer is then all-reduced.  Returns this rank's summed loss (detached)."""
+    params.zero_grad()
+    total = torch.zeros((), device=params.flat.device)
+    for k in keyframes_of_rank(len(keyframe_losses), rank, world_size):
+        loss = keyframe_losses[k](params.leaves)
+        loss.backward()
+        total = total + loss.detach()
+    allreduce_gradients(params, group)
+    return total

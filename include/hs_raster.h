@@ -100,13 +100,14 @@ int hs_backward(const hs_camera* cam, int P, int S, int num_rendered, const floa
 int hs_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
                     unsigned char* present, void* stream);
 
-/* Measurement aids.  hs_profile_enable(1) makes every subsequent call record CUDA events around each kernel
- * on the launching stream; hs_profile_read() waits for them and returns the elapsed milliseconds of the most
- * recent launch of each stage (-1 = not run): [preprocess, scan, duplicate, sort, ranges, blend_fwd, blend_bwd,
- * geom_bwd].  hs_kernel_launch_count() = kernels of this library launched so far; hs_library_call_count() =
- * CUB device-wide primitives (scan, radix sort) called so far. */
+/* Measurement aids.  After hs_profile_enable(1) every kernel launch of this library is bracketed by its own
+ * CUDA event pair on the launching stream.  hs_profile_read() waits for all recorded pairs and returns, per
+ * stage, the summed elapsed milliseconds and the number of launches since the previous read, in the order
+ * [preprocess, scan, duplicate, sort, ranges, blend_fwd, blend_bwd, geom_bwd].
+ * hs_kernel_launch_count() = kernels of this library launched so far; hs_library_call_count() = CUB
+ * device-wide primitives (scan, radix sort) called so far. */
 int hs_profile_enable(int on);
-int hs_profile_read(float ms[8]);
+int hs_profile_read(float total_ms[8], int count[8]);
 long long hs_kernel_launch_count(void);
 long long hs_library_call_count(void);
 
