@@ -293,3 +293,38 @@ def test_public_api_autograd_and_edge_cases():
                                                   opacities=sc["opacities"], colors_precomp=sc["colors_precomp"],
                                                   scales=sc["scales"], rotations=sc["rotations"],
                                                   semantics_precomp=sc["semantics_precomp"][:, :5].contiguous())
+
+
+def test_keyframe_parallel_mapping_gradient_sum():
+    """SURVEY.md section 8e criterion on one GPU: the flat gradient buffer after a K-keyframe mapping iteration
+    equals the sum of the K single-keyframe gradients (world_size 1; the 2-rank logic is tested with gloo)."""
+    import diff_gaussian_rasterization as dgr
+    from hier_slam_b200.mapping import FlatParams, mapping_iteration
+    from hier_slam_b200.scene import keyframe_poses
+    cfg = CONFIGS["small"]
+    sc = make_scene(cfg, 7, device="cuda")
+    poses = keyframe_poses(3, seed=2)
+    ug = upstream_grads(cfg, 1, device="cuda")
+
+    def make_loss(k):
+        settings = pt.make_settings(dgr.GaussianRasterizationSettings, cfg, "cuda", w2c=poses[k])
+        r = dgr.GaussianRasterizer_semantic(settings)
+
+        def f(lv):
+            color, radii, sem, depth, median, opac = r(
+                means3D=lv["means3D"], means2D=torch.zeros_like(lv["means3D"]), opacities=lv["opacities"],
+                colors_precomp=lv["colors_precomp"], scales=lv["scales"], rotations=lv["rotations"],
+                semantics_precomp=lv["semantics_precomp"])
+            return (color * ug["color"]).sum() + (sem * ug["semantic"]).sum() + (depth * ug["depth"]).sum()
+        return f
+    losses = [make_loss(k) for k in range(3)]
+    params = FlatParams(sc)
+    mapping_iteration(params, losses, 0, 1)
+    total = params.flat_grad.clone()
+    acc = torch.zeros_like(total)
+    for k in range(3):
+        p1 = FlatParams(sc)
+        mapping_iteration(p1, [losses[k]], 0, 1)
+        acc += p1.flat_grad
+    assert_grads_close(total, acc, "sum of keyframe gradients", tol=1e-5)
+    assert float(total.abs().max()) > 0

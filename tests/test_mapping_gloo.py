@@ -1,0 +1,85 @@
+"""Host-side logic of the keyframe-parallel mapping mode (hier_slam_b200/mapping.py) with world_size 2 on CPU
+(gloo): keyframe k -> rank k mod G, gradients accumulate in ONE flat buffer, ONE all_reduce, and the result
+equals the sum of the K single-keyframe gradients.  The renderer is replaced by a differentiable stand-in (the
+CUDA rasterizer cannot run here); the GPU version of this test lives in tests/test_gpu_parity.py."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from hier_slam_b200.mapping import FlatParams, keyframes_of_rank, mapping_iteration
+
+K = 5
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _scene():
+    g = torch.Generator().manual_seed(0)
+    return dict(means3D=torch.randn(37, 3, generator=g), colors_precomp=torch.rand(37, 3, generator=g),
+                semantics_precomp=torch.rand(37, 7, generator=g), opacities=torch.rand(37, 1, generator=g))
+
+
+def _loss_fns():
+    g = torch.Generator().manual_seed(1)
+    ws = [torch.randn(3, 3, generator=g) for _ in range(K)]
+
+    def make(k):
+        def f(leaves):
+            cam = leaves["means3D"] @ ws[k]
+            return ((cam.sin() * leaves["colors_precomp"]).sum() * leaves["opacities"].mean()
+                    + (leaves["semantics_precomp"] ** 2).sum() * (k + 1))
+        return f
+    return [make(k) for k in range(K)]
+
+
+def _worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    params = FlatParams(_scene())
+    loss = mapping_iteration(params, _loss_fns(), rank, world)
+    out[rank] = (params.flat_grad.clone(), float(loss))
+    dist.destroy_process_group()
+
+
+def test_partition_is_round_robin():
+    assert keyframes_of_rank(8, 0, 1) == list(range(8))
+    assert keyframes_of_rank(8, 1, 2) == [1, 3, 5, 7]
+    assert keyframes_of_rank(8, 3, 4) == [3, 7]
+    assert sorted(sum((keyframes_of_rank(5, r, 2) for r in range(2)), [])) == list(range(5))
+
+
+def test_flat_params_views_share_storage():
+    p = FlatParams(_scene())
+    assert p.flat_grad.numel() == p.flat.numel() and p.flat.numel() % 64 == 0
+    for k, leaf in p.leaves.items():
+        assert leaf.requires_grad and leaf.grad.data_ptr() >= p.flat_grad.data_ptr()
+        assert leaf.data_ptr() % 256 == p.flat.data_ptr() % 256
+    (p.leaves["means3D"].sum() * 2).backward()
+    o = p.offsets["means3D"]
+    assert float(p.flat_grad[o:o + 37 * 3].sum()) == 2 * 37 * 3          # autograd accumulated INTO the flat buffer
+    p.zero_grad()
+    assert float(p.flat_grad.abs().sum()) == 0
+
+
+def test_allreduced_gradient_equals_sum_of_keyframe_gradients():
+    world = 2
+    port = _free_port()
+    with mp.Manager() as m:
+        out = m.dict()
+        mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
+        res = {r: out[r] for r in range(world)}
+    single = FlatParams(_scene())
+    total = mapping_iteration(single, _loss_fns(), 0, 1)
+    for r in range(world):
+        assert torch.allclose(res[r][0], single.flat_grad, rtol=1e-5, atol=1e-6)     # every rank holds the full sum
+    assert abs(sum(res[r][1] for r in range(world)) - float(total)) < 1e-3 * abs(float(total))
