@@ -22,6 +22,7 @@ from . import _lib
 # 'exact' : the mathematically intended gradient.
 SEM_ALPHA_GRAD = os.environ.get("HS_SEM_ALPHA_GRAD", "ref")
 NO_CULL = os.environ.get("HS_NO_CULL", "0") == "1"
+BWD_SIMT = os.environ.get("HS_BWD_SIMT", "0") == "1"   # SIMT blend backward instead of the tensor-core one
 
 _contig_cache: dict = {}   # id(tensor) -> (weakref(tensor), version, contiguous copy)
 
@@ -204,6 +205,8 @@ def _backward(background, means3D, radii, colors, semantics, scales, rotations, 
             rot_c = _f32c(rotations, "rotations", device) if have_scales else None
             cov_c = _f32c(cov3D_precomp, "cov3D_precomp", device) if cov3D_precomp is not None else None
             flags = _lib.HS_SEM_ALPHA_EXACT if SEM_ALPHA_GRAD == "exact" else 0
+            if BWD_SIMT:
+                flags |= _lib.HS_BWD_SIMT
             _lib.check(lib.hs_backward(
                 ctypes.byref(cam), P, S, int(R), _ptr(means3D_c), _ptr(radii), _ptr(colors_c), _ptr(sem_c),
                 _ptr(scales_c), _ptr(rot_c), _ptr(cov_c), _ptr(geomBuffer), _ptr(binningBuffer), _ptr(imageBuffer),

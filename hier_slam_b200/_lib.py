@@ -23,6 +23,7 @@ STAGES = ["preprocess", "scan", "duplicate", "sort", "ranges", "blend_fwd", "ble
 
 HS_SEM_ALPHA_EXACT = 1
 HS_NO_CULL = 2
+HS_BWD_SIMT = 4
 
 
 class HsCamera(Structure):

@@ -36,7 +36,7 @@ static bool g_prof_on = false;
 static std::mutex g_prof_mu;
 static std::vector<ProfRec> g_recs;
 static std::vector<ProfRec> g_free;
-static thread_local int g_open = -1;
+
 static long long g_launches = 0;      // kernels written in this library
 static long long g_lib_calls = 0;     // CUB device-wide primitives (scan, sort)
 void count_launch(int n) { g_launches += n; }
@@ -58,7 +58,7 @@ void prof_begin(int stage, cudaStream_t stream) {
     r.stage = stage;
     cudaEventRecord(r.e0, stream);
     g_recs.push_back(r);
-    g_open = (int)g_recs.size() - 1;
+
 }
 void prof_end(int stage, cudaStream_t stream) {
     if (!g_prof_on) return;

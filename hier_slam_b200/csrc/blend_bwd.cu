@@ -284,6 +284,10 @@ int launch_blend_backward(int S, const Camera& cam, const GeomView& g, const Bin
                           float* dL_dcolors, float* dL_dsemantics, float* dL_ddepths, int flags,
                           cudaStream_t stream, bool debug) {
     const bool exact = (flags & HS_FLAG_SEM_ALPHA_EXACT) != 0 && S > 0 && dL_sem != nullptr;
+    if (!exact && !(flags & HS_FLAG_BWD_SHUFFLE) && S <= 74)  // S = 102 would not fit in shared memory
+        return launch_blend_backward_mma(S, cam, g, b, img, bg, colors, dL_color, dL_sem, dL_depth, dL_median,
+                                         dL_opacity, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolors, dL_dsemantics,
+                                         dL_ddepths, stream, debug);
 #define HS_BWD_CASE(SV)                                                                                          \
     case SV:                                                                                                     \
         if (exact)                                                                                               \

@@ -1,0 +1,385 @@
+// Backward of the alpha compositing, tensor-core version (default path; reference behaviour:
+// cuda_rasterizer/backward.cu:669-899 / :472-666 with quirk Q1 in its observable form, see blend_bwd.cu for the
+// SIMT version that also implements the 'exact' semantic gradient).
+//
+// Per (tile, Gaussian j) the backward needs sums over the tile's pixels.  All of them are contractions:
+//     dL/dfeat[j][c]  = sum_pix w[j,pix] * dL/dout[pix][c]          c in {sem 0..S-1, r, g, b, depth, silhouette}
+//     moments[j][m]   = sum_pix g[j,pix] * phi_m(pix)               phi = {1, x, y, x^2, x y, y^2} (tile-centred)
+// with w = alpha * T_front and g = dL/dG * G.  The 2D-mean, conic and opacity gradients are closed-form functions of
+// the six moments (dx = x_j - x, so sum g dx^2 = x_j^2 M0 - 2 x_j M1 + M3, ...).  Each warp owns a 16x2 pixel strip:
+//   phase 1 (SIMT, one pixel per lane): walk 16 Gaussians back to front exactly like the reference (same alpha / T
+//            arithmetic), write w and g into two per-warp shared-memory matrices [16][32];
+//   phase 2 (tensor cores): D[16 Gaussians][8 channels] += A[16][8 pixels] * B[8 pixels][8 channels] with
+//            mma.sync.m16n8k8 TF32 and the 3xTF32 split (a_hi*b_hi + a_lo*b_hi + a_hi*b_lo, fp32 accumulate), so the
+//            result keeps fp32 accuracy (the moment basis is exactly representable in TF32, two products suffice);
+//   then     every warp stores its D tiles into a warp-private partial tile (no shared-memory atomics: fp32 atomicAdd on
+//            shared memory is a CAS loop), and once per round all 256 threads sum the 8 partials and flush each
+//            (tile, Gaussian, channel) ONCE to global memory with coalesced atomics.
+// This replaces the (S+10)-value warp shuffle reduction of the SIMT version -- 64 % of a step in round 1 -- by
+// ~8 tensor instructions per (warp, Gaussian).
+#include "hs_common.cuh"
+
+namespace hs {
+
+template <int S>
+struct MmaCfg {
+    static constexpr int NF = S + 5;                 // sem[S] r g b depth silhouette
+    static constexpr int NBF = (NF + 7) / 8;         // feature n-tiles
+    static constexpr int KA = 8 * NBF + 8;           // + one n-tile of moments
+    static constexpr bool B_IN_REGS = (NBF <= 4);    // dL fragments live in registers for S <= 27
+    static constexpr int DS = 8 * NBF + ((8 - (8 * NBF) % 32 + 32) % 32);  // smem dL row stride == 8 (mod 32)
+    static constexpr int BATCH = B_IN_REGS ? 32 : 16;  // Gaussians staged per round (multiple of the 16-row MMA tile)
+    static constexpr int WS = 36;                    // row stride of the per-warp w / g matrices (conflict-free)
+};
+
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t a0, const uint32_t a1, const uint32_t a2,
+                                         const uint32_t a3, const uint32_t b0, const uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+// TF32 keeps the upper 19 bits; the remainder is exactly representable in fp32.
+__device__ __forceinline__ float tf32_lo(const float x) {
+    return x - __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+}
+
+template <int S>
+__global__ void __launch_bounds__(256, (MmaCfg<S>::B_IN_REGS ? 2 : 1)) blend_backward_mma_kernel(
+    const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H, int grid_x,
+    const float* __restrict__ bg_color, const float2* __restrict__ means2D, const float4* __restrict__ conic_opacity,
+    const float* __restrict__ colors, const float* __restrict__ depths, const float* __restrict__ final_Ts,
+    const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dpixels,
+    const float* __restrict__ dL_dpixels_sem, const float* __restrict__ dL_dpixel_depths,
+    const float* __restrict__ dL_dpixel_medians, const float* __restrict__ dL_dpixel_opacitys,
+    float* __restrict__ dL_dmean2D, float* __restrict__ dL_dconic2D, float* __restrict__ dL_dopacity,
+    float* __restrict__ dL_dcolors, float* __restrict__ dL_dsemantics, float* __restrict__ dL_ddepths) {
+    using Cfg = MmaCfg<S>;
+    constexpr int B = Cfg::BATCH, NF = Cfg::NF, NBF = Cfg::NBF, KA = Cfg::KA, WS = Cfg::WS, DS = Cfg::DS;
+    constexpr bool BREG = Cfg::B_IN_REGS;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4* s_co = reinterpret_cast<float4*>(smem_raw);          // [B]
+    float4* s_feat = s_co + B;                                   // [B] r g b depth
+    float* s_part = reinterpret_cast<float*>(s_feat + B);        // [8 warps][B][KA] warp-private partial sums
+    float* s_w = s_part + 8 * B * KA;                            // [8 warps][16][WS]
+    float* s_g = s_w + 8 * 16 * WS;                              // [8 warps][16][WS]
+    float2* s_xy = reinterpret_cast<float2*>(s_g + 8 * 16 * WS); // [B]
+    int* s_id = reinterpret_cast<int*>(s_xy + B);                // [B]
+    uint32_t* s_valid = reinterpret_cast<uint32_t*>(s_id + B);   // [8] rows of s_part each warp wrote this round
+    float* s_dL = reinterpret_cast<float*>(s_valid + 8);         // [256][DS]   (only when !BREG)
+    __shared__ int s_maxc;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tile_x = blockIdx.x, tile_y = blockIdx.y;
+    const uint32_t px = tile_x * HS_TILE_X + (lane & 15);
+    const uint32_t py = tile_y * HS_TILE_Y + 2 * warp + (lane >> 4);
+    const uint32_t pix_id = W * py + px;
+    const float2 pixf = {(float)px, (float)py};
+    const bool inside = px < (uint32_t)W && py < (uint32_t)H;
+    const uint2 range = ranges[tile_y * grid_x + tile_x];
+    const size_t HW = (size_t)H * W;
+
+    const float T_final = inside ? final_Ts[pix_id] : 0;
+    float T = T_final;
+    const int last_contributor = inside ? (int)n_contrib[pix_id] : 0;
+
+    if (tid == 0) s_maxc = 0;
+    __syncthreads();
+    {
+        int m = last_contributor;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (lane == 0 && m > 0) atomicMax(&s_maxc, m);
+    }
+    __syncthreads();
+    const int total = min(s_maxc, (int)(range.y - range.x));
+    if (total <= 0) return;
+
+    // upstream-gradient plane of feature channel c (nullptr = treated as zero): sem[S] r g b depth silhouette
+    auto plane_of = [&](int c) -> const float* {
+        if (c < S) return dL_dpixels_sem ? dL_dpixels_sem + (size_t)c * HW : nullptr;
+        if (c < S + 3) return dL_dpixels ? dL_dpixels + (size_t)(c - S) * HW : nullptr;
+        if (c == S + 3) return dL_dpixel_depths;
+        if (c == S + 4) return dL_dpixel_opacitys;
+        return nullptr;
+    };
+    // global pixel index of pixel p (0..31) of this warp's 16x2 strip, -1 outside the image
+    auto pixel_of = [&](int p) -> int {
+        const uint32_t x = tile_x * HS_TILE_X + (p & 15), y = tile_y * HS_TILE_Y + 2 * warp + (p >> 4);
+        return (x < (uint32_t)W && y < (uint32_t)H) ? (int)(W * y + x) : -1;
+    };
+
+    // this lane's own pixel: what the alpha-gradient recurrence needs
+    float dL_rgb[3] = {0.f, 0.f, 0.f}, dL_depth = 0.f, dL_median = 0.f, dL_op = 0.f;
+    if (inside) {
+        if (dL_dpixels) {
+#pragma unroll
+            for (int i = 0; i < 3; i++) dL_rgb[i] = dL_dpixels[i * HW + pix_id];
+        }
+        if (dL_dpixel_depths) dL_depth = dL_dpixel_depths[pix_id];
+        if (dL_dpixel_medians) dL_median = dL_dpixel_medians[pix_id];
+        if (dL_dpixel_opacitys) dL_op = dL_dpixel_opacitys[pix_id];
+    }
+    float bg_dot_dpixel = 0;
+#pragma unroll
+    for (int i = 0; i < 3; i++) bg_dot_dpixel += bg_color[i] * dL_rgb[i];
+
+    // B operands (k = pixel, n = channel).  Fragment element (kb, nb, h): pixel 8 kb + lane%4 + 4 h, channel 8 nb + lane/4.
+    const int qk = lane & 3, qn = lane >> 2;
+    float bfrag[BREG ? NBF * 8 : 1];
+    if (BREG) {
+        int pid[8];
+#pragma unroll
+        for (int kb = 0; kb < 4; kb++)
+#pragma unroll
+            for (int h = 0; h < 2; h++) pid[kb * 2 + h] = pixel_of(8 * kb + qk + 4 * h);
+#pragma unroll
+        for (int nb = 0; nb < NBF; nb++) {
+            const float* pl = plane_of(8 * nb + qn);
+#pragma unroll
+            for (int e = 0; e < 8; e++) bfrag[nb * 8 + e] = (pl != nullptr && pid[e] >= 0) ? __ldg(pl + pid[e]) : 0.f;
+        }
+    } else {
+        float* my = s_dL + (size_t)(warp * 32) * DS;
+        const int id = pixel_of(lane);
+        for (int c = 0; c < 8 * NBF; c++) {
+            const float* pl = plane_of(c);
+            my[lane * DS + c] = (pl != nullptr && id >= 0) ? __ldg(pl + id) : 0.f;
+        }
+    }
+    // moment basis for this lane's fragment pixels: column qn of {1, x, y, x^2, xy, y^2, 0, 0}, tile-centred
+    float mfrag[8];
+#pragma unroll
+    for (int kb = 0; kb < 4; kb++)
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int p = 8 * kb + qk + 4 * h;
+            const float x = (float)(p & 15) - 7.5f, y = (float)(2 * warp + (p >> 4)) - 7.5f;
+            mfrag[kb * 2 + h] = qn == 0 ? 1.f : qn == 1 ? x : qn == 2 ? y : qn == 3 ? x * x : qn == 4 ? x * y
+                                : qn == 5 ? y * y : 0.f;
+        }
+
+    float* wm = s_w + warp * 16 * WS;
+    float* gm = s_g + warp * 16 * WS;
+    float last_alpha = 0.f, last_q = 0.f, accum_q = 0.f;
+
+    const int rounds = (total + B - 1) / B;
+    for (int i = 0; i < rounds; i++) {
+        __syncthreads();  // previous batch flushed
+        const int nb_ = min(B, total - i * B);
+        if (tid < nb_) {
+            const int id = point_list[range.x + (total - 1 - i * B - tid)];
+            s_id[tid] = id;
+            s_xy[tid] = means2D[id];
+            s_co[tid] = conic_opacity[id];
+            s_feat[tid] = {__ldg(colors + 3 * (size_t)id), __ldg(colors + 3 * (size_t)id + 1),
+                           __ldg(colors + 3 * (size_t)id + 2), depths[id]};
+        }
+        __syncthreads();
+        uint32_t valid_rows = 0;   // warp-uniform: rows (Gaussians of this round) this warp contributed to
+
+        for (int c0 = 0; c0 < nb_; c0 += 16) {
+                        // ---------------- phase 1: 16 Gaussians, back to front ------------------------------------------------
+            // (a) alpha of 8 Gaussians at a time, branch-free: eight independent dependency chains per lane (ILP);
+            // (b) the sequential transmittance / colour-behind recurrences, skipped per Gaussian by a warp vote.
+            uint32_t act_mask = 0;
+#pragma unroll 1   // keep the loop rolled: the kernel must stay inside the instruction cache
+            for (int sub = 0; sub < 2; sub++) {
+                const int jb = c0 + 8 * sub;
+                if (jb >= nb_) break;
+                float oG[8];
+                uint32_t abits = 0;
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int j = min(jb + u, nb_ - 1);
+                    const float2 xy = s_xy[j];
+                    const float2 d = {xy.x - pixf.x, xy.y - pixf.y};
+                    const float4 con_o = s_co[j];
+                    const float power = gauss_power(d, con_o);
+                    const float og = con_o.w * exp(power);
+                    const int gi = total - 1 - i * B - (jb + u);
+                    const bool active = (jb + u < nb_) && (gi < last_contributor) && !(power > 0.0f) &&
+                                        !(min(0.99f, og) < 1.0f / 255.0f);
+                    oG[u] = og;
+                    abits |= (active ? 1u : 0u) << u;
+                }
+                const uint32_t any_bits = __reduce_or_sync(0xffffffffu, abits);
+                act_mask |= any_bits << (8 * sub);
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    if (!((any_bits >> u) & 1)) continue;   // warp-uniform
+                    const int j = jb + u;
+                    const bool act = (abits >> u) & 1;
+                    const float alpha = min(0.99f, oG[u]);
+                    // same IEEE division as the reference (backward.cu:815): the reconstructed transmittance decides
+                    // which Gaussian receives the median-depth gradient, so it is kept bit-identical
+                    const float test_T = T / (1.f - alpha);
+                    const float4 f = s_feat[j];
+                    float q = f.x * dL_rgb[0] + f.y * dL_rgb[1] + f.z * dL_rgb[2];
+                    q = fmaf(f.w, dL_depth, q);
+                    q += dL_op;
+                    const float acc_new = last_alpha * last_q + (1.f - last_alpha) * accum_q;
+                    float dL_dalpha = (q - acc_new) * test_T;
+                    if (bg_dot_dpixel != 0.f) dL_dalpha -= __fdividef(T_final, 1.f - alpha) * bg_dot_dpixel;
+                    if (act && test_T > 0.5f && T < 0.5 && dL_median != 0.f)
+                        atomicAdd(dL_ddepths + s_id[j], dL_median);   // the Gaussian that crossed T = 0.5 (quirk Q4)
+                    wm[(8 * sub + u) * WS + lane] = act ? alpha * test_T : 0.f;
+                    gm[(8 * sub + u) * WS + lane] = act ? dL_dalpha * oG[u] : 0.f;   // dL/dG * G = (o dL/dalpha) G
+                    accum_q = act ? acc_new : accum_q;
+                    last_q = act ? q : last_q;
+                    last_alpha = act ? alpha : last_alpha;
+                    T = act ? test_T : T;
+                }
+            }
+            __syncwarp();
+            valid_rows |= act_mask << c0;
+            // ---------------- phase 2: D[16 x 8] tiles on the tensor cores ---------------------------------------
+            const bool v0 = (act_mask >> qn) & 1, v1 = (act_mask >> (qn + 8)) & 1;
+            float acc[NBF + 1][4];
+#pragma unroll
+            for (int nb = 0; nb <= NBF; nb++)
+#pragma unroll
+                for (int r = 0; r < 4; r++) acc[nb][r] = 0.f;
+            if (act_mask != 0) {
+#pragma unroll
+            for (int kb = 0; kb < 4; kb++) {
+                const int col = 8 * kb + qk;
+                const float a0 = v0 ? wm[qn * WS + col] : 0.f, a1 = v1 ? wm[(qn + 8) * WS + col] : 0.f;
+                const float a2 = v0 ? wm[qn * WS + col + 4] : 0.f, a3 = v1 ? wm[(qn + 8) * WS + col + 4] : 0.f;
+                const uint32_t ah0 = __float_as_uint(a0), ah1 = __float_as_uint(a1), ah2 = __float_as_uint(a2),
+                               ah3 = __float_as_uint(a3);
+                const uint32_t al0 = __float_as_uint(tf32_lo(a0)), al1 = __float_as_uint(tf32_lo(a1)),
+                               al2 = __float_as_uint(tf32_lo(a2)), al3 = __float_as_uint(tf32_lo(a3));
+#pragma unroll
+                for (int nb = 0; nb < NBF; nb++) {
+                    float b0, b1;
+                    if (BREG) {
+                        b0 = bfrag[(nb * 4 + kb) * 2];
+                        b1 = bfrag[(nb * 4 + kb) * 2 + 1];
+                    } else {
+                        const float* my = s_dL + (size_t)(warp * 32 + col) * DS + 8 * nb + qn;
+                        b0 = my[0];
+                        b1 = my[4 * DS];
+                    }
+                    const uint32_t bh0 = __float_as_uint(b0), bh1 = __float_as_uint(b1);
+                    mma_tf32(acc[nb], ah0, ah1, ah2, ah3, bh0, bh1);
+                    mma_tf32(acc[nb], al0, al1, al2, al3, bh0, bh1);
+                    mma_tf32(acc[nb], ah0, ah1, ah2, ah3, __float_as_uint(tf32_lo(b0)), __float_as_uint(tf32_lo(b1)));
+                }
+                // moments: the basis is exact in TF32, two products suffice
+                const float e0 = v0 ? gm[qn * WS + col] : 0.f, e1 = v1 ? gm[(qn + 8) * WS + col] : 0.f;
+                const float e2 = v0 ? gm[qn * WS + col + 4] : 0.f, e3 = v1 ? gm[(qn + 8) * WS + col + 4] : 0.f;
+                const uint32_t mb0 = __float_as_uint(mfrag[kb * 2]), mb1 = __float_as_uint(mfrag[kb * 2 + 1]);
+                mma_tf32(acc[NBF], __float_as_uint(e0), __float_as_uint(e1), __float_as_uint(e2), __float_as_uint(e3),
+                         mb0, mb1);
+                mma_tf32(acc[NBF], __float_as_uint(tf32_lo(e0)), __float_as_uint(tf32_lo(e1)),
+                         __float_as_uint(tf32_lo(e2)), __float_as_uint(tf32_lo(e3)), mb0, mb1);
+            }
+            }
+            // D fragment: rows qn / qn+8, columns 2 qk, 2 qk + 1 of each n-tile -> this warp's private partial tile.
+            // Every row of the chunk is written (rows without contribution hold exact zeros: their A rows were zero),
+            // so the reduction below needs no per-warp validity tests.
+            float* pt = s_part + (size_t)(warp * B + c0) * KA + 2 * qk;
+#pragma unroll
+            for (int nb = 0; nb <= NBF; nb++) {
+                *reinterpret_cast<float2*>(pt + qn * KA + 8 * nb) = make_float2(acc[nb][0], acc[nb][1]);
+                *reinterpret_cast<float2*>(pt + (qn + 8) * KA + 8 * nb) = make_float2(acc[nb][2], acc[nb][3]);
+            }
+            __syncwarp();  // wm / gm are rewritten by the next chunk
+        }
+        if (lane == 0) s_valid[warp] = valid_rows;
+        __syncthreads();
+
+        // ---------------- reduce the 8 warp-private tiles and flush: thread <-> (Gaussian j, column c) -----------------
+        // consecutive threads own consecutive columns -> coalesced global atomics; the 8 moment columns of a row sit in
+        // 8 consecutive lanes of one warp, so the closed-form 2D-mean / conic / opacity terms gather them by shuffle.
+        const float cx = (float)(tile_x * HS_TILE_X) + 7.5f, cy = (float)(tile_y * HS_TILE_Y) + 7.5f;
+        uint32_t any_rows = 0;
+#pragma unroll
+        for (int wv = 0; wv < 8; wv++) any_rows |= s_valid[wv];
+        const int n_chunk_rows = (nb_ + 15) & ~15;   // rows of s_part that were written this round
+#pragma unroll 1
+        for (int it = 0; it < (B * KA + 255) / 256; it++) {
+            const int e = tid + 256 * it;
+            const int j = e / KA, c = e - j * KA;
+            float sum = 0.f;
+            if (j < n_chunk_rows) {
+                float p8[8];
+#pragma unroll
+                for (int wv = 0; wv < 8; wv++) p8[wv] = s_part[(size_t)(wv * B + j) * KA + c];
+                sum = ((p8[0] + p8[1]) + (p8[2] + p8[3])) + ((p8[4] + p8[5]) + (p8[6] + p8[7]));
+            }
+            const bool touched = (j < nb_) && ((any_rows >> j) & 1);
+            const int m = c - 8 * NBF;            // moment index for the last n-tile
+            const int base = lane - (m > 0 ? m : 0);
+            const float M0 = __shfl_sync(0xffffffffu, sum, base), M1 = __shfl_sync(0xffffffffu, sum, base + 1);
+            const float M2 = __shfl_sync(0xffffffffu, sum, base + 2), M3 = __shfl_sync(0xffffffffu, sum, base + 3);
+            const float M4 = __shfl_sync(0xffffffffu, sum, base + 4), M5 = __shfl_sync(0xffffffffu, sum, base + 5);
+            if (!touched) continue;
+            const size_t id = (size_t)s_id[j];
+            if (c < S) atomicAdd(dL_dsemantics + id * S + c, sum);
+            else if (c < S + 3) atomicAdd(dL_dcolors + id * 3 + (c - S), sum);
+            else if (c == S + 3) atomicAdd(dL_ddepths + id, sum);
+            else if (c == S + 4) atomicAdd(dL_dopacity + id, sum);            // sum_pix w dL/d(silhouette)  (quirk Q2)
+            else if (m >= 0 && m < 6) {
+                const float2 xy = s_xy[j];
+                const float4 co = s_co[j];
+                const float xj = xy.x - cx, yj = xy.y - cy;
+                const float sgdx = xj * M0 - M1, sgdy = yj * M0 - M2;  // sum g dx, sum g dy
+                if (m == 0) atomicAdd(dL_dopacity + id, M0 / co.w);           // sum_pix G dL/dalpha
+                else if (m == 1) atomicAdd(dL_dmean2D + id * 3, -(co.x * sgdx + co.y * sgdy) * (0.5f * W));
+                else if (m == 2) atomicAdd(dL_dmean2D + id * 3 + 1, -(co.z * sgdy + co.y * sgdx) * (0.5f * H));
+                else if (m == 3) atomicAdd(dL_dconic2D + id * 4, -0.5f * (xj * xj * M0 - 2.f * xj * M1 + M3));
+                else if (m == 4) atomicAdd(dL_dconic2D + id * 4 + 1, -0.5f * (xj * yj * M0 - xj * M2 - yj * M1 + M4));
+                else atomicAdd(dL_dconic2D + id * 4 + 3, -0.5f * (yj * yj * M0 - 2.f * yj * M2 + M5));
+            }
+        }
+    }
+}
+
+template <int S>
+static int launch_bwd_mma_t(const Camera& cam, const GeomView& g, const BinningView& b, const ImageView& img,
+                            const float* bg, const float* colors, const float* dL_color, const float* dL_sem,
+                            const float* dL_depth, const float* dL_median, const float* dL_opacity, float* dL_dmean2D,
+                            float* dL_dconic, float* dL_dopacity, float* dL_dcolors, float* dL_dsemantics,
+                            float* dL_ddepths, cudaStream_t stream, bool debug) {
+    using Cfg = MmaCfg<S>;
+    size_t smem = (size_t)Cfg::BATCH * (2 * sizeof(float4) + 8 * Cfg::KA * sizeof(float) + sizeof(float2) + sizeof(int)) +
+                  (size_t)2 * 8 * 16 * Cfg::WS * sizeof(float) + 8 * sizeof(uint32_t);
+    if (!Cfg::B_IN_REGS) smem += (size_t)256 * Cfg::DS * sizeof(float);
+    auto k = blend_backward_mma_kernel<S>;
+    HS_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(cam.grid_x, cam.grid_y, 1);
+    prof_begin(ST_BLEND_BWD, stream);
+    k<<<grid, 256, smem, stream>>>(img.ranges, b.point_list, cam.W, cam.H, cam.grid_x, bg, g.means2D, g.conic_opacity,
+                                   colors, g.depths, img.final_T, img.n_contrib, dL_color, dL_sem, dL_depth, dL_median,
+                                   dL_opacity, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolors, dL_dsemantics,
+                                   dL_ddepths);
+    prof_end(ST_BLEND_BWD, stream);
+    HS_LAUNCH_OK(stream, debug);
+    return 0;
+}
+
+int launch_blend_backward_mma(int S, const Camera& cam, const GeomView& g, const BinningView& b, const ImageView& img,
+                              const float* bg, const float* colors, const float* dL_color, const float* dL_sem,
+                              const float* dL_depth, const float* dL_median, const float* dL_opacity,
+                              float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolors,
+                              float* dL_dsemantics, float* dL_ddepths, cudaStream_t stream, bool debug) {
+#define HS_BWDM_CASE(SV)                                                                                        \
+    case SV:                                                                                                    \
+        return launch_bwd_mma_t<SV>(cam, g, b, img, bg, colors, dL_color, dL_sem, dL_depth, dL_median, dL_opacity, \
+                                    dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolors, dL_dsemantics, dL_ddepths,  \
+                                    stream, debug);
+    switch (S) {
+        HS_BWDM_CASE(0)
+        HS_BWDM_CASE(16)
+        HS_BWDM_CASE(26)
+        HS_BWDM_CASE(74)
+        default:
+            set_error("tensor-core blend backward: S=%d is not instantiated (built: 0,16,26,74)", S);
+            return 3;
+    }
+#undef HS_BWDM_CASE
+}
+
+}  // namespace hs

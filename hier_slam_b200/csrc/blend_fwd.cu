@@ -21,29 +21,6 @@ struct FwdCfg {
     static constexpr size_t SMEM = (size_t)BATCH * (sizeof(float2) + 2 * sizeof(float4) + sizeof(int) + FS * sizeof(float));
 };
 
-// Conservative pixel-space box outside of which alpha < 1/255 for this Gaussian (or power > 0).
-// alpha = min(0.99, o * exp(power)) >= 1/255  <=>  power >= -ln(255 o); power = -q/2 with
-// q = A dx^2 + 2 B dx dy + C dy^2, so |dx| <= sqrt(2 tau C / det), |dy| <= sqrt(2 tau A / det).
-// All margins err on the side of keeping the Gaussian; non-finite or degenerate inputs disable the test.
-__device__ __forceinline__ float4 footprint_box(const float2 xy, const float4 co) {
-    const float kInf = __int_as_float(0x7f800000);
-    float4 all = {-kInf, kInf, -kInf, kInf};
-    const float A = co.x, B = co.y, C = co.z, o = co.w;
-    if (!(o >= 0.0039f)) {  // strictly below 1/255 = 0.0039215...: can never pass the alpha test
-        if (o < 0.0039f) return {kInf, -kInf, kInf, -kInf};
-        return all;  // NaN opacity: let the exact test decide
-    }
-    const float tau = __logf(o * 255.0f) + 0.02f;
-    const float ac = A * C, bb = B * B;
-    const float det = (ac - bb) - 1e-6f * (fabsf(ac) + bb);
-    if (!(det > 0.f) || !(A > 0.f) || !(C > 0.f) || !(tau > 0.f)) return all;
-    const float k = 2.0f * tau / det;
-    const float hx = sqrtf(k * C) * 1.001f + 0.01f;
-    const float hy = sqrtf(k * A) * 1.001f + 0.01f;
-    if (!(hx < 1e8f) || !(hy < 1e8f)) return all;
-    return {xy.x - hx, xy.x + hx, xy.y - hy, xy.y + hy};
-}
-
 template <int S, bool MASK>
 __global__ void __launch_bounds__(256) blend_forward_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H, int grid_x,

@@ -228,6 +228,7 @@ int hs_backward(const hs_camera* c, int P, int S, int R, const float* means3D, c
         if (binning_view((char*)binning_state, (size_t)R, &b)) return 2;
         int kflags = 0;
         if (flags & HS_SEM_ALPHA_EXACT) kflags |= HS_FLAG_SEM_ALPHA_EXACT;
+        if (flags & HS_BWD_SIMT) kflags |= HS_FLAG_BWD_SHUFFLE;
         rc = launch_blend_backward(S, cam, g, b, img, c->bg, colors, semantics, dL_dout_color, dL_dout_semantic,
                                    dL_dout_depth, dL_dout_median_depth, dL_dout_opacity, dL_dmeans2D, dL_dconic,
                                    dL_dopacity, dL_dcolors, dL_dsemantics, dL_ddepths, kflags, stream, debug);

@@ -100,6 +100,11 @@ int launch_blend_backward(int S, const Camera& cam, const GeomView& g, const Bin
                           const float* dL_opacity, float* dL_dmean2D, float* dL_dconic, float* dL_dopacity,
                           float* dL_dcolors, float* dL_dsemantics, float* dL_ddepths, int flags,
                           cudaStream_t stream, bool debug);
+int launch_blend_backward_mma(int S, const Camera& cam, const GeomView& g, const BinningView& b, const ImageView& img,
+                              const float* bg, const float* colors, const float* dL_color, const float* dL_sem,
+                              const float* dL_depth, const float* dL_median, const float* dL_opacity,
+                              float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolors,
+                              float* dL_dsemantics, float* dL_ddepths, cudaStream_t stream, bool debug);
 int launch_geom_backward(int P, const float* means3D, const int* radii, const float* scales,
                          const float* rotations, const float* cov3D_precomp, const Camera& cam,
                          const float* dL_dmean2D, const float* dL_dconic, const float* dL_ddepths,
@@ -116,13 +121,35 @@ __device__ __forceinline__ float gauss_power(const float2 d, const float4 con_o)
     const float q = __fmaf_rn(d.x, __fmul_rn(d.x, con_o.x), __fmul_rn(d.y, __fmul_rn(d.y, con_o.z)));
     return __fmaf_rn(q, -0.5f, -__fmul_rn(d.y, __fmul_rn(d.x, con_o.y)));
 }
+// Conservative pixel-space box outside of which alpha < 1/255 for this Gaussian (or power > 0).
+// alpha = min(0.99, o * exp(power)) >= 1/255  <=>  power >= -ln(255 o); power = -q/2 with
+// q = A dx^2 + 2 B dx dy + C dy^2, so |dx| <= sqrt(2 tau C / det), |dy| <= sqrt(2 tau A / det).
+// All margins err on the side of keeping the Gaussian; non-finite or degenerate inputs disable the test.
+__device__ __forceinline__ float4 footprint_box(const float2 xy, const float4 co) {
+    const float kInf = __int_as_float(0x7f800000);
+    float4 all = {-kInf, kInf, -kInf, kInf};
+    const float A = co.x, B = co.y, C = co.z, o = co.w;
+    if (!(o >= 0.0039f)) {  // strictly below 1/255 = 0.0039215...: can never pass the alpha test
+        if (o < 0.0039f) return {kInf, -kInf, kInf, -kInf};
+        return all;  // NaN opacity: let the exact test decide
+    }
+    const float tau = __logf(o * 255.0f) + 0.02f;
+    const float ac = A * C, bb = B * B;
+    const float det = (ac - bb) - 1e-6f * (fabsf(ac) + bb);
+    if (!(det > 0.f) || !(A > 0.f) || !(C > 0.f) || !(tau > 0.f)) return all;
+    const float k = 2.0f * tau / det;
+    const float hx = sqrtf(k * C) * 1.001f + 0.01f;
+    const float hy = sqrtf(k * A) * 1.001f + 0.01f;
+    if (!(hx < 1e8f) || !(hy < 1e8f)) return all;
+    return {xy.x - hx, xy.x + hx, xy.y - hy, xy.y + hy};
+}
 #endif
 
 // flags shared by the blend kernels
 enum : int {
     HS_FLAG_SEM_ALPHA_EXACT = 1,   // semantic channels contribute to dL/dalpha (reference quirk Q1 off)
     HS_FLAG_NO_CULL = 2,           // disable the conservative per-warp footprint test
-    HS_FLAG_BWD_SHUFFLE = 4,       // backward: plain warp-shuffle reduction instead of the default path
+    HS_FLAG_BWD_SHUFFLE = 4,       // backward: SIMT warp-shuffle reduction instead of the tensor-core path
 };
 
 }  // namespace hs

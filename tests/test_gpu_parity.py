@@ -236,6 +236,14 @@ def test_full_size_properties_c2():
     g1, g2, g12 = (pt.run_backward(C, settings, scene, f, u) for u in (u1, u2, u12))
     for k in g1:
         assert_grads_close(g12[k], 2.0 * g1[k] + g2[k], f"linearity of {k}", tol=1e-4)
+    # tensor-core (3xTF32) backward == SIMT backward to fp32 accuracy
+    C.BWD_SIMT = True
+    try:
+        g1s = pt.run_backward(C, settings, scene, f, u1)
+    finally:
+        C.BWD_SIMT = False
+    for k in g1:
+        assert_grads_close(g1[k], g1s[k], f"mma-vs-simt {k}", tol=2e-5)
     # None upstream gradients == zero upstream gradients
     z = {k: (v if k in ("color", "depth") else None) for k, v in u1.items()}
     zz = {k: (v if k in ("color", "depth") else torch.zeros_like(v)) for k, v in u1.items()}

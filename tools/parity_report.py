@@ -120,6 +120,11 @@ def report(key, iters, P=None, S=None, semantic=True):
         newC.SEM_ALPHA_GRAD = "exact"
         out["t_new_bwd_exact"] = timeit(lambda: pt.run_backward(newC, settings, scene, f_new, grads, semantic), iters)
         newC.SEM_ALPHA_GRAD = "ref"
+        newC.BWD_SIMT = True
+        out["t_new_bwd_simt"] = timeit(lambda: pt.run_backward(newC, settings, scene, f_new, grads, semantic), iters)
+        g_simt = pt.run_backward(newC, settings, scene, f_new, grads, semantic)
+        newC.BWD_SIMT = False
+        out["grad_err_mma_vs_simt"] = {k: pt.grad_err(g_new[k], g_simt[k]) for k in g_new}
         newC.NO_CULL = True
         out["t_new_fwd_nocull"] = timeit(lambda: pt.run_forward(newC, settings, scene, semantic), iters)
         newC.NO_CULL = False
