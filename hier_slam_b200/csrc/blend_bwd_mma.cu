@@ -44,8 +44,11 @@ __device__ __forceinline__ float tf32_lo(const float x) {
     return x - __uint_as_float(__float_as_uint(x) & 0xffffe000u);
 }
 
-template <int S>
-__global__ void __launch_bounds__(256, (MmaCfg<S>::B_IN_REGS ? 2 : 1)) blend_backward_mma_kernel(
+// NW = warps per CTA: a CTA owns a 16 x (2 NW) pixel slab of a tile (NW = 8: the whole tile; NW = 4: half a tile,
+// two CTAs walk the same Gaussian list).  Smaller CTAs give the register / shared-memory limited kernel a finer
+// occupancy granularity and cheaper barriers.
+template <int S, int NW>
+__global__ void __launch_bounds__(32 * NW, (MmaCfg<S>::B_IN_REGS ? (16 / NW) : 1)) blend_backward_mma_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H, int grid_x,
     const float* __restrict__ bg_color, const float2* __restrict__ means2D, const float4* __restrict__ conic_opacity,
     const float* __restrict__ colors, const float* __restrict__ depths, const float* __restrict__ final_Ts,
@@ -60,19 +63,21 @@ __global__ void __launch_bounds__(256, (MmaCfg<S>::B_IN_REGS ? 2 : 1)) blend_bac
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4* s_co = reinterpret_cast<float4*>(smem_raw);          // [B]
     float4* s_feat = s_co + B;                                   // [B] r g b depth
-    float* s_part = reinterpret_cast<float*>(s_feat + B);        // [8 warps][B][KA] warp-private partial sums
-    float* s_w = s_part + 8 * B * KA;                            // [8 warps][16][WS]
-    float* s_g = s_w + 8 * 16 * WS;                              // [8 warps][16][WS]
-    float2* s_xy = reinterpret_cast<float2*>(s_g + 8 * 16 * WS); // [B]
+    float* s_part = reinterpret_cast<float*>(s_feat + B);        // [NW warps][B][KA] warp-private partial sums
+    float* s_w = s_part + NW * B * KA;                           // [NW warps][16][WS]
+    float* s_g = s_w + NW * 16 * WS;                             // [NW warps][16][WS]
+    float2* s_xy = reinterpret_cast<float2*>(s_g + NW * 16 * WS); // [B]
     int* s_id = reinterpret_cast<int*>(s_xy + B);                // [B]
-    uint32_t* s_valid = reinterpret_cast<uint32_t*>(s_id + B);   // [8] rows of s_part each warp wrote this round
-    float* s_dL = reinterpret_cast<float*>(s_valid + 8);         // [256][DS]   (only when !BREG)
+    uint32_t* s_valid = reinterpret_cast<uint32_t*>(s_id + B);   // [NW] rows of s_part each warp wrote this round
+    float* s_dL = reinterpret_cast<float*>(s_valid + 8);         // [32 NW][DS]   (only when !BREG)
     __shared__ int s_maxc;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int tile_x = blockIdx.x, tile_y = blockIdx.y;
+    constexpr int SLABS = 8 / NW;                                // CTAs per tile
+    const int tile_x = blockIdx.x, tile_y = blockIdx.y / SLABS;
+    const int row0 = (blockIdx.y % SLABS) * (2 * NW) + 2 * warp;   // first tile row of this warp's 16x2 strip
     const uint32_t px = tile_x * HS_TILE_X + (lane & 15);
-    const uint32_t py = tile_y * HS_TILE_Y + 2 * warp + (lane >> 4);
+    const uint32_t py = tile_y * HS_TILE_Y + row0 + (lane >> 4);
     const uint32_t pix_id = W * py + px;
     const float2 pixf = {(float)px, (float)py};
     const bool inside = px < (uint32_t)W && py < (uint32_t)H;
@@ -105,7 +110,7 @@ __global__ void __launch_bounds__(256, (MmaCfg<S>::B_IN_REGS ? 2 : 1)) blend_bac
     };
     // global pixel index of pixel p (0..31) of this warp's 16x2 strip, -1 outside the image
     auto pixel_of = [&](int p) -> int {
-        const uint32_t x = tile_x * HS_TILE_X + (p & 15), y = tile_y * HS_TILE_Y + 2 * warp + (p >> 4);
+        const uint32_t x = tile_x * HS_TILE_X + (p & 15), y = tile_y * HS_TILE_Y + row0 + (p >> 4);
         return (x < (uint32_t)W && y < (uint32_t)H) ? (int)(W * y + x) : -1;
     };
 
@@ -154,11 +159,20 @@ __global__ void __launch_bounds__(256, (MmaCfg<S>::B_IN_REGS ? 2 : 1)) blend_bac
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             const int p = 8 * kb + qk + 4 * h;
-            const float x = (float)(p & 15) - 7.5f, y = (float)(2 * warp + (p >> 4)) - 7.5f;
+            const float x = (float)(p & 15) - 7.5f, y = (float)(row0 + (p >> 4)) - 7.5f;
             mfrag[kb * 2 + h] = qn == 0 ? 1.f : qn == 1 ? x : qn == 2 ? y : qn == 3 ? x * x : qn == 4 ? x * y
                                 : qn == 5 ? y * y : 0.f;
         }
 
+    // flush destinations of the feature columns this lane owns (column c = 32 k + lane): pointer + row stride
+    float* feat_dst[(NBF * 8 + 31) / 32];
+    int feat_stride[(NBF * 8 + 31) / 32];
+#pragma unroll
+    for (int k = 0; k < (NBF * 8 + 31) / 32; k++) {
+        const int c = 32 * k + lane;
+        feat_dst[k] = c < S ? dL_dsemantics + c : c < S + 3 ? dL_dcolors + (c - S) : c == S + 3 ? dL_ddepths : dL_dopacity;
+        feat_stride[k] = c < S ? S : c < S + 3 ? 3 : 1;
+    }
     float* wm = s_w + warp * 16 * WS;
     float* gm = s_g + warp * 16 * WS;
     float last_alpha = 0.f, last_q = 0.f, accum_q = 0.f;
@@ -296,62 +310,75 @@ __global__ void __launch_bounds__(256, (MmaCfg<S>::B_IN_REGS ? 2 : 1)) blend_bac
         const float cx = (float)(tile_x * HS_TILE_X) + 7.5f, cy = (float)(tile_y * HS_TILE_Y) + 7.5f;
         uint32_t any_rows = 0;
 #pragma unroll
-        for (int wv = 0; wv < 8; wv++) any_rows |= s_valid[wv];
-        const int n_chunk_rows = (nb_ + 15) & ~15;   // rows of s_part that were written this round
+        for (int wv = 0; wv < NW; wv++) any_rows |= s_valid[wv];
+        // pass A, feature columns: lane <-> column (destination pointer and row stride are fixed per lane, so the loop
+        // body is divergence-free), warp <-> Gaussian row.
 #pragma unroll 1
-        for (int it = 0; it < (B * KA + 255) / 256; it++) {
-            const int e = tid + 256 * it;
-            const int j = e / KA, c = e - j * KA;
-            float sum = 0.f;
-            if (j < n_chunk_rows) {
-                float p8[8];
+        for (int j = warp; j < nb_; j += NW) {
+            if (!((any_rows >> j) & 1)) continue;   // warp-uniform
+            const size_t id = (size_t)s_id[j];
 #pragma unroll
-                for (int wv = 0; wv < 8; wv++) p8[wv] = s_part[(size_t)(wv * B + j) * KA + c];
-                sum = ((p8[0] + p8[1]) + (p8[2] + p8[3])) + ((p8[4] + p8[5]) + (p8[6] + p8[7]));
+            for (int cb = 0; cb < NBF * 8; cb += 32) {
+                const int c = cb + lane;
+                if (c < NF) {
+                    float p8[NW];
+#pragma unroll
+                    for (int wv = 0; wv < NW; wv++) p8[wv] = s_part[(size_t)(wv * B + j) * KA + c];
+#pragma unroll
+                    for (int st = 1; st < NW; st <<= 1)
+#pragma unroll
+                        for (int wv = 0; wv + st < NW; wv += 2 * st) p8[wv] += p8[wv + st];
+                    atomicAdd(feat_dst[cb / 32] + id * feat_stride[cb / 32], p8[0]);
+                }
             }
-            const bool touched = (j < nb_) && ((any_rows >> j) & 1);
-            const int m = c - 8 * NBF;            // moment index for the last n-tile
-            const int base = lane - (m > 0 ? m : 0);
+        }
+        // pass B, moments: 8 consecutive lanes <-> the moment columns of one Gaussian
+#pragma unroll 1
+        for (int e = tid; e < nb_ * 8; e += 32 * NW) {
+            const int j = e >> 3, m = e & 7;
+            float p8[NW];
+#pragma unroll
+            for (int wv = 0; wv < NW; wv++) p8[wv] = s_part[(size_t)(wv * B + j) * KA + 8 * NBF + m];
+#pragma unroll
+            for (int st = 1; st < NW; st <<= 1)
+#pragma unroll
+                for (int wv = 0; wv + st < NW; wv += 2 * st) p8[wv] += p8[wv + st];
+            const float sum = p8[0];
+            const int base = lane & ~7;
             const float M0 = __shfl_sync(0xffffffffu, sum, base), M1 = __shfl_sync(0xffffffffu, sum, base + 1);
             const float M2 = __shfl_sync(0xffffffffu, sum, base + 2), M3 = __shfl_sync(0xffffffffu, sum, base + 3);
             const float M4 = __shfl_sync(0xffffffffu, sum, base + 4), M5 = __shfl_sync(0xffffffffu, sum, base + 5);
-            if (!touched) continue;
+            if (!((any_rows >> j) & 1) || m >= 6) continue;
             const size_t id = (size_t)s_id[j];
-            if (c < S) atomicAdd(dL_dsemantics + id * S + c, sum);
-            else if (c < S + 3) atomicAdd(dL_dcolors + id * 3 + (c - S), sum);
-            else if (c == S + 3) atomicAdd(dL_ddepths + id, sum);
-            else if (c == S + 4) atomicAdd(dL_dopacity + id, sum);            // sum_pix w dL/d(silhouette)  (quirk Q2)
-            else if (m >= 0 && m < 6) {
-                const float2 xy = s_xy[j];
-                const float4 co = s_co[j];
-                const float xj = xy.x - cx, yj = xy.y - cy;
-                const float sgdx = xj * M0 - M1, sgdy = yj * M0 - M2;  // sum g dx, sum g dy
-                if (m == 0) atomicAdd(dL_dopacity + id, M0 / co.w);           // sum_pix G dL/dalpha
-                else if (m == 1) atomicAdd(dL_dmean2D + id * 3, -(co.x * sgdx + co.y * sgdy) * (0.5f * W));
-                else if (m == 2) atomicAdd(dL_dmean2D + id * 3 + 1, -(co.z * sgdy + co.y * sgdx) * (0.5f * H));
-                else if (m == 3) atomicAdd(dL_dconic2D + id * 4, -0.5f * (xj * xj * M0 - 2.f * xj * M1 + M3));
-                else if (m == 4) atomicAdd(dL_dconic2D + id * 4 + 1, -0.5f * (xj * yj * M0 - xj * M2 - yj * M1 + M4));
-                else atomicAdd(dL_dconic2D + id * 4 + 3, -0.5f * (yj * yj * M0 - 2.f * yj * M2 + M5));
-            }
+            const float2 xy = s_xy[j];
+            const float4 co = s_co[j];
+            const float xj = xy.x - cx, yj = xy.y - cy;
+            const float sgdx = xj * M0 - M1, sgdy = yj * M0 - M2;  // sum g dx, sum g dy
+            if (m == 0) atomicAdd(dL_dopacity + id, M0 / co.w);           // sum_pix G dL/dalpha
+            else if (m == 1) atomicAdd(dL_dmean2D + id * 3, -(co.x * sgdx + co.y * sgdy) * (0.5f * W));
+            else if (m == 2) atomicAdd(dL_dmean2D + id * 3 + 1, -(co.z * sgdy + co.y * sgdx) * (0.5f * H));
+            else if (m == 3) atomicAdd(dL_dconic2D + id * 4, -0.5f * (xj * xj * M0 - 2.f * xj * M1 + M3));
+            else if (m == 4) atomicAdd(dL_dconic2D + id * 4 + 1, -0.5f * (xj * yj * M0 - xj * M2 - yj * M1 + M4));
+            else atomicAdd(dL_dconic2D + id * 4 + 3, -0.5f * (yj * yj * M0 - 2.f * yj * M2 + M5));
         }
     }
 }
 
-template <int S>
+template <int S, int NW>
 static int launch_bwd_mma_t(const Camera& cam, const GeomView& g, const BinningView& b, const ImageView& img,
                             const float* bg, const float* colors, const float* dL_color, const float* dL_sem,
                             const float* dL_depth, const float* dL_median, const float* dL_opacity, float* dL_dmean2D,
                             float* dL_dconic, float* dL_dopacity, float* dL_dcolors, float* dL_dsemantics,
                             float* dL_ddepths, cudaStream_t stream, bool debug) {
     using Cfg = MmaCfg<S>;
-    size_t smem = (size_t)Cfg::BATCH * (2 * sizeof(float4) + 8 * Cfg::KA * sizeof(float) + sizeof(float2) + sizeof(int)) +
-                  (size_t)2 * 8 * 16 * Cfg::WS * sizeof(float) + 8 * sizeof(uint32_t);
-    if (!Cfg::B_IN_REGS) smem += (size_t)256 * Cfg::DS * sizeof(float);
-    auto k = blend_backward_mma_kernel<S>;
+    size_t smem = (size_t)Cfg::BATCH * (2 * sizeof(float4) + NW * Cfg::KA * sizeof(float) + sizeof(float2) + sizeof(int)) +
+                  (size_t)2 * NW * 16 * Cfg::WS * sizeof(float) + 8 * sizeof(uint32_t);
+    if (!Cfg::B_IN_REGS) smem += (size_t)32 * NW * Cfg::DS * sizeof(float);
+    auto k = blend_backward_mma_kernel<S, NW>;
     HS_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid(cam.grid_x, cam.grid_y, 1);
+    dim3 grid(cam.grid_x, cam.grid_y * (8 / NW), 1);
     prof_begin(ST_BLEND_BWD, stream);
-    k<<<grid, 256, smem, stream>>>(img.ranges, b.point_list, cam.W, cam.H, cam.grid_x, bg, g.means2D, g.conic_opacity,
+    k<<<grid, 32 * NW, smem, stream>>>(img.ranges, b.point_list, cam.W, cam.H, cam.grid_x, bg, g.means2D, g.conic_opacity,
                                    colors, g.depths, img.final_T, img.n_contrib, dL_color, dL_sem, dL_depth, dL_median,
                                    dL_opacity, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolors, dL_dsemantics,
                                    dL_ddepths);
@@ -365,9 +392,11 @@ int launch_blend_backward_mma(int S, const Camera& cam, const GeomView& g, const
                               const float* dL_depth, const float* dL_median, const float* dL_opacity,
                               float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolors,
                               float* dL_dsemantics, float* dL_ddepths, cudaStream_t stream, bool debug) {
+// warps per CTA: half-tile CTAs while the dL fragments fit in registers, whole-tile CTAs (dL tile in smem) above
+#define HS_BWD_NW(SV) 8   /* measured on c2: whole-tile CTAs (1.44 ms) beat half-tile CTAs (1.59 ms) */
 #define HS_BWDM_CASE(SV)                                                                                        \
     case SV:                                                                                                    \
-        return launch_bwd_mma_t<SV>(cam, g, b, img, bg, colors, dL_color, dL_sem, dL_depth, dL_median, dL_opacity, \
+        return launch_bwd_mma_t<SV, HS_BWD_NW(SV)>(cam, g, b, img, bg, colors, dL_color, dL_sem, dL_depth, dL_median, dL_opacity, \
                                     dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolors, dL_dsemantics, dL_ddepths,  \
                                     stream, debug);
     switch (S) {
