@@ -18,6 +18,7 @@
 // This replaces the (S+10)-value warp shuffle reduction of the SIMT version -- 64 % of a step in round 1 -- by
 // ~8 tensor instructions per (warp, Gaussian).
 #include "hs_common.cuh"
+#include <cuda_pipeline.h>
 
 namespace hs {
 
@@ -61,14 +62,15 @@ __global__ void __launch_bounds__(32 * NW, (MmaCfg<S>::B_IN_REGS ? (16 / NW) : 1
     constexpr int B = Cfg::BATCH, NF = Cfg::NF, NBF = Cfg::NBF, KA = Cfg::KA, WS = Cfg::WS, DS = Cfg::DS;
     constexpr bool BREG = Cfg::B_IN_REGS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float4* s_co = reinterpret_cast<float4*>(smem_raw);          // [B]
-    float4* s_feat = s_co + B;                                   // [B] r g b depth
-    float* s_part = reinterpret_cast<float*>(s_feat + B);        // [NW warps][B][KA] warp-private partial sums
+    // per-Gaussian staging is double-buffered and filled with cp.async one round ahead (ids two rounds ahead)
+    float4* s_co2 = reinterpret_cast<float4*>(smem_raw);         // [2][B] conic + opacity
+    float4* s_feat2 = s_co2 + 2 * B;                             // [2][B] r g b depth
+    float* s_part = reinterpret_cast<float*>(s_feat2 + 2 * B);   // [NW warps][B][KA] warp-private partial sums
     float* s_w = s_part + NW * B * KA;                           // [NW warps][16][WS]
     float* s_g = s_w + NW * 16 * WS;                             // [NW warps][16][WS]
-    float2* s_xy = reinterpret_cast<float2*>(s_g + NW * 16 * WS); // [B]
-    int* s_id = reinterpret_cast<int*>(s_xy + B);                // [B]
-    uint32_t* s_valid = reinterpret_cast<uint32_t*>(s_id + B);   // [NW] rows of s_part each warp wrote this round
+    float2* s_xy2 = reinterpret_cast<float2*>(s_g + NW * 16 * WS); // [2][B]
+    int* s_id3 = reinterpret_cast<int*>(s_xy2 + 2 * B);          // [3][B] ring of Gaussian ids
+    uint32_t* s_valid = reinterpret_cast<uint32_t*>(s_id3 + 3 * B);   // [NW] rows of s_part each warp wrote this round
     float* s_dL = reinterpret_cast<float*>(s_valid + 8);         // [32 NW][DS]   (only when !BREG)
     __shared__ int s_maxc;
 
@@ -178,18 +180,44 @@ __global__ void __launch_bounds__(32 * NW, (MmaCfg<S>::B_IN_REGS ? (16 / NW) : 1
     float last_alpha = 0.f, last_q = 0.f, accum_q = 0.f;
 
     const int rounds = (total + B - 1) / B;
-    for (int i = 0; i < rounds; i++) {
-        __syncthreads();  // previous batch flushed
-        const int nb_ = min(B, total - i * B);
-        if (tid < nb_) {
-            const int id = point_list[range.x + (total - 1 - i * B - tid)];
-            s_id[tid] = id;
-            s_xy[tid] = means2D[id];
-            s_co[tid] = conic_opacity[id];
-            s_feat[tid] = {__ldg(colors + 3 * (size_t)id), __ldg(colors + 3 * (size_t)id + 1),
-                           __ldg(colors + 3 * (size_t)id + 2), depths[id]};
+    // list position of entry t of round r (back to front), and the asynchronous gathers of one round
+    auto list_pos = [&](int r, int t) { return range.x + (total - 1 - r * B - t); };
+    auto gather_round = [&](int r) {   // ids of round r must already be in s_id3[r % 3]
+        const int n = min(B, total - r * B);
+        if (tid < n) {
+            const int id = s_id3[(r % 3) * B + tid];
+            const int bf = (r & 1) * B + tid;
+            __pipeline_memcpy_async(s_xy2 + bf, means2D + id, 8);
+            __pipeline_memcpy_async(s_co2 + bf, conic_opacity + id, 16);
+            float* f = reinterpret_cast<float*>(s_feat2 + bf);
+            __pipeline_memcpy_async(f, colors + 3 * (size_t)id, 4);
+            __pipeline_memcpy_async(f + 1, colors + 3 * (size_t)id + 1, 4);
+            __pipeline_memcpy_async(f + 2, colors + 3 * (size_t)id + 2, 4);
+            __pipeline_memcpy_async(f + 3, depths + id, 4);
         }
-        __syncthreads();
+    };
+    auto fetch_ids = [&](int r) {
+        const int n = min(B, total - r * B);
+        if (r < rounds && tid < n) __pipeline_memcpy_async(s_id3 + (r % 3) * B + tid, point_list + list_pos(r, tid), 4);
+    };
+    fetch_ids(0);
+    fetch_ids(1);
+    __pipeline_commit();
+    __pipeline_wait_prior(0);
+    __syncthreads();
+    gather_round(0);
+    __pipeline_commit();
+    for (int i = 0; i < rounds; i++) {
+        __pipeline_wait_prior(0);
+        __syncthreads();  // staging of round i landed, ids of round i+1 present, previous flush finished
+        const int nb_ = min(B, total - i * B);
+        if (i + 1 < rounds) gather_round(i + 1);
+        fetch_ids(i + 2);
+        __pipeline_commit();
+        const float2* s_xy = s_xy2 + (i & 1) * B;
+        const float4* s_co = s_co2 + (i & 1) * B;
+        const float4* s_feat = s_feat2 + (i & 1) * B;
+        const int* s_id = s_id3 + (i % 3) * B;
         uint32_t valid_rows = 0;   // warp-uniform: rows (Gaussians of this round) this warp contributed to
 
         for (int c0 = 0; c0 < nb_; c0 += 16) {
@@ -371,7 +399,7 @@ static int launch_bwd_mma_t(const Camera& cam, const GeomView& g, const BinningV
                             float* dL_dconic, float* dL_dopacity, float* dL_dcolors, float* dL_dsemantics,
                             float* dL_ddepths, cudaStream_t stream, bool debug) {
     using Cfg = MmaCfg<S>;
-    size_t smem = (size_t)Cfg::BATCH * (2 * sizeof(float4) + NW * Cfg::KA * sizeof(float) + sizeof(float2) + sizeof(int)) +
+    size_t smem = (size_t)Cfg::BATCH * (4 * sizeof(float4) + NW * Cfg::KA * sizeof(float) + 2 * sizeof(float2) + 3 * sizeof(int)) +
                   (size_t)2 * NW * 16 * Cfg::WS * sizeof(float) + 8 * sizeof(uint32_t);
     if (!Cfg::B_IN_REGS) smem += (size_t)32 * NW * Cfg::DS * sizeof(float);
     auto k = blend_backward_mma_kernel<S, NW>;
