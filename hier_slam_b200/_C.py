@@ -22,6 +22,7 @@ from . import _lib
 # 'exact' : the mathematically intended gradient.
 SEM_ALPHA_GRAD = os.environ.get("HS_SEM_ALPHA_GRAD", "ref")
 NO_CULL = os.environ.get("HS_NO_CULL", "0") == "1"
+FWD_SIMT = os.environ.get("HS_FWD_SIMT", "0") == "1"   # SIMT blend forward instead of the tensor-core one
 BWD_SIMT = os.environ.get("HS_BWD_SIMT", "0") == "1"   # SIMT blend backward instead of the tensor-core one
 
 _contig_cache: dict = {}   # id(tensor) -> (weakref(tensor), version, contiguous copy)
@@ -126,7 +127,7 @@ def _forward(background, means3D, colors, semantics, opacity, scales, rotations,
         out_median = torch.empty(1, H, W, **fopt)
         out_opacity = torch.empty(1, H, W, **fopt)
         out_mask = None if semantic else torch.empty(1, H, W, **fopt)
-        flags = _lib.HS_NO_CULL if NO_CULL else 0
+        flags = (_lib.HS_NO_CULL if NO_CULL else 0) | (_lib.HS_FWD_SIMT if FWD_SIMT else 0)
         _lib.check(lib.hs_forward_render(ctypes.byref(cam), P, S, num_rendered, _ptr(colors_c), _ptr(sem_c),
                                          _ptr(radii), _ptr(geomBuffer), _ptr(binningBuffer), bin_bytes,
                                          _ptr(imgBuffer), img_bytes, _ptr(out_color), _ptr(out_sem), _ptr(out_depth),

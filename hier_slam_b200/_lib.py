@@ -24,6 +24,7 @@ STAGES = ["preprocess", "scan", "duplicate", "sort", "ranges", "blend_fwd", "ble
 HS_SEM_ALPHA_EXACT = 1
 HS_NO_CULL = 2
 HS_BWD_SIMT = 4
+HS_FWD_SIMT = 8
 
 
 class HsCamera(Structure):

@@ -94,6 +94,10 @@ int launch_blend_forward(int S, const Camera& cam, const GeomView& g, const Binn
                          const float* colors, const float* semantics, float* out_color, float* out_semantic,
                          float* out_depth, float* out_median, float* out_opacity, float* out_mask, int flags,
                          cudaStream_t stream, bool debug);
+int launch_blend_forward_mma(int S, const Camera& cam, const GeomView& g, const BinningView& b, const ImageView& img,
+                             const float* colors, const float* semantics, float* out_color, float* out_semantic,
+                             float* out_depth, float* out_median, float* out_opacity, float* out_mask,
+                             cudaStream_t stream, bool debug);
 int launch_blend_backward(int S, const Camera& cam, const GeomView& g, const BinningView& b, const ImageView& img,
                           const float* bg, const float* colors, const float* semantics, const float* dL_color,
                           const float* dL_sem, const float* dL_depth, const float* dL_median,
@@ -149,6 +153,8 @@ __device__ __forceinline__ float4 footprint_box(const float2 xy, const float4 co
 enum : int {
     HS_FLAG_SEM_ALPHA_EXACT = 1,   // semantic channels contribute to dL/dalpha (reference quirk Q1 off)
     HS_FLAG_NO_CULL = 2,           // disable the conservative per-warp footprint test
+    HS_FLAG_SEM_UNALIGNED = 16,    // internal: semantics base pointer is only 4-byte aligned (scalar cp.async)
+    HS_FLAG_FWD_SIMT = 8,          // forward: SIMT blend instead of the tensor-core path
     HS_FLAG_BWD_SHUFFLE = 4,       // backward: SIMT warp-shuffle reduction instead of the tensor-core path
 };
 

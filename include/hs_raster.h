@@ -39,6 +39,7 @@ extern "C" {
                                 gradient).  Default (0) reproduces the reference, whose kernel reads the semantic
                                 feature from a never-written scratch buffer (backward.cu:834, rasterizer_impl.cu:673). */
 #define HS_BWD_SIMT 4        /* backward: use the SIMT (warp-shuffle) blend backward instead of the tensor-core one */
+#define HS_FWD_SIMT 8        /* forward: use the SIMT blend forward instead of the tensor-core one */
 #define HS_NO_CULL 2         /* forward: disable the conservative per-warp footprint test (results are identical) */
 
 /* Mirror of GaussianRasterizationSettings (diff_gaussian_rasterization/__init__.py:161-173). */
