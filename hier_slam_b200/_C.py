@@ -22,8 +22,9 @@ from . import _lib
 # 'exact' : the mathematically intended gradient.
 SEM_ALPHA_GRAD = os.environ.get("HS_SEM_ALPHA_GRAD", "ref")
 NO_CULL = os.environ.get("HS_NO_CULL", "0") == "1"
-FWD_SIMT = os.environ.get("HS_FWD_SIMT", "0") == "1"   # SIMT blend forward instead of the tensor-core one
+FWD_MMA = os.environ.get("HS_FWD_MMA", "0") == "1"     # opt into the tensor-core blend forward (slower; for study)
 BWD_SIMT = os.environ.get("HS_BWD_SIMT", "0") == "1"   # SIMT blend backward instead of the tensor-core one
+SORT_GLOBAL = os.environ.get("HS_SORT_GLOBAL", "0") == "1"   # reference-style global radix sort instead of tile buckets
 
 _contig_cache: dict = {}   # id(tensor) -> (weakref(tensor), version, contiguous copy)
 
@@ -112,23 +113,26 @@ def _forward(background, means3D, colors, semantics, opacity, scales, rotations,
                             prefiltered, debug)
         geom_bytes = lib.hs_geom_state_bytes(P)
         geomBuffer = torch.empty(geom_bytes, **byte)
+        img_bytes = lib.hs_image_state_bytes(H, W)
+        imgBuffer = torch.empty(img_bytes, **byte)
         R = ctypes.c_int(0)
+        max_tile = ctypes.c_int(0)
         _lib.check(lib.hs_forward_geometry(ctypes.byref(cam), P, _ptr(means3D_c), _ptr(opac_c), _ptr(scales_c),
                                            _ptr(rot_c), _ptr(cov_c), _ptr(radii), _ptr(geomBuffer), geom_bytes,
-                                           ctypes.byref(R), stream), "hs_forward_geometry")
+                                           _ptr(imgBuffer), img_bytes, _lib.HS_SORT_GLOBAL if SORT_GLOBAL else 0,
+                                           ctypes.byref(R), ctypes.byref(max_tile), stream), "hs_forward_geometry")
         num_rendered = int(R.value)
         bin_bytes = lib.hs_binning_state_bytes(num_rendered)
         binningBuffer = torch.empty(bin_bytes, **byte)
-        img_bytes = lib.hs_image_state_bytes(H, W)
-        imgBuffer = torch.empty(img_bytes, **byte)
         out_color = torch.empty(3, H, W, **fopt)
         out_sem = torch.empty(S, H, W, **fopt) if semantic else None
         out_depth = torch.empty(1, H, W, **fopt)
         out_median = torch.empty(1, H, W, **fopt)
         out_opacity = torch.empty(1, H, W, **fopt)
         out_mask = None if semantic else torch.empty(1, H, W, **fopt)
-        flags = (_lib.HS_NO_CULL if NO_CULL else 0) | (_lib.HS_FWD_SIMT if FWD_SIMT else 0)
-        _lib.check(lib.hs_forward_render(ctypes.byref(cam), P, S, num_rendered, _ptr(colors_c), _ptr(sem_c),
+        flags = (_lib.HS_NO_CULL if NO_CULL else 0) | (_lib.HS_FWD_MMA if FWD_MMA else 0)
+        _lib.check(lib.hs_forward_render(ctypes.byref(cam), P, S, num_rendered, int(max_tile.value), _ptr(colors_c),
+                                         _ptr(sem_c),
                                          _ptr(radii), _ptr(geomBuffer), _ptr(binningBuffer), bin_bytes,
                                          _ptr(imgBuffer), img_bytes, _ptr(out_color), _ptr(out_sem), _ptr(out_depth),
                                          _ptr(out_median), _ptr(out_opacity), _ptr(out_mask), flags, stream),

@@ -24,7 +24,8 @@ STAGES = ["preprocess", "scan", "duplicate", "sort", "ranges", "blend_fwd", "ble
 HS_SEM_ALPHA_EXACT = 1
 HS_NO_CULL = 2
 HS_BWD_SIMT = 4
-HS_FWD_SIMT = 8
+HS_FWD_MMA = 8
+HS_SORT_GLOBAL = 32
 
 
 class HsCamera(Structure):
@@ -58,10 +59,10 @@ def load() -> ctypes.CDLL:
     lib.hs_image_state_bytes.restype = c_size_t
     lib.hs_binning_state_bytes.argtypes = [c_int]
     lib.hs_binning_state_bytes.restype = c_size_t
-    lib.hs_forward_geometry.argtypes = [POINTER(HsCamera), c_int, vp, vp, vp, vp, vp, vp, vp, c_size_t,
-                                        POINTER(c_int), vp]
+    lib.hs_forward_geometry.argtypes = [POINTER(HsCamera), c_int, vp, vp, vp, vp, vp, vp, vp, c_size_t, vp, c_size_t,
+                                        c_int, POINTER(c_int), POINTER(c_int), vp]
     lib.hs_forward_geometry.restype = c_int
-    lib.hs_forward_render.argtypes = [POINTER(HsCamera), c_int, c_int, c_int, vp, vp, vp, vp, vp, c_size_t, vp,
+    lib.hs_forward_render.argtypes = [POINTER(HsCamera), c_int, c_int, c_int, c_int, vp, vp, vp, vp, vp, c_size_t, vp,
                                       c_size_t, vp, vp, vp, vp, vp, vp, c_int, vp]
     lib.hs_forward_render.restype = c_int
     lib.hs_backward.argtypes = [POINTER(HsCamera), c_int, c_int, c_int] + [vp] * 25 + [c_int, vp]
@@ -78,7 +79,7 @@ def load() -> ctypes.CDLL:
     lib.hs_profile_read.argtypes = [POINTER(c_float), POINTER(c_int)]
     lib.hs_kernel_launch_count.restype = ctypes.c_longlong
     lib.hs_library_call_count.restype = ctypes.c_longlong
-    if lib.hs_abi_version() != 1:
+    if lib.hs_abi_version() != 2:
         raise ImportError("libhsraster.so ABI version mismatch; rebuild with `python -m hier_slam_b200.build --force`")
     _lib = lib
     return lib

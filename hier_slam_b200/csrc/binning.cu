@@ -121,6 +121,8 @@ int image_view(char* base, size_t N, size_t tiles, ImageView* v) {
     carve(p, v->final_T, N);
     carve(p, v->n_contrib, N);
     carve(p, v->ranges, tiles);
+    carve(p, v->tile_count, tiles * HS_CTR_STRIDE);
+    carve(p, v->info, 4);
     v->total_bytes = (size_t)(p - base) + HS_ALIGN;
     return 0;
 }
@@ -241,6 +243,251 @@ __global__ void tile_ranges_kernel(int L, const uint64_t* __restrict__ keys, uin
         }
     }
     if (idx == L - 1) ranges[currtile].y = L;
+}
+
+// ---- tile-bucket binning (default path) ----------------------------------------------------------------------
+// The reference sorts all R (tile | depth) keys globally (6 radix passes over 12 R bytes each).  The same sorted list
+// is obtained with one counting pass and one short sort per tile:
+//   1. preprocess_kernel counts the instances of every tile (tile_count, atomics);
+//   2. tile_scan_kernel turns the counts into [start, end) ranges (== identifyTileRanges, empty tiles keep (0,0)),
+//      scatter cursors, num_rendered and the longest tile list;
+//   3. scatter_kernel writes (depth bits << 32 | Gaussian id) of every instance into its tile's segment, in arbitrary
+//      order (cursor atomics);
+//   4. tile_sort_kernel sorts each segment in shared memory on the whole 64-bit word.  Depths are positive floats, so
+//      their bit patterns order like the values; the id in the low word reproduces the tie order of the reference's
+//      STABLE sort over a list that is generated in Gaussian order.  All words of a segment are distinct, so the
+//      result does not depend on the scatter order: point_list and the sorted keys are bit-identical to the
+//      reference's (tests/test_gpu_parity.py).
+__global__ void __launch_bounds__(1024) tile_scan_kernel(int tiles, uint32_t* __restrict__ tile_count,
+                                                         uint2* __restrict__ ranges, uint32_t* __restrict__ info) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_carry = 0;
+    uint32_t my_max = 0;
+    __syncthreads();
+    for (int base = 0; base < tiles; base += 1024) {
+        const int t = base + tid;
+        const uint32_t c = t < tiles ? tile_count[(size_t)t * HS_CTR_STRIDE] : 0;
+        my_max = max(my_max, c);
+        uint32_t incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = s_warp[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += v;
+            }
+            s_warp[lane] = w;   // inclusive scan of the warp totals
+        }
+        __syncthreads();
+        const uint32_t carry = s_carry;
+        const uint32_t start = carry + (warp > 0 ? s_warp[warp - 1] : 0) + incl - c;
+        if (t < tiles) {
+            ranges[t] = c > 0 ? make_uint2(start, start + c) : make_uint2(0u, 0u);
+            tile_count[(size_t)t * HS_CTR_STRIDE] = start;   // scatter cursor
+        }
+        __syncthreads();
+        if (tid == 1023) s_carry = carry + s_warp[31];
+        __syncthreads();
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) my_max = max(my_max, __shfl_xor_sync(0xffffffffu, my_max, o));
+    if (lane == 0) s_warp[warp] = my_max;
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t m = 0;
+        for (int w = 0; w < 32; w++) m = max(m, s_warp[w]);
+        info[0] = s_carry;
+        info[1] = m;
+    }
+}
+
+int launch_tile_scan(const Camera& cam, const ImageView& img, cudaStream_t stream, bool debug) {
+    prof_begin(ST_SCAN, stream);
+    tile_scan_kernel<<<1, 1024, 0, stream>>>(cam.grid_x * cam.grid_y, img.tile_count, img.ranges, img.info);
+    prof_end(ST_SCAN, stream);
+    HS_LAUNCH_OK(stream, debug);
+    return 0;
+}
+
+__global__ void __launch_bounds__(256) scatter_kernel(int P, const float2* __restrict__ points_xy,
+                                                      const float* __restrict__ depths,
+                                                      uint32_t* __restrict__ cursor, uint64_t* __restrict__ seg,
+                                                      const int* __restrict__ radii, unsigned gx, unsigned gy) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    uint32_t w = 0, count = 0, dbits = 0;
+    uint2 rmin = {0, 0}, rmax = {0, 0};
+    if (idx < P && radii[idx] > 0) {
+        get_rect_dev(points_xy[idx], radii[idx], rmin, rmax, gx, gy);
+        w = rmax.x - rmin.x;
+        count = w * (rmax.y - rmin.y);
+        dbits = __float_as_uint(depths[idx]);
+    }
+    const uint32_t kSmall = 4;
+    if (count > 0 && count <= kSmall) {
+        const uint64_t word = ((uint64_t)dbits << 32) | (uint32_t)idx;
+        for (uint32_t n = 0; n < count; n++) {
+            const uint32_t tile = (rmin.y + n / w) * gx + rmin.x + n % w;
+            seg[atomicAdd(cursor + (size_t)tile * HS_CTR_STRIDE, 1u)] = word;
+        }
+    }
+    unsigned big = __ballot_sync(0xffffffffu, count > kSmall);
+    while (big) {
+        const int src = __ffs(big) - 1;
+        big &= big - 1;
+        const uint32_t s_w = __shfl_sync(0xffffffffu, w, src);
+        const uint32_t s_count = __shfl_sync(0xffffffffu, count, src);
+        const uint32_t s_db = __shfl_sync(0xffffffffu, dbits, src);
+        const uint32_t s_x0 = __shfl_sync(0xffffffffu, rmin.x, src);
+        const uint32_t s_y0 = __shfl_sync(0xffffffffu, rmin.y, src);
+        const uint32_t s_idx = (blockIdx.x * blockDim.x + (threadIdx.x & ~31)) + src;
+        const uint64_t word = ((uint64_t)s_db << 32) | s_idx;
+        for (uint32_t n = lane; n < s_count; n += 32) {
+            const uint32_t tile = (s_y0 + n / s_w) * gx + s_x0 + n % s_w;
+            seg[atomicAdd(cursor + (size_t)tile * HS_CTR_STRIDE, 1u)] = word;
+        }
+    }
+}
+
+// One CTA per tile; handles the tiles whose list length n satisfies lo < n <= hi (the host launches one size class
+// with small CTAs and, only if a longer list exists, a second one with 1024 threads and a large shared buffer).
+// Bitonic network on 64-bit words, padded to a power of two with ~0.  A thread keeps 2^Q words in registers and runs
+// Q consecutive strides of the network on them per shared-memory round trip (the words of one item are closed under
+// those strides), which cuts the shared-memory traffic and the barriers by ~Q compared with one stride per pass.
+__device__ __forceinline__ uint32_t sort_pad(uint32_t i) { return i + (i >> 3); }   // one pad word per 8: no bank conflicts
+
+__device__ __forceinline__ void cmpx(uint64_t& a, uint64_t& b, bool up) {
+    const bool sw = (a > b) == up;
+    const uint64_t x = sw ? b : a, y = sw ? a : b;
+    a = x;
+    b = y;
+}
+
+// strides jh, jh/2, ..., jh >> (Q-1) of phase k
+template <int Q>
+__device__ __forceinline__ void bitonic_pass(uint64_t* s, uint32_t n2, uint32_t k, uint32_t jh, int tid, int T) {
+    constexpr int E = 1 << Q;
+    const uint32_t sl = jh >> (Q - 1);
+    const int lsl = 31 - __clz(sl);
+    for (uint32_t u = tid; u < (n2 >> Q); u += T) {
+        const uint32_t base = ((u >> lsl) << (lsl + Q)) | (u & (sl - 1));
+        const bool up = (base & k) == 0;
+        uint64_t v[E];
+#pragma unroll
+        for (int e = 0; e < E; e++) v[e] = s[sort_pad(base + e * sl)];
+#pragma unroll
+        for (int st = Q - 1; st >= 0; st--)
+#pragma unroll
+            for (int e = 0; e < E; e++)
+                if (!(e & (1 << st))) cmpx(v[e], v[e | (1 << st)], up);
+#pragma unroll
+        for (int e = 0; e < E; e++) s[sort_pad(base + e * sl)] = v[e];
+    }
+}
+
+// phases k = 2, 4, 8 on 8 consecutive words per thread
+__device__ __forceinline__ void bitonic_first8(uint64_t* s, uint32_t n2, int tid, int T) {
+    for (uint32_t u = tid; u < (n2 >> 3); u += T) {
+        const uint32_t base = u << 3;
+        uint64_t v[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) v[e] = s[sort_pad(base + e)];
+#pragma unroll
+        for (int k = 2; k <= 8; k <<= 1)
+#pragma unroll
+            for (int st = k >> 1; st > 0; st >>= 1)
+#pragma unroll
+                for (int e = 0; e < 8; e++)
+                    if (!(e & st)) cmpx(v[e], v[e | st], ((base + e) & k) == 0);
+#pragma unroll
+        for (int e = 0; e < 8; e++) s[sort_pad(base + e)] = v[e];
+    }
+}
+
+template <int T>
+__global__ void __launch_bounds__(T) tile_sort_kernel(const uint2* __restrict__ ranges, const uint64_t* __restrict__ seg,
+                                                      uint32_t* __restrict__ point_list, uint64_t* __restrict__ keys,
+                                                      uint32_t lo, uint32_t hi) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* s = reinterpret_cast<uint64_t*>(smem_raw);
+    const uint32_t tile = blockIdx.x;
+    const uint2 range = ranges[tile];
+    const uint32_t n = range.y - range.x;
+    if (n <= lo || n > hi) return;
+    uint32_t n2 = 8;
+    while (n2 < n) n2 <<= 1;
+    const int tid = threadIdx.x;
+    for (uint32_t i = tid; i < n2; i += T) s[sort_pad(i)] = i < n ? seg[range.x + i] : ~0ull;
+    __syncthreads();
+    bitonic_first8(s, n2, tid, T);
+    __syncthreads();
+    int m = 4;
+    for (uint32_t k = 16; k <= n2; k <<= 1, m++) {
+        uint32_t j = k >> 1;
+        const int rem = m % 3;
+        if (rem == 1) {
+            bitonic_pass<1>(s, n2, k, j, tid, T);
+            j >>= 1;
+            __syncthreads();
+        } else if (rem == 2) {
+            bitonic_pass<2>(s, n2, k, j, tid, T);
+            j >>= 2;
+            __syncthreads();
+        }
+        for (; j >= 4; j >>= 3) {
+            bitonic_pass<3>(s, n2, k, j, tid, T);
+            __syncthreads();
+        }
+    }
+    const uint64_t hi_word = (uint64_t)tile << 32;
+    for (uint32_t i = tid; i < n; i += T) {
+        const uint64_t v = s[sort_pad(i)];
+        point_list[range.x + i] = (uint32_t)v;
+        keys[range.x + i] = hi_word | (v >> 32);   // the reference's sorted key: tile << 32 | depth bits
+    }
+}
+
+int launch_tile_binning(int P, int R, int max_tile, const Camera& cam, const int* radii, const GeomView& g,
+                        const BinningView& b, const ImageView& img, cudaStream_t stream, bool debug) {
+    if (P <= 0 || R <= 0) return 0;
+    const int tiles = cam.grid_x * cam.grid_y;
+    prof_begin(ST_DUPLICATE, stream);
+    scatter_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, g.means2D, g.depths, img.tile_count, b.keys_unsorted, radii,
+                                                       cam.grid_x, cam.grid_y);
+    prof_end(ST_DUPLICATE, stream);
+    HS_LAUNCH_OK(stream, debug);
+    prof_begin(ST_SORT, stream);
+    const uint32_t small_cap = HS_TILE_SORT_SMALL;
+    {
+        uint32_t cap = 8;
+        while (cap < (uint32_t)max_tile && cap < small_cap) cap <<= 1;
+        tile_sort_kernel<128><<<tiles, 128, (cap + cap / 8) * sizeof(uint64_t), stream>>>(
+            img.ranges, b.keys_unsorted, b.point_list, b.keys, 0u, small_cap);
+        count_launch();
+    }
+    if ((uint32_t)max_tile > small_cap) {
+        uint32_t cap = small_cap;
+        while (cap < (uint32_t)max_tile) cap <<= 1;
+        auto k = tile_sort_kernel<1024>;
+        const size_t smem = (size_t)(cap + cap / 8) * sizeof(uint64_t);
+        HS_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<tiles, 1024, smem, stream>>>(img.ranges, b.keys_unsorted, b.point_list, b.keys, small_cap,
+                                                          (uint32_t)HS_TILE_SORT_MAX);
+        count_launch();
+    }
+    prof_end(ST_SORT, stream);
+    HS_CUDA_OK(cudaGetLastError());
+    if (debug) HS_CUDA_OK(cudaStreamSynchronize(stream));
+    return 0;
 }
 
 int launch_binning(int P, int R, const Camera& cam, const int* radii, const GeomView& g, const BinningView& b,

@@ -221,9 +221,10 @@ int launch_blend_forward(int S, const Camera& cam, const GeomView& g, const Binn
                          const float* colors, const float* semantics, float* out_color, float* out_semantic,
                          float* out_depth, float* out_median, float* out_opacity, float* out_mask, int flags,
                          cudaStream_t stream, bool debug) {
-    // The tensor-core forward pays off only when the channel blend dominates the per-pixel alpha evaluation
-    // (measured on c2, S = 26: 894 us vs 571 us for the SIMT blend), so it is used for the wide semantic trees only.
-    if (S >= 64 && S <= 74 && !(flags & HS_FLAG_FWD_SIMT))
+    // The tensor-core forward (blend_fwd_mma.cu) is opt-in: on B200 the per-pixel alpha evaluation, not the channel
+    // blend, dominates the forward, and the SIMT blend below is faster at every measured S
+    // (c2, S = 26: 536 us vs 894 us; c5, S = 74: 438 us vs 943 us).
+    if ((flags & HS_FLAG_FWD_MMA) && S <= 74)
         return launch_blend_forward_mma(S, cam, g, b, img, colors, semantics, out_color, out_semantic, out_depth,
                                         out_median, out_opacity, out_mask, stream, debug);
 #define HS_FWD_CASE(SV)                                                                                      \

@@ -99,15 +99,17 @@ int hs_binning_state_layout(int R, size_t off[4]) {
 
 int hs_forward_geometry(const hs_camera* c, int P, const float* means3D, const float* opacities,
                         const float* scales, const float* rotations, const float* cov3D_precomp, int* radii,
-                        void* geom_state, size_t geom_state_bytes, int* num_rendered, void* stream_) {
+                        void* geom_state, size_t geom_state_bytes, void* image_state, size_t image_state_bytes,
+                        int flags, int* num_rendered, int* max_tile_list, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     Camera cam;
     if (make_camera(c, &cam)) return 1;
-    if (num_rendered == nullptr) {
-        set_error("num_rendered is NULL");
+    if (num_rendered == nullptr || max_tile_list == nullptr) {
+        set_error("num_rendered / max_tile_list is NULL");
         return 1;
     }
     *num_rendered = 0;
+    *max_tile_list = 0;
     if (P <= 0) return 0;
     if (means3D == nullptr || opacities == nullptr || radii == nullptr || geom_state == nullptr) {
         set_error("hs_forward_geometry: NULL argument");
@@ -128,22 +130,51 @@ int hs_forward_geometry(const hs_camera* c, int P, const float* means3D, const f
         return 1;
     }
     const bool debug = c->debug != 0;
-    int rc = launch_preprocess(P, means3D, scales, rotations, opacities, cov3D_precomp, cam, radii, g, stream, debug);
-    if (rc) return rc;
-    rc = launch_scan(P, g, stream, debug);
-    if (rc) return rc;
     int* host = pinned_int();
     if (host == nullptr) {
         set_error("cudaHostAlloc failed");
         return 2;
     }
-    HS_CUDA_OK(cudaMemcpyAsync(host, g.point_offsets + (P - 1), sizeof(int), cudaMemcpyDeviceToHost, stream));
+    if (flags & HS_SORT_GLOBAL) {
+        // reference-style binning: offsets scan over the Gaussians, the count is the last offset
+        int rc = launch_preprocess(P, means3D, scales, rotations, opacities, cov3D_precomp, cam, radii, g, nullptr,
+                                   stream, debug);
+        if (rc) return rc;
+        rc = launch_scan(P, g, stream, debug);
+        if (rc) return rc;
+        HS_CUDA_OK(cudaMemcpyAsync(host, g.point_offsets + (P - 1), sizeof(int), cudaMemcpyDeviceToHost, stream));
+        HS_CUDA_OK(cudaStreamSynchronize(stream));
+        *num_rendered = host[0];
+        *max_tile_list = -1;   // unknown: hs_forward_render will use the global sort
+        return 0;
+    }
+    // tile-bucket binning: per-tile counts in the preprocess pass, tile scan -> ranges, cursors, count, longest list
+    if (image_state == nullptr || (reinterpret_cast<uintptr_t>(image_state) & (HS_ALIGN - 1)) != 0) {
+        set_error("image_state must be a %d-byte aligned device buffer", HS_ALIGN);
+        return 1;
+    }
+    const size_t tiles = (size_t)cam.grid_x * cam.grid_y;
+    ImageView img;
+    image_view((char*)image_state, (size_t)cam.W * cam.H, tiles, &img);
+    if (img.total_bytes > image_state_bytes + HS_ALIGN) {
+        set_error("image_state too small");
+        return 1;
+    }
+    HS_CUDA_OK(cudaMemsetAsync(img.tile_count, 0, sizeof(uint32_t) * tiles * HS_CTR_STRIDE, stream));
+    int rc = launch_preprocess(P, means3D, scales, rotations, opacities, cov3D_precomp, cam, radii, g, img.tile_count,
+                               stream, debug);
+    if (rc) return rc;
+    rc = launch_tile_scan(cam, img, stream, debug);
+    if (rc) return rc;
+    HS_CUDA_OK(cudaMemcpyAsync(host, img.info, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream));
     HS_CUDA_OK(cudaStreamSynchronize(stream));
-    *num_rendered = *host;
+    *num_rendered = host[0];
+    *max_tile_list = host[1];
     return 0;
 }
 
-int hs_forward_render(const hs_camera* c, int P, int S, int R, const float* colors, const float* semantics,
+int hs_forward_render(const hs_camera* c, int P, int S, int R, int max_tile_list, const float* colors,
+                      const float* semantics,
                       const int* radii, void* geom_state, void* binning_state, size_t binning_state_bytes,
                       void* image_state, size_t image_state_bytes, float* out_color, float* out_semantic,
                       float* out_depth, float* out_median_depth, float* out_opacity, float* out_mask, int flags,
@@ -175,6 +206,7 @@ int hs_forward_render(const hs_camera* c, int P, int S, int R, const float* colo
     } else {
         g = GeomView{};
     }
+    if (P <= 0 || R <= 0) HS_CUDA_OK(cudaMemsetAsync(img.ranges, 0, sizeof(uint2) * tiles, stream));
     if (R > 0) {
         if (binning_state == nullptr) {
             set_error("binning_state is NULL");
@@ -193,7 +225,16 @@ int hs_forward_render(const hs_camera* c, int P, int S, int R, const float* colo
         b = BinningView{};
     }
     const bool debug = c->debug != 0;
-    int rc = launch_binning(P, R, cam, radii, g, b, img, stream, debug);
+    int rc = 0;
+    if (max_tile_list >= 0 && max_tile_list <= HS_TILE_SORT_MAX) {
+        rc = launch_tile_binning(P, R, max_tile_list, cam, radii, g, b, img, stream, debug);
+    } else {
+        // global radix sort: requested (HS_SORT_GLOBAL in hs_forward_geometry) or a tile list too long for the
+        // shared-memory sort; in the second case the offsets scan has not run yet
+        if (max_tile_list >= 0 && P > 0) rc = launch_scan(P, g, stream, debug);
+        if (rc) return rc;
+        rc = launch_binning(P, R, cam, radii, g, b, img, stream, debug);
+    }
     if (rc) return rc;
     return launch_blend_forward(S, cam, g, b, img, colors, semantics, out_color, out_semantic, out_depth,
                                 out_median_depth, out_opacity, out_mask, flags, stream, debug);

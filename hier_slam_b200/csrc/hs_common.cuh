@@ -9,6 +9,10 @@
 #define HS_TILE_Y 16          // reference: cuda_rasterizer/config.h:17  (BLOCK_Y)
 #define HS_TILE_PIX 256
 #define HS_ALIGN 256          // every array inside an opaque state buffer is 256-B aligned
+#define HS_CTR_STRIDE 32          // per-tile counters sit 128 B apart: L2 atomics serialise per line, not per word
+#define HS_TILE_SORT_SMALL 2048   // tile lists up to this length are sorted by 256-thread CTAs
+#define HS_TILE_SORT_MAX 16384    // longest tile list the in-shared-memory sort takes (128 KB); beyond it the
+                                  // global radix sort is used for the whole frame
 
 namespace hs {
 
@@ -59,6 +63,10 @@ struct ImageView {
     float* final_T;           // f32[N]
     uint32_t* n_contrib;      // u32[N]
     uint2* ranges;            // uint2[tiles]
+    // tile-bucket binning (default path): per-tile instance counts (turned into scatter cursors by the tile scan)
+    // and info = {num_rendered, longest tile list}
+    uint32_t* tile_count;     // u32[tiles]
+    uint32_t* info;           // u32[4]
     size_t total_bytes;
 };
 struct BinningView {
@@ -86,8 +94,11 @@ struct Camera {
 
 int launch_preprocess(int P, const float* means3D, const float* scales, const float* rotations,
                       const float* opacities, const float* cov3D_precomp, const Camera& cam, int* radii,
-                      const GeomView& g, cudaStream_t stream, bool debug);
+                      const GeomView& g, uint32_t* tile_count, cudaStream_t stream, bool debug);
 int launch_scan(int P, const GeomView& g, cudaStream_t stream, bool debug);
+int launch_tile_scan(const Camera& cam, const ImageView& img, cudaStream_t stream, bool debug);
+int launch_tile_binning(int P, int R, int max_tile, const Camera& cam, const int* radii, const GeomView& g,
+                        const BinningView& b, const ImageView& img, cudaStream_t stream, bool debug);
 int launch_binning(int P, int R, const Camera& cam, const int* radii, const GeomView& g, const BinningView& b,
                    const ImageView& img, cudaStream_t stream, bool debug);
 int launch_blend_forward(int S, const Camera& cam, const GeomView& g, const BinningView& b, const ImageView& img,
@@ -153,8 +164,10 @@ __device__ __forceinline__ float4 footprint_box(const float2 xy, const float4 co
 enum : int {
     HS_FLAG_SEM_ALPHA_EXACT = 1,   // semantic channels contribute to dL/dalpha (reference quirk Q1 off)
     HS_FLAG_NO_CULL = 2,           // disable the conservative per-warp footprint test
+    HS_FLAG_SORT_CUB = 32,         // binning: reference-style scan + duplicate + global radix sort (CUB) instead of
+                                   // the tile-bucket sort (identical sorted keys / lists / ranges)
     HS_FLAG_SEM_UNALIGNED = 16,    // internal: semantics base pointer is only 4-byte aligned (scalar cp.async)
-    HS_FLAG_FWD_SIMT = 8,          // forward: SIMT blend instead of the tensor-core path
+    HS_FLAG_FWD_MMA = 8,           // forward: opt into the tensor-core blend (slower than SIMT on B200; kept for study)
     HS_FLAG_BWD_SHUFFLE = 4,       // backward: SIMT warp-shuffle reduction instead of the tensor-core path
 };
 

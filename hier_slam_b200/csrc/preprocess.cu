@@ -144,7 +144,8 @@ __global__ void __launch_bounds__(256) preprocess_kernel(int P, const float* __r
                                                          int* __restrict__ radii, float* __restrict__ depths,
                                                          float2* __restrict__ means2D,
                                                          float4* __restrict__ conic_opacity,
-                                                         uint32_t* __restrict__ tiles_touched) {
+                                                         uint32_t* __restrict__ tiles_touched,
+                                                         uint32_t* __restrict__ tile_count) {
     __shared__ __align__(16) float s_means[256 * 3];
     __shared__ __align__(16) float s_scales[256 * 3];
     __shared__ float s_view[16];
@@ -157,14 +158,15 @@ __global__ void __launch_bounds__(256) preprocess_kernel(int P, const float* __r
     else if (threadIdx.x < 32) s_proj[threadIdx.x - 16] = __ldg(cam.proj + threadIdx.x - 16);
     __syncthreads();
     const int idx = base + threadIdx.x;
-    if (idx >= P) return;
 
     int my_radii = 0;
     uint32_t my_tiles = 0;
     float my_depth = 0.f;
     float2 my_xy = {0.f, 0.f};
     float4 my_co = {0.f, 0.f, 0.f, 0.f};
+    uint2 my_rmin = {0, 0}, my_rmax = {0, 0};
     do {
+        if (idx >= P) break;
         const float3 p_orig = {s_means[3 * threadIdx.x], s_means[3 * threadIdx.x + 1], s_means[3 * threadIdx.x + 2]};
         // in_frustum (auxiliary.h:139-164): only the near-plane test is live
         float4 p_hom = xform4x4(p_orig, s_proj);
@@ -202,7 +204,29 @@ __global__ void __launch_bounds__(256) preprocess_kernel(int P, const float* __r
         my_xy = point_image;
         my_co = {conic.x, conic.y, conic.z, __ldg(opacities + idx)};
         my_tiles = (rect_max.y - rect_min.y) * (rect_max.x - rect_min.x);
+        my_rmin = rect_min;
+        my_rmax = rect_max;
     } while (0);
+    // Per-tile instance counts for the tile-bucket sort (binning.cu).  Rects of more than 4 tiles are expanded by the
+    // whole warp.
+    if (tile_count != nullptr) {
+        const uint32_t w = my_rmax.x - my_rmin.x;
+        if (my_tiles > 0 && my_tiles <= 4) {
+            for (uint32_t n = 0; n < my_tiles; n++)
+                atomicAdd(tile_count + (size_t)((my_rmin.y + n / w) * cam.grid_x + my_rmin.x + n % w) * HS_CTR_STRIDE, 1u);
+        }
+        unsigned big = __ballot_sync(0xffffffffu, my_tiles > 4);
+        const int lane = threadIdx.x & 31;
+        while (big) {
+            const int src = __ffs(big) - 1;
+            big &= big - 1;
+            const uint32_t s_w = __shfl_sync(0xffffffffu, w, src), s_n = __shfl_sync(0xffffffffu, my_tiles, src);
+            const uint32_t s_x0 = __shfl_sync(0xffffffffu, my_rmin.x, src), s_y0 = __shfl_sync(0xffffffffu, my_rmin.y, src);
+            for (uint32_t n = lane; n < s_n; n += 32)
+                atomicAdd(tile_count + (size_t)((s_y0 + n / s_w) * cam.grid_x + s_x0 + n % s_w) * HS_CTR_STRIDE, 1u);
+        }
+    }
+    if (idx >= P) return;
     // Unlike the reference (which leaves stale bytes for culled Gaussians) every field is written, so the
     // state buffers never need a memset and can come from torch.empty.
     radii[idx] = my_radii;
@@ -214,12 +238,13 @@ __global__ void __launch_bounds__(256) preprocess_kernel(int P, const float* __r
 
 int launch_preprocess(int P, const float* means3D, const float* scales, const float* rotations,
                       const float* opacities, const float* cov3D_precomp, const Camera& cam, int* radii,
-                      const GeomView& g, cudaStream_t stream, bool debug) {
+                      const GeomView& g, uint32_t* tile_count, cudaStream_t stream, bool debug) {
     if (P <= 0) return 0;
     prof_begin(ST_PREPROCESS, stream);
     preprocess_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, means3D, scales, (const float4*)rotations, opacities,
                                                           cov3D_precomp, cam, radii, g.depths, g.means2D,
-                                                          g.conic_opacity, g.tiles_touched);
+                                                          g.conic_opacity, g.tiles_touched,
+                                                          tile_count);
     prof_end(ST_PREPROCESS, stream);
     HS_LAUNCH_OK(stream, debug);
     return 0;

@@ -32,15 +32,18 @@
 extern "C" {
 #endif
 
-#define HS_RASTER_ABI_VERSION 1
+#define HS_RASTER_ABI_VERSION 2
 
 /* flags (bit-or) */
 #define HS_SEM_ALPHA_EXACT 1 /* backward: semantic channels contribute to dL/dalpha (the mathematically intended
                                 gradient).  Default (0) reproduces the reference, whose kernel reads the semantic
                                 feature from a never-written scratch buffer (backward.cu:834, rasterizer_impl.cu:673). */
 #define HS_BWD_SIMT 4        /* backward: use the SIMT (warp-shuffle) blend backward instead of the tensor-core one */
-#define HS_FWD_SIMT 8        /* forward: use the SIMT blend forward instead of the tensor-core one */
+#define HS_FWD_MMA 8         /* forward: opt into the tensor-core (3xTF32 mma) blend; measured slower than the SIMT blend */
 #define HS_NO_CULL 2         /* forward: disable the conservative per-warp footprint test (results are identical) */
+#define HS_SORT_GLOBAL 32    /* hs_forward_geometry: reference-style binning (offsets scan, key duplication, one global
+                                radix sort) instead of the default per-tile bucket sort; sorted keys, tile lists and
+                                ranges are bit-identical either way */
 
 /* Mirror of GaussianRasterizationSettings (diff_gaussian_rasterization/__init__.py:161-173). */
 typedef struct hs_camera {
@@ -67,18 +70,22 @@ size_t hs_geom_state_bytes(int P);
 size_t hs_image_state_bytes(int image_height, int image_width);
 size_t hs_binning_state_bytes(int num_rendered);
 
-/* Stage 1 of the forward: per-Gaussian projection / cull / tile count + offsets scan.
- * Writes radii[P] (int32, device), fills geom_state, and returns the number of (Gaussian, tile) instances in
- * *num_rendered (HOST pointer).  Synchronises `stream` once (the only host sync of a forward+backward).
- * scales/rotations may be NULL iff cov3D_precomp is given, and vice versa. */
+/* Stage 1 of the forward: per-Gaussian projection / cull / tile counting.
+ * Writes radii[P] (int32, device), fills geom_state and the tile ranges inside image_state, and returns (HOST
+ * pointers) the number of (Gaussian, tile) instances in *num_rendered and the length of the longest tile list in
+ * *max_tile_list (-1 with HS_SORT_GLOBAL).  Synchronises `stream` once (the only host sync of a forward+backward).
+ * scales/rotations may be NULL iff cov3D_precomp is given, and vice versa.  flags: 0 or HS_SORT_GLOBAL. */
 int hs_forward_geometry(const hs_camera* cam, int P, const float* means3D, const float* opacities,
                         const float* scales, const float* rotations, const float* cov3D_precomp, int* radii,
-                        void* geom_state, size_t geom_state_bytes, int* num_rendered, void* stream);
+                        void* geom_state, size_t geom_state_bytes, void* image_state, size_t image_state_bytes,
+                        int flags, int* num_rendered, int* max_tile_list, void* stream);
 
-/* Stage 2 of the forward: key duplication, sort, tile ranges, alpha compositing.
+/* Stage 2 of the forward: instance scatter + per-tile sort (or key duplication, global sort and range
+ * identification), alpha compositing.  num_rendered and max_tile_list are the values stage 1 returned; image_state
+ * is the buffer stage 1 filled.
  * Outputs (device): out_color[3,H,W], out_semantic[S,H,W] (S > 0), out_depth[1,H,W], out_median_depth[1,H,W],
  * out_opacity[1,H,W], out_mask[1,H,W] (may be NULL; only written when S == 0).  No output needs initialisation. */
-int hs_forward_render(const hs_camera* cam, int P, int S, int num_rendered, const float* colors,
+int hs_forward_render(const hs_camera* cam, int P, int S, int num_rendered, int max_tile_list, const float* colors,
                       const float* semantics, const int* radii, void* geom_state, void* binning_state,
                       size_t binning_state_bytes, void* image_state, size_t image_state_bytes, float* out_color,
                       float* out_semantic, float* out_depth, float* out_median_depth, float* out_opacity,
@@ -106,8 +113,9 @@ int hs_mark_visible(int P, const float* means3D, const float* viewmatrix, const 
  * CUDA event pair on the launching stream.  hs_profile_read() waits for all recorded pairs and returns, per
  * stage, the summed elapsed milliseconds and the number of launches since the previous read, in the order
  * [preprocess, scan, duplicate, sort, ranges, blend_fwd, blend_bwd, geom_bwd].
- * hs_kernel_launch_count() = kernels of this library launched so far; hs_library_call_count() = CUB
- * device-wide primitives (scan, radix sort) called so far. */
+ * With the default tile-bucket binning "scan" is the tile scan, "duplicate" the instance scatter, "sort" the per-tile
+ * sort and "ranges" is empty.  hs_kernel_launch_count() = kernels of this library launched so far;
+ * hs_library_call_count() = CUB device-wide primitives (scan, radix sort; HS_SORT_GLOBAL only) called so far. */
 int hs_profile_enable(int on);
 int hs_profile_read(float total_ms[8], int count[8]);
 long long hs_kernel_launch_count(void);

@@ -32,6 +32,27 @@ def new_impl():
     return _C, GaussianRasterizationSettings
 
 
+def global_sort_views(C, settings, scene, f, semantic=True):
+    """Runs the forward again with the reference-style binning (HS_SORT_GLOBAL: offsets scan, key duplication, one
+    global radix sort), checks that the default tile-bucket binning produced the same sorted keys, tile lists, ranges
+    and images bit for bit, and returns the state views of the global run (they also hold the unsorted arrays)."""
+    C.SORT_GLOBAL = True
+    try:
+        fg = pt.run_forward(C, settings, scene, semantic)
+    finally:
+        C.SORT_GLOBAL = False
+    P, H, W = scene["means3D"].shape[0], settings.image_height, settings.image_width
+    sv = C.state_views(P, H, W, f["R"], f["geomBuffer"], f["binningBuffer"], f["imgBuffer"])
+    sg = C.state_views(P, H, W, fg["R"], fg["geomBuffer"], fg["binningBuffer"], fg["imgBuffer"])
+    assert f["R"] == fg["R"] and torch.equal(f["radii"], fg["radii"])
+    for k in ("keys", "point_list", "ranges", "n_contrib", "tiles_touched"):
+        assert torch.equal(sv[k], sg[k]), f"tile-bucket vs global sort: {k}"
+    assert pt.bits_equal(sv["final_T"], sg["final_T"]) == 0
+    for k in ("color", "depth", "median_depth", "final_opacity"):
+        assert pt.bits_equal(f[k], fg[k]) == 0, k
+    return sg
+
+
 def assert_images_close(a, b, what):
     mx, viol = pt.image_err(a, b, IMG_ATOL, IMG_RTOL)
     assert viol == 0, f"{what}: {viol} pixels outside {IMG_ATOL}+{IMG_RTOL}*|ref| (max abs err {mx:.3e})"
@@ -62,8 +83,11 @@ def test_against_reference_golden(path):
     for k in ("depths", "means2D", "conic_opacity"):
         assert pt.bits_equal(sv[k][vis], T("st_" + k)[vis]) == 0, k
     assert torch.equal(sv["tiles_touched"], T("st_tiles_touched"))
-    for k in ("keys_unsorted", "point_list_unsorted", "keys", "point_list", "ranges", "n_contrib"):
+    for k in ("keys", "point_list", "ranges", "n_contrib"):
         assert torch.equal(sv[k], T("st_" + k)), k
+    sg = global_sort_views(C, settings, scene, f)
+    for k in ("keys_unsorted", "point_list_unsorted"):
+        assert torch.equal(sg[k], T("st_" + k)), k
     assert pt.bits_equal(sv["final_T"], T("st_final_T")) == 0
     for k in ("color", "semantic", "depth", "median_depth", "final_opacity"):
         assert_images_close(f[k], T(k), k)
@@ -102,7 +126,8 @@ def test_against_cpu_oracle(key, S, semantic):
     assert float((geom["means2D"][both] - sv["means2D"][both]).abs().max()) < 2e-3
     keys_u, vals_u = O.duplicate_with_keys(sv["depths"], sv["means2D"], radii, W, H)
     assert keys_u.numel() == f["R"]
-    assert torch.equal(keys_u, sv["keys_unsorted"]) and torch.equal(vals_u.int(), sv["point_list_unsorted"])
+    sg = global_sort_views(C, settings, scene, f, semantic)
+    assert torch.equal(keys_u, sg["keys_unsorted"].cpu()) and torch.equal(vals_u.int(), sg["point_list_unsorted"].cpu())
     skeys, plist, ranges = O.sort_and_ranges(keys_u, vals_u, W, H)
     assert torch.equal(skeys, sv["keys"]) and torch.equal(plist.int(), sv["point_list"])
     assert torch.equal(ranges.int(), sv["ranges"])
@@ -168,8 +193,11 @@ def test_against_live_reference(key, P, S):
     for k in ("depths", "means2D", "conic_opacity"):
         assert pt.bits_equal(sv[k][vis], sr[k][vis]) == 0, k
     assert torch.equal(sv["tiles_touched"], sr["tiles_touched"])
-    for k in ("keys_unsorted", "point_list_unsorted", "keys", "point_list", "ranges", "n_contrib"):
+    for k in ("keys", "point_list", "ranges", "n_contrib"):
         assert torch.equal(sv[k], sr[k]), k
+    sg = global_sort_views(C, settings, scene, f)
+    for k in ("keys_unsorted", "point_list_unsorted"):
+        assert torch.equal(sg[k], sr[k]), k
     for k in ("color", "semantic", "depth", "median_depth", "final_opacity"):
         assert_images_close(f[k], fr[k], k)
     g = pt.run_backward(C, settings, scene, f, ug)
@@ -207,10 +235,11 @@ def test_full_size_properties_c2():
     sv = C.state_views(P, H, W, f["R"], f["geomBuffer"], f["binningBuffer"], f["imgBuffer"])
     keys = sv["keys"]
     assert bool((keys[1:] >= keys[:-1]).all())                                   # sortedness
-    assert int(sv["tiles_touched"].long().sum()) == f["R"] == int(sv["point_offsets"][-1])
+    sg = global_sort_views(C, settings, scene, f)                                # tile buckets == global radix sort
+    assert int(sv["tiles_touched"].long().sum()) == f["R"] == int(sg["point_offsets"][-1])
     same = keys[1:] == keys[:-1]
     assert bool((sv["point_list"][1:][same] > sv["point_list"][:-1][same]).all())  # stability
-    assert torch.equal(torch.sort(sv["point_list"].long())[0], torch.sort(sv["point_list_unsorted"].long())[0])
+    assert torch.equal(torch.sort(sv["point_list"].long())[0], torch.sort(sg["point_list_unsorted"].long())[0])
     rg = sv["ranges"].long()
     assert int((rg[:, 1] - rg[:, 0]).sum()) == f["R"]
     tile_of = (keys >> 32)

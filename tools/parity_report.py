@@ -90,8 +90,14 @@ def report(key, iters, P=None, S=None, semantic=True):
         for i, nm in enumerate(("conic_x", "conic_y", "conic_z", "opacity")):
             ex[nm] = pt.bits_equal(sv_new["conic_opacity"][vis][:, i], sv_ref["conic_opacity"][vis][:, i])
         if ex["R_equal"] and f_new["R"] > 0:
-            for k in ("keys_unsorted", "point_list_unsorted", "keys", "point_list"):
+            for k in ("keys", "point_list"):                     # default path: tile-bucket binning
                 ex[k] = pt.bits_equal(sv_new[k], sv_ref[k])
+            newC.SORT_GLOBAL = True                               # reference-style binning: also the unsorted arrays
+            f_gl = pt.run_forward(newC, settings, scene, semantic)
+            newC.SORT_GLOBAL = False
+            sv_gl = newC.state_views(Pn, H, W, f_gl["R"], f_gl["geomBuffer"], f_gl["binningBuffer"], f_gl["imgBuffer"])
+            for k in ("keys_unsorted", "point_list_unsorted", "keys", "point_list"):
+                ex["global_sort:" + k] = pt.bits_equal(sv_gl[k], sv_ref[k])
         ex["ranges"] = pt.bits_equal(sv_new["ranges"], sv_ref["ranges"])
         ex["n_contrib"] = pt.bits_equal(sv_new["n_contrib"], sv_ref["n_contrib"])
         ex["final_T"] = pt.bits_equal(sv_new["final_T"], sv_ref["final_T"])

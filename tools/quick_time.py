@@ -15,7 +15,7 @@ settings = pt.make_settings(GaussianRasterizationSettings, cfg)
 lib = _lib.load()
 for simt in (False, True):
     _C.BWD_SIMT = simt
-    _C.FWD_SIMT = simt
+    _C.FWD_MMA = False
     for _ in range(3):
         f = pt.run_forward(_C, settings, scene); g = pt.run_backward(_C, settings, scene, f, grads)
     torch.cuda.synchronize()
@@ -26,11 +26,10 @@ for simt in (False, True):
     prof = _lib.profile_read(); lib.hs_profile_enable(0)
     print(json.dumps({"config": key, "bwd_simt": simt, **{k: round(v[0] / v[1] * 1e3, 1) for k, v in prof.items()}}))
 _C.BWD_SIMT = False
-_C.FWD_SIMT = False
+_C.FWD_MMA = True
 fm = pt.run_forward(_C, settings, scene)
-_C.FWD_SIMT = True
+_C.FWD_MMA = False
 fs = pt.run_forward(_C, settings, scene)
-_C.FWD_SIMT = False
 P, H, W = scene["means3D"].shape[0], cfg.height, cfg.width
 sm = _C.state_views(P, H, W, fm["R"], fm["geomBuffer"], fm["binningBuffer"], fm["imgBuffer"])
 ss = _C.state_views(P, H, W, fs["R"], fs["geomBuffer"], fs["binningBuffer"], fs["imgBuffer"])
