@@ -116,11 +116,11 @@ def _forward(background, means3D, colors, semantics, opacity, scales, rotations,
         img_bytes = lib.hs_image_state_bytes(H, W)
         imgBuffer = torch.empty(img_bytes, **byte)
         R = ctypes.c_int(0)
-        max_tile = ctypes.c_int(0)
+        hint = ctypes.c_int(0)
         _lib.check(lib.hs_forward_geometry(ctypes.byref(cam), P, _ptr(means3D_c), _ptr(opac_c), _ptr(scales_c),
                                            _ptr(rot_c), _ptr(cov_c), _ptr(radii), _ptr(geomBuffer), geom_bytes,
                                            _ptr(imgBuffer), img_bytes, _lib.HS_SORT_GLOBAL if SORT_GLOBAL else 0,
-                                           ctypes.byref(R), ctypes.byref(max_tile), stream), "hs_forward_geometry")
+                                           ctypes.byref(R), ctypes.byref(hint), stream), "hs_forward_geometry")
         num_rendered = int(R.value)
         bin_bytes = lib.hs_binning_state_bytes(num_rendered)
         binningBuffer = torch.empty(bin_bytes, **byte)
@@ -131,7 +131,7 @@ def _forward(background, means3D, colors, semantics, opacity, scales, rotations,
         out_opacity = torch.empty(1, H, W, **fopt)
         out_mask = None if semantic else torch.empty(1, H, W, **fopt)
         flags = (_lib.HS_NO_CULL if NO_CULL else 0) | (_lib.HS_FWD_MMA if FWD_MMA else 0)
-        _lib.check(lib.hs_forward_render(ctypes.byref(cam), P, S, num_rendered, int(max_tile.value), _ptr(colors_c),
+        _lib.check(lib.hs_forward_render(ctypes.byref(cam), P, S, num_rendered, int(hint.value), _ptr(colors_c),
                                          _ptr(sem_c),
                                          _ptr(radii), _ptr(geomBuffer), _ptr(binningBuffer), bin_bytes,
                                          _ptr(imgBuffer), img_bytes, _ptr(out_color), _ptr(out_sem), _ptr(out_depth),

@@ -264,12 +264,13 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(int tiles, uint32_t* __
     __shared__ uint32_t s_carry;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_carry = 0;
-    uint32_t my_max = 0;
+    uint32_t my_max = 0, my_small = 0;
     __syncthreads();
     for (int base = 0; base < tiles; base += 1024) {
         const int t = base + tid;
         const uint32_t c = t < tiles ? tile_count[(size_t)t * HS_CTR_STRIDE] : 0;
         my_max = max(my_max, c);
+        my_small += (c > 0 && c <= HS_TILE_SORT_SMALL) ? 1u : 0u;
         uint32_t incl = c;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -299,14 +300,25 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(int tiles, uint32_t* __
         __syncthreads();
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) my_max = max(my_max, __shfl_xor_sync(0xffffffffu, my_max, o));
-    if (lane == 0) s_warp[warp] = my_max;
+    for (int o = 16; o > 0; o >>= 1) {
+        my_max = max(my_max, __shfl_xor_sync(0xffffffffu, my_max, o));
+        my_small += __shfl_xor_sync(0xffffffffu, my_small, o);
+    }
+    __shared__ uint32_t s_small[32];
+    if (lane == 0) {
+        s_warp[warp] = my_max;
+        s_small[warp] = my_small;
+    }
     __syncthreads();
     if (tid == 0) {
-        uint32_t m = 0;
-        for (int w = 0; w < 32; w++) m = max(m, s_warp[w]);
-        info[0] = s_carry;
-        info[1] = m;
+        uint32_t m = 0, ns = 0;
+        for (int w = 0; w < 32; w++) {
+            m = max(m, s_warp[w]);
+            ns += s_small[w];
+        }
+        info[0] = s_carry;   // num_rendered
+        info[1] = m;         // longest tile list
+        info[2] = ns;        // non-empty tiles with at most HS_TILE_SORT_SMALL entries
     }
 }
 
@@ -359,11 +371,14 @@ __global__ void __launch_bounds__(256) scatter_kernel(int P, const float2* __res
 }
 
 // One CTA per tile; handles the tiles whose list length n satisfies lo < n <= hi (the host launches one size class
-// with small CTAs and, only if a longer list exists, a second one with 1024 threads and a large shared buffer).
+// with small CTAs and, only if longer lists exist, a second one with 512 threads and a large shared buffer).
 // Bitonic network on 64-bit words, padded to a power of two with ~0.  A thread keeps 2^Q words in registers and runs
 // Q consecutive strides of the network on them per shared-memory round trip (the words of one item are closed under
 // those strides), which cuts the shared-memory traffic and the barriers by ~Q compared with one stride per pass.
-__device__ __forceinline__ uint32_t sort_pad(uint32_t i) { return i + (i >> 3); }   // one pad word per 8: no bank conflicts
+// Every phase ends with one pass over strides 8, 4, 2, 1 (16 consecutive words per thread); the passes above it have
+// strides >= 16, where consecutive lanes touch consecutive words.  With one pad word per 16 both access patterns are
+// free of bank conflicts.
+__device__ __forceinline__ uint32_t sort_pad(uint32_t i) { return i + (i >> 4); }
 
 __device__ __forceinline__ void cmpx(uint64_t& a, uint64_t& b, bool up) {
     const bool sw = (a > b) == up;
@@ -394,22 +409,22 @@ __device__ __forceinline__ void bitonic_pass(uint64_t* s, uint32_t n2, uint32_t 
     }
 }
 
-// phases k = 2, 4, 8 on 8 consecutive words per thread
-__device__ __forceinline__ void bitonic_first8(uint64_t* s, uint32_t n2, int tid, int T) {
-    for (uint32_t u = tid; u < (n2 >> 3); u += T) {
-        const uint32_t base = u << 3;
-        uint64_t v[8];
+// phases k = 2, 4, 8, 16 on 16 consecutive words per thread
+__device__ __forceinline__ void bitonic_first16(uint64_t* s, uint32_t n2, int tid, int T) {
+    for (uint32_t u = tid; u < (n2 >> 4); u += T) {
+        const uint32_t base = u << 4;
+        uint64_t v[16];
 #pragma unroll
-        for (int e = 0; e < 8; e++) v[e] = s[sort_pad(base + e)];
+        for (int e = 0; e < 16; e++) v[e] = s[sort_pad(base + e)];
 #pragma unroll
-        for (int k = 2; k <= 8; k <<= 1)
+        for (int k = 2; k <= 16; k <<= 1)
 #pragma unroll
             for (int st = k >> 1; st > 0; st >>= 1)
 #pragma unroll
-                for (int e = 0; e < 8; e++)
+                for (int e = 0; e < 16; e++)
                     if (!(e & st)) cmpx(v[e], v[e | st], ((base + e) & k) == 0);
 #pragma unroll
-        for (int e = 0; e < 8; e++) s[sort_pad(base + e)] = v[e];
+        for (int e = 0; e < 16; e++) s[sort_pad(base + e)] = v[e];
     }
 }
 
@@ -423,17 +438,17 @@ __global__ void __launch_bounds__(T) tile_sort_kernel(const uint2* __restrict__ 
     const uint2 range = ranges[tile];
     const uint32_t n = range.y - range.x;
     if (n <= lo || n > hi) return;
-    uint32_t n2 = 8;
+    uint32_t n2 = 16;
     while (n2 < n) n2 <<= 1;
     const int tid = threadIdx.x;
     for (uint32_t i = tid; i < n2; i += T) s[sort_pad(i)] = i < n ? seg[range.x + i] : ~0ull;
     __syncthreads();
-    bitonic_first8(s, n2, tid, T);
+    bitonic_first16(s, n2, tid, T);
     __syncthreads();
-    int m = 4;
-    for (uint32_t k = 16; k <= n2; k <<= 1, m++) {
-        uint32_t j = k >> 1;
-        const int rem = m % 3;
+    int m = 5;   // log2(k)
+    for (uint32_t k = 32; k <= n2; k <<= 1, m++) {
+        uint32_t j = k >> 1;            // strides k/2 ... 16 in groups of <= 3, then 8 4 2 1
+        const int rem = (m - 4) % 3;
         if (rem == 1) {
             bitonic_pass<1>(s, n2, k, j, tid, T);
             j >>= 1;
@@ -443,10 +458,12 @@ __global__ void __launch_bounds__(T) tile_sort_kernel(const uint2* __restrict__ 
             j >>= 2;
             __syncthreads();
         }
-        for (; j >= 4; j >>= 3) {
+        for (; j >= 64; j >>= 3) {
             bitonic_pass<3>(s, n2, k, j, tid, T);
             __syncthreads();
         }
+        bitonic_pass<4>(s, n2, k, 8, tid, T);
+        __syncthreads();
     }
     const uint64_t hi_word = (uint64_t)tile << 32;
     for (uint32_t i = tid; i < n; i += T) {
@@ -456,7 +473,7 @@ __global__ void __launch_bounds__(T) tile_sort_kernel(const uint2* __restrict__ 
     }
 }
 
-int launch_tile_binning(int P, int R, int max_tile, const Camera& cam, const int* radii, const GeomView& g,
+int launch_tile_binning(int P, int R, int max_tile, int n_small, const Camera& cam, const int* radii, const GeomView& g,
                         const BinningView& b, const ImageView& img, cudaStream_t stream, bool debug) {
     if (P <= 0 || R <= 0) return 0;
     const int tiles = cam.grid_x * cam.grid_y;
@@ -467,21 +484,21 @@ int launch_tile_binning(int P, int R, int max_tile, const Camera& cam, const int
     HS_LAUNCH_OK(stream, debug);
     prof_begin(ST_SORT, stream);
     const uint32_t small_cap = HS_TILE_SORT_SMALL;
-    {
-        uint32_t cap = 8;
+    if (n_small > 0) {
+        uint32_t cap = 16;
         while (cap < (uint32_t)max_tile && cap < small_cap) cap <<= 1;
-        tile_sort_kernel<128><<<tiles, 128, (cap + cap / 8) * sizeof(uint64_t), stream>>>(
+        tile_sort_kernel<128><<<tiles, 128, (cap + cap / 16) * sizeof(uint64_t), stream>>>(
             img.ranges, b.keys_unsorted, b.point_list, b.keys, 0u, small_cap);
         count_launch();
     }
     if ((uint32_t)max_tile > small_cap) {
         uint32_t cap = small_cap;
         while (cap < (uint32_t)max_tile) cap <<= 1;
-        auto k = tile_sort_kernel<1024>;
-        const size_t smem = (size_t)(cap + cap / 8) * sizeof(uint64_t);
+        auto k = tile_sort_kernel<512>;
+        const size_t smem = (size_t)(cap + cap / 16) * sizeof(uint64_t);
         HS_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k<<<tiles, 1024, smem, stream>>>(img.ranges, b.keys_unsorted, b.point_list, b.keys, small_cap,
-                                                          (uint32_t)HS_TILE_SORT_MAX);
+        k<<<tiles, 512, smem, stream>>>(img.ranges, b.keys_unsorted, b.point_list, b.keys, small_cap,
+                                         (uint32_t)HS_TILE_SORT_MAX);
         count_launch();
     }
     prof_end(ST_SORT, stream);

@@ -12,6 +12,10 @@ long long lib_calls();
 
 using namespace hs;
 
+// binning_hint (opaque to the caller): longest tile list in the low bits, flag = no tile in the small sort class
+#define HS_HINT_MASK 0x0fffffff
+#define HS_HINT_NO_SMALL 0x10000000
+
 static int make_camera(const hs_camera* c, Camera* cam) {
     if (c == nullptr) {
         set_error("hs_camera is NULL");
@@ -100,16 +104,16 @@ int hs_binning_state_layout(int R, size_t off[4]) {
 int hs_forward_geometry(const hs_camera* c, int P, const float* means3D, const float* opacities,
                         const float* scales, const float* rotations, const float* cov3D_precomp, int* radii,
                         void* geom_state, size_t geom_state_bytes, void* image_state, size_t image_state_bytes,
-                        int flags, int* num_rendered, int* max_tile_list, void* stream_) {
+                        int flags, int* num_rendered, int* binning_hint, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     Camera cam;
     if (make_camera(c, &cam)) return 1;
-    if (num_rendered == nullptr || max_tile_list == nullptr) {
-        set_error("num_rendered / max_tile_list is NULL");
+    if (num_rendered == nullptr || binning_hint == nullptr) {
+        set_error("num_rendered / binning_hint is NULL");
         return 1;
     }
     *num_rendered = 0;
-    *max_tile_list = 0;
+    *binning_hint = 0;
     if (P <= 0) return 0;
     if (means3D == nullptr || opacities == nullptr || radii == nullptr || geom_state == nullptr) {
         set_error("hs_forward_geometry: NULL argument");
@@ -145,7 +149,7 @@ int hs_forward_geometry(const hs_camera* c, int P, const float* means3D, const f
         HS_CUDA_OK(cudaMemcpyAsync(host, g.point_offsets + (P - 1), sizeof(int), cudaMemcpyDeviceToHost, stream));
         HS_CUDA_OK(cudaStreamSynchronize(stream));
         *num_rendered = host[0];
-        *max_tile_list = -1;   // unknown: hs_forward_render will use the global sort
+        *binning_hint = -1;   // unknown: hs_forward_render will use the global sort
         return 0;
     }
     // tile-bucket binning: per-tile counts in the preprocess pass, tile scan -> ranges, cursors, count, longest list
@@ -166,14 +170,15 @@ int hs_forward_geometry(const hs_camera* c, int P, const float* means3D, const f
     if (rc) return rc;
     rc = launch_tile_scan(cam, img, stream, debug);
     if (rc) return rc;
-    HS_CUDA_OK(cudaMemcpyAsync(host, img.info, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    HS_CUDA_OK(cudaMemcpyAsync(host, img.info, 3 * sizeof(int), cudaMemcpyDeviceToHost, stream));
     HS_CUDA_OK(cudaStreamSynchronize(stream));
     *num_rendered = host[0];
-    *max_tile_list = host[1];
+    // longest tile list, and whether any tile falls in the small sort class
+    *binning_hint = (host[1] > HS_HINT_MASK ? HS_HINT_MASK : host[1]) | (host[2] == 0 ? HS_HINT_NO_SMALL : 0);
     return 0;
 }
 
-int hs_forward_render(const hs_camera* c, int P, int S, int R, int max_tile_list, const float* colors,
+int hs_forward_render(const hs_camera* c, int P, int S, int R, int binning_hint, const float* colors,
                       const float* semantics,
                       const int* radii, void* geom_state, void* binning_state, size_t binning_state_bytes,
                       void* image_state, size_t image_state_bytes, float* out_color, float* out_semantic,
@@ -226,12 +231,14 @@ int hs_forward_render(const hs_camera* c, int P, int S, int R, int max_tile_list
     }
     const bool debug = c->debug != 0;
     int rc = 0;
-    if (max_tile_list >= 0 && max_tile_list <= HS_TILE_SORT_MAX) {
-        rc = launch_tile_binning(P, R, max_tile_list, cam, radii, g, b, img, stream, debug);
+    const int max_tile = binning_hint & HS_HINT_MASK;
+    if (binning_hint >= 0 && max_tile <= HS_TILE_SORT_MAX) {
+        rc = launch_tile_binning(P, R, max_tile, (binning_hint & HS_HINT_NO_SMALL) ? 0 : 1, cam, radii, g, b, img, stream,
+                                 debug);
     } else {
         // global radix sort: requested (HS_SORT_GLOBAL in hs_forward_geometry) or a tile list too long for the
         // shared-memory sort; in the second case the offsets scan has not run yet
-        if (max_tile_list >= 0 && P > 0) rc = launch_scan(P, g, stream, debug);
+        if (binning_hint >= 0 && P > 0) rc = launch_scan(P, g, stream, debug);
         if (rc) return rc;
         rc = launch_binning(P, R, cam, radii, g, b, img, stream, debug);
     }

@@ -97,7 +97,7 @@ int launch_preprocess(int P, const float* means3D, const float* scales, const fl
                       const GeomView& g, uint32_t* tile_count, cudaStream_t stream, bool debug);
 int launch_scan(int P, const GeomView& g, cudaStream_t stream, bool debug);
 int launch_tile_scan(const Camera& cam, const ImageView& img, cudaStream_t stream, bool debug);
-int launch_tile_binning(int P, int R, int max_tile, const Camera& cam, const int* radii, const GeomView& g,
+int launch_tile_binning(int P, int R, int max_tile, int n_small, const Camera& cam, const int* radii, const GeomView& g,
                         const BinningView& b, const ImageView& img, cudaStream_t stream, bool debug);
 int launch_binning(int P, int R, const Camera& cam, const int* radii, const GeomView& g, const BinningView& b,
                    const ImageView& img, cudaStream_t stream, bool debug);

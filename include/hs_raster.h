@@ -72,20 +72,20 @@ size_t hs_binning_state_bytes(int num_rendered);
 
 /* Stage 1 of the forward: per-Gaussian projection / cull / tile counting.
  * Writes radii[P] (int32, device), fills geom_state and the tile ranges inside image_state, and returns (HOST
- * pointers) the number of (Gaussian, tile) instances in *num_rendered and the length of the longest tile list in
- * *max_tile_list (-1 with HS_SORT_GLOBAL).  Synchronises `stream` once (the only host sync of a forward+backward).
+ * pointers) the number of (Gaussian, tile) instances in *num_rendered and, in *binning_hint, an opaque value that
+ * must be handed to hs_forward_render (it encodes the longest tile list; -1 with HS_SORT_GLOBAL).  Synchronises `stream` once (the only host sync of a forward+backward).
  * scales/rotations may be NULL iff cov3D_precomp is given, and vice versa.  flags: 0 or HS_SORT_GLOBAL. */
 int hs_forward_geometry(const hs_camera* cam, int P, const float* means3D, const float* opacities,
                         const float* scales, const float* rotations, const float* cov3D_precomp, int* radii,
                         void* geom_state, size_t geom_state_bytes, void* image_state, size_t image_state_bytes,
-                        int flags, int* num_rendered, int* max_tile_list, void* stream);
+                        int flags, int* num_rendered, int* binning_hint, void* stream);
 
 /* Stage 2 of the forward: instance scatter + per-tile sort (or key duplication, global sort and range
- * identification), alpha compositing.  num_rendered and max_tile_list are the values stage 1 returned; image_state
+ * identification), alpha compositing.  num_rendered and binning_hint are the values stage 1 returned; image_state
  * is the buffer stage 1 filled.
  * Outputs (device): out_color[3,H,W], out_semantic[S,H,W] (S > 0), out_depth[1,H,W], out_median_depth[1,H,W],
  * out_opacity[1,H,W], out_mask[1,H,W] (may be NULL; only written when S == 0).  No output needs initialisation. */
-int hs_forward_render(const hs_camera* cam, int P, int S, int num_rendered, int max_tile_list, const float* colors,
+int hs_forward_render(const hs_camera* cam, int P, int S, int num_rendered, int binning_hint, const float* colors,
                       const float* semantics, const int* radii, void* geom_state, void* binning_state,
                       size_t binning_state_bytes, void* image_state, size_t image_state_bytes, float* out_color,
                       float* out_semantic, float* out_depth, float* out_median_depth, float* out_opacity,
