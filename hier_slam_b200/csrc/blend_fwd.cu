@@ -25,8 +25,23 @@ struct FwdCfg {
                                                     3 * sizeof(int) + sizeof(uint32_t));
 };
 
+// Packed FP32 FMA (sm_100 FFMA2): two IEEE fused multiply-adds per issue slot, bit-identical to two FFMAs.
+__device__ __forceinline__ void ffma2(unsigned long long& acc, const unsigned long long a, const unsigned long long b) {
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
+}
+__device__ __forceinline__ unsigned long long pack2(const float lo, const float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ float2 unpack2(const unsigned long long v) {
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
+
 template <int S, bool MASK>
-__global__ void __launch_bounds__(256) blend_forward_kernel(
+__global__ void __launch_bounds__(256, (S <= 26 ? 3 : 1)) blend_forward_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H, int grid_x,
     const float2* __restrict__ means2D, const float* __restrict__ colors, const float* __restrict__ depths,
     const float* __restrict__ semantics, const float4* __restrict__ conic_opacity, float* __restrict__ final_T,
@@ -62,9 +77,11 @@ __global__ void __launch_bounds__(256) blend_forward_kernel(
 
     float T = 1.0f;
     uint32_t last_contributor = 0;
-    float acc[4 + S];
+    static_assert((4 + S) % 2 == 0, "feature rows are blended two channels per FFMA2");
+    constexpr int F2 = (4 + S) / 2;
+    unsigned long long acc2[F2];   // packed channel pairs: (r g) (b depth) (s0 s1) ...
 #pragma unroll
-    for (int k = 0; k < 4 + S; k++) acc[k] = 0.f;
+    for (int k = 0; k < F2; k++) acc2[k] = 0ull;
     float median_D = 15.0f;
     float M = 0.f;
 
@@ -142,38 +159,69 @@ __global__ void __launch_bounds__(256) blend_forward_kernel(
         }
         __syncthreads();
 
-        for (int j = 0; !done && j < nb; j++) {
-            if (!((s_mask[j] >> warp) & 1)) continue;   // warp-uniform
-            const float2 xy = s_xy[j];
-            const float2 d = {xy.x - pixf.x, xy.y - pixf.y};
-            const float4 con_o = s_co[j];
-            const float power = gauss_power(d, con_o);
-            if (power > 0.0f) continue;
-            const float alpha = min(0.99f, con_o.w * exp(power));
-            if (alpha < 1.0f / 255.0f) continue;
-            const float test_T = T * (1 - alpha);
-            if (test_T < 0.0001f) {
-                done = true;
-                continue;
-            }
-            const float w = alpha * T;
-            const float4* f4 = reinterpret_cast<const float4*>(s_feat + j * FS);
+        // The inner loop is written without divergent branches: all 32 lanes of a warp stay together, a lane that
+        // does not take a Gaussian (outside its footprint, alpha < 1/255, already saturated) blends it with weight 0
+        // (x + 0 * f == x bit for bit for finite f), and the only branches are warp-uniform votes.  Gaussians that
+        // survive the strip cull are taken U at a time so that the U alpha evaluations (independent of T) overlap.
+        constexpr int U = 4;
+#pragma unroll 1
+        for (int k0 = 0; k0 < nb; k0 += 32) {
+            const int jl = k0 + (tid & 31);
+            uint32_t bits = __ballot_sync(0xffffffffu, jl < nb && ((s_mask[jl] >> warp) & 1));
+            if (__all_sync(0xffffffffu, done)) break;
+#pragma unroll 1
+            while (bits) {
+                int jj[U];
+                float al[U];
+                bool ok[U];
 #pragma unroll
-            for (int q = 0; q < (4 + S + 3) / 4; q++) {
-                const float4 v = f4[q];
-                acc[4 * q] = fmaf(v.x, w, acc[4 * q]);
-                if (4 * q + 1 < 4 + S) acc[4 * q + 1] = fmaf(v.y, w, acc[4 * q + 1]);
-                if (4 * q + 2 < 4 + S) acc[4 * q + 2] = fmaf(v.z, w, acc[4 * q + 2]);
-                if (4 * q + 3 < 4 + S) acc[4 * q + 3] = fmaf(v.w, w, acc[4 * q + 3]);
+                for (int u = 0; u < U; u++) {
+                    const bool have = bits != 0;
+                    jj[u] = have ? k0 + __ffs(bits) - 1 : jj[0];
+                    bits &= bits - 1;
+                    const float2 xy = s_xy[jj[u]];
+                    const float2 d = {xy.x - pixf.x, xy.y - pixf.y};
+                    const float4 con_o = s_co[jj[u]];
+                    const float power = gauss_power(d, con_o);
+                    al[u] = min(0.99f, con_o.w * exp(power));
+                    ok[u] = have && !(power > 0.0f) && !(al[u] < 1.0f / 255.0f);
+                }
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    bool v = ok[u] && !done;
+                    const float test_T = T * (1 - al[u]);
+                    if (v && test_T < 0.0001f) {
+                        done = true;
+                        v = false;
+                    }
+                    if (!__any_sync(0xffffffffu, v)) continue;   // warp-uniform
+                    const float w = v ? al[u] * T : 0.f;
+                    const ulonglong2* f4 = reinterpret_cast<const ulonglong2*>(s_feat + jj[u] * FS);
+                    float depth_j;
+#pragma unroll
+                    for (int q = 0; q < (4 + S + 3) / 4; q++) {
+                        const ulonglong2 f = f4[q];
+                        if (q == 0) depth_j = unpack2(f.y).y;
+                        ffma2(acc2[2 * q], f.x, pack2(w, w));
+                        if (2 * q + 1 < F2) ffma2(acc2[2 * q + 1], f.y, pack2(w, w));
+                    }
+                    if (MASK) M += w;
+                    if (v && T > 0.5f && test_T < 0.5) median_D = depth_j;
+                    T = v ? test_T : T;
+                    last_contributor = v ? i * B + jj[u] + 1 : last_contributor;
+                }
             }
-            if (MASK) M += w;
-            if (T > 0.5f && test_T < 0.5) median_D = f4[0].w;
-            T = test_T;
-            last_contributor = i * B + j + 1;
         }
     }
     __pipeline_wait_prior(0);
 
+    float acc[4 + S];
+#pragma unroll
+    for (int k = 0; k < F2; k++) {
+        const float2 a = unpack2(acc2[k]);
+        acc[2 * k] = a.x;
+        acc[2 * k + 1] = a.y;
+    }
     if (inside) {
         const size_t HW = (size_t)H * W;
         final_T[pix_id] = T;
