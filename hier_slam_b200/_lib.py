@@ -9,7 +9,7 @@ import os
 from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_size_t, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libhsraster.so")
+LIB_PATH = os.environ.get("HS_LIB", os.path.join(HERE, "libhsraster.so"))
 
 # every symbol include/hs_raster.h declares (tests check that the library exports all of them)
 EXPORTED_SYMBOLS = [

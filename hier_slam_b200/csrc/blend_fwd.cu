@@ -12,6 +12,13 @@
 #include "hs_common.cuh"
 #include <cuda_pipeline.h>
 
+#ifndef HS_FWD_U
+#define HS_FWD_U 2      // Gaussians whose alpha is evaluated together (independent dependency chains per lane)
+#endif
+#ifndef HS_FWD_OCC
+#define HS_FWD_OCC 3    // CTAs per SM the narrow instantiations (S <= 26) are compiled for
+#endif
+
 namespace hs {
 
 template <int S>
@@ -41,7 +48,7 @@ __device__ __forceinline__ float2 unpack2(const unsigned long long v) {
 }
 
 template <int S, bool MASK>
-__global__ void __launch_bounds__(256, (S <= 26 ? 3 : 1)) blend_forward_kernel(
+__global__ void __launch_bounds__(256, (S <= 26 ? HS_FWD_OCC : 1)) blend_forward_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H, int grid_x,
     const float2* __restrict__ means2D, const float* __restrict__ colors, const float* __restrict__ depths,
     const float* __restrict__ semantics, const float4* __restrict__ conic_opacity, float* __restrict__ final_T,
@@ -163,7 +170,7 @@ __global__ void __launch_bounds__(256, (S <= 26 ? 3 : 1)) blend_forward_kernel(
         // does not take a Gaussian (outside its footprint, alpha < 1/255, already saturated) blends it with weight 0
         // (x + 0 * f == x bit for bit for finite f), and the only branches are warp-uniform votes.  Gaussians that
         // survive the strip cull are taken U at a time so that the U alpha evaluations (independent of T) overlap.
-        constexpr int U = 4;
+        constexpr int U = HS_FWD_U;
 #pragma unroll 1
         for (int k0 = 0; k0 < nb; k0 += 32) {
             const int jl = k0 + (tid & 31);
