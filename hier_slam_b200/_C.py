@@ -22,7 +22,6 @@ from . import _lib
 # 'exact' : the mathematically intended gradient.
 SEM_ALPHA_GRAD = os.environ.get("HS_SEM_ALPHA_GRAD", "ref")
 NO_CULL = os.environ.get("HS_NO_CULL", "0") == "1"
-FWD_MMA = os.environ.get("HS_FWD_MMA", "0") == "1"     # opt into the tensor-core blend forward (slower; for study)
 BWD_SIMT = os.environ.get("HS_BWD_SIMT", "0") == "1"   # SIMT blend backward instead of the tensor-core one
 SORT_GLOBAL = os.environ.get("HS_SORT_GLOBAL", "0") == "1"   # reference-style global radix sort instead of tile buckets
 
@@ -130,7 +129,7 @@ def _forward(background, means3D, colors, semantics, opacity, scales, rotations,
         out_median = torch.empty(1, H, W, **fopt)
         out_opacity = torch.empty(1, H, W, **fopt)
         out_mask = None if semantic else torch.empty(1, H, W, **fopt)
-        flags = (_lib.HS_NO_CULL if NO_CULL else 0) | (_lib.HS_FWD_MMA if FWD_MMA else 0)
+        flags = _lib.HS_NO_CULL if NO_CULL else 0
         _lib.check(lib.hs_forward_render(ctypes.byref(cam), P, S, num_rendered, int(hint.value), _ptr(colors_c),
                                          _ptr(sem_c),
                                          _ptr(radii), _ptr(geomBuffer), _ptr(binningBuffer), bin_bytes,
@@ -303,10 +302,11 @@ def state_views(P: int, H: int, W: int, R: int, geomBuffer, binningBuffer, imgBu
     out["n_contrib"] = view(imgBuffer, off[1], N, torch.int32)
     out["ranges"] = view(imgBuffer, off[2], 2 * tiles, torch.int32).view(tiles, 2)
     if R > 0:
-        off = (ctypes.c_size_t * 4)()
+        off = (ctypes.c_size_t * 5)()
         lib.hs_binning_state_layout(R, off)
         out["point_list"] = view(binningBuffer, off[0], R, torch.int32)
         out["point_list_unsorted"] = view(binningBuffer, off[1], R, torch.int32)
         out["keys"] = view(binningBuffer, off[2], R, torch.int64)
         out["keys_unsorted"] = view(binningBuffer, off[3], R, torch.int64)
+        out["strip_hits"] = view(binningBuffer, off[4], R, torch.uint8)
     return out

@@ -24,7 +24,6 @@ STAGES = ["preprocess", "scan", "duplicate", "sort", "ranges", "blend_fwd", "ble
 HS_SEM_ALPHA_EXACT = 1
 HS_NO_CULL = 2
 HS_BWD_SIMT = 4
-HS_FWD_MMA = 8
 HS_SORT_GLOBAL = 32
 
 

@@ -133,6 +133,7 @@ int binning_view(char* base, size_t R, BinningView* v) {
     carve(p, v->point_list_unsorted, R);
     carve(p, v->keys, R);
     carve(p, v->keys_unsorted, R);
+    carve(p, v->strip_hits, R);
     v->sort_temp_bytes = 0;
     if (R > 0) {
         HS_CUDA_OK(cub::DeviceRadixSort::SortPairs(nullptr, v->sort_temp_bytes, v->keys_unsorted, v->keys,

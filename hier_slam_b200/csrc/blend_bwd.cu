@@ -283,7 +283,11 @@ int launch_blend_backward(int S, const Camera& cam, const GeomView& g, const Bin
                           const float* dL_opacity, float* dL_dmean2D, float* dL_dconic, float* dL_dopacity,
                           float* dL_dcolors, float* dL_dsemantics, float* dL_ddepths, int flags,
                           cudaStream_t stream, bool debug) {
-    const bool exact = (flags & HS_FLAG_SEM_ALPHA_EXACT) != 0 && S > 0 && dL_sem != nullptr;
+    // No upstream semantic gradient (tracking: the pose loss uses colour and depth only, scripts/hierslam.py:780-796):
+    // dL/dsemantics is identically zero and the semantic channels cannot reach dL/dalpha in either Q1 mode, so the
+    // non-semantic instantiation computes exactly the same gradients; dL_dsemantics keeps the caller's zeros.
+    if (dL_sem == nullptr) S = 0;
+    const bool exact = (flags & HS_FLAG_SEM_ALPHA_EXACT) != 0 && S > 0;
     if (!exact && !(flags & HS_FLAG_BWD_SHUFFLE) && S <= 74)  // S = 102 would not fit in shared memory
         return launch_blend_backward_mma(S, cam, g, b, img, bg, colors, dL_color, dL_sem, dL_depth, dL_median,
                                          dL_opacity, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolors, dL_dsemantics,

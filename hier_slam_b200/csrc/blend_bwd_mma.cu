@@ -53,7 +53,8 @@ __global__ void __launch_bounds__(32 * NW, (MmaCfg<S>::B_IN_REGS ? (16 / NW) : 1
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H, int grid_x,
     const float* __restrict__ bg_color, const float2* __restrict__ means2D, const float4* __restrict__ conic_opacity,
     const float* __restrict__ colors, const float* __restrict__ depths, const float* __restrict__ final_Ts,
-    const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dpixels,
+    const uint32_t* __restrict__ n_contrib, const uint8_t* __restrict__ strip_hits,
+    const float* __restrict__ dL_dpixels,
     const float* __restrict__ dL_dpixels_sem, const float* __restrict__ dL_dpixel_depths,
     const float* __restrict__ dL_dpixel_medians, const float* __restrict__ dL_dpixel_opacitys,
     float* __restrict__ dL_dmean2D, float* __restrict__ dL_dconic2D, float* __restrict__ dL_dopacity,
@@ -71,7 +72,8 @@ __global__ void __launch_bounds__(32 * NW, (MmaCfg<S>::B_IN_REGS ? (16 / NW) : 1
     float2* s_xy2 = reinterpret_cast<float2*>(s_g + NW * 16 * WS); // [2][B]
     int* s_id3 = reinterpret_cast<int*>(s_xy2 + 2 * B);          // [3][B] ring of Gaussian ids
     uint32_t* s_valid = reinterpret_cast<uint32_t*>(s_id3 + 3 * B);   // [NW] rows of s_part each warp wrote this round
-    float* s_dL = reinterpret_cast<float*>(s_valid + 8);         // [32 NW][DS]   (only when !BREG)
+    uint32_t* s_hit3 = s_valid + 8;                              // [3][B] strips the forward blended each entry into
+    float* s_dL = reinterpret_cast<float*>(s_hit3 + 3 * B);      // [32 NW][DS]   (only when !BREG)
     __shared__ int s_maxc;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -198,8 +200,12 @@ __global__ void __launch_bounds__(32 * NW, (MmaCfg<S>::B_IN_REGS ? (16 / NW) : 1
     };
     auto fetch_ids = [&](int r) {
         const int n = min(B, total - r * B);
-        if (r < rounds && tid < n) __pipeline_memcpy_async(s_id3 + (r % 3) * B + tid, point_list + list_pos(r, tid), 4);
+        if (r < rounds && tid < n) {
+            __pipeline_memcpy_async(s_id3 + (r % 3) * B + tid, point_list + list_pos(r, tid), 4);
+            s_hit3[(r % 3) * B + tid] = strip_hits[list_pos(r, tid)];
+        }
     };
+    const int strip = (blockIdx.y % SLABS) * NW + warp;   // this warp's 16x2 strip of the tile
     fetch_ids(0);
     fetch_ids(1);
     __pipeline_commit();
@@ -218,39 +224,46 @@ __global__ void __launch_bounds__(32 * NW, (MmaCfg<S>::B_IN_REGS ? (16 / NW) : 1
         const float4* s_co = s_co2 + (i & 1) * B;
         const float4* s_feat = s_feat2 + (i & 1) * B;
         const int* s_id = s_id3 + (i % 3) * B;
+        const uint32_t* s_hit = s_hit3 + (i % 3) * B;
         uint32_t valid_rows = 0;   // warp-uniform: rows (Gaussians of this round) this warp contributed to
 
         for (int c0 = 0; c0 < nb_; c0 += 16) {
                         // ---------------- phase 1: 16 Gaussians, back to front ------------------------------------------------
             // (a) alpha of 8 Gaussians at a time, branch-free: eight independent dependency chains per lane (ILP);
             // (b) the sequential transmittance / colour-behind recurrences, skipped per Gaussian by a warp vote.
+            // Entries of this chunk that the forward blended into this warp's strip (exactly the set with a
+            // contributing lane; every other entry has act == false in all lanes and is not even evaluated).
+            uint32_t todo = __ballot_sync(0xffffffffu, lane < 16 && c0 + lane < nb_ && ((s_hit[c0 + lane] >> strip) & 1u));
             uint32_t act_mask = 0;
 #pragma unroll 1   // keep the loop rolled: the kernel must stay inside the instruction cache
-            for (int sub = 0; sub < 2; sub++) {
-                const int jb = c0 + 8 * sub;
-                if (jb >= nb_) break;
+            while (todo) {
                 float oG[8];
+                int rowv[8];
                 uint32_t abits = 0;
 #pragma unroll
                 for (int u = 0; u < 8; u++) {
-                    const int j = min(jb + u, nb_ - 1);
+                    const bool have = todo != 0;
+                    rowv[u] = have ? __ffs(todo) - 1 : rowv[0];
+                    todo &= todo - 1;
+                    const int j = c0 + rowv[u];
                     const float2 xy = s_xy[j];
                     const float2 d = {xy.x - pixf.x, xy.y - pixf.y};
                     const float4 con_o = s_co[j];
                     const float power = gauss_power(d, con_o);
                     const float og = con_o.w * exp(power);
-                    const int gi = total - 1 - i * B - (jb + u);
-                    const bool active = (jb + u < nb_) && (gi < last_contributor) && !(power > 0.0f) &&
+                    const int gi = total - 1 - i * B - j;
+                    const bool active = have && (gi < last_contributor) && !(power > 0.0f) &&
                                         !(min(0.99f, og) < 1.0f / 255.0f);
                     oG[u] = og;
                     abits |= (active ? 1u : 0u) << u;
                 }
                 const uint32_t any_bits = __reduce_or_sync(0xffffffffu, abits);
-                act_mask |= any_bits << (8 * sub);
 #pragma unroll
                 for (int u = 0; u < 8; u++) {
                     if (!((any_bits >> u) & 1)) continue;   // warp-uniform
-                    const int j = jb + u;
+                    const int row = rowv[u];
+                    const int j = c0 + row;
+                    act_mask |= 1u << row;
                     const bool act = (abits >> u) & 1;
                     const float alpha = min(0.99f, oG[u]);
                     // same IEEE division as the reference (backward.cu:815): the reconstructed transmittance decides
@@ -265,8 +278,8 @@ __global__ void __launch_bounds__(32 * NW, (MmaCfg<S>::B_IN_REGS ? (16 / NW) : 1
                     if (bg_dot_dpixel != 0.f) dL_dalpha -= __fdividef(T_final, 1.f - alpha) * bg_dot_dpixel;
                     if (act && test_T > 0.5f && T < 0.5 && dL_median != 0.f)
                         atomicAdd(dL_ddepths + s_id[j], dL_median);   // the Gaussian that crossed T = 0.5 (quirk Q4)
-                    wm[(8 * sub + u) * WS + lane] = act ? alpha * test_T : 0.f;
-                    gm[(8 * sub + u) * WS + lane] = act ? dL_dalpha * oG[u] : 0.f;   // dL/dG * G = (o dL/dalpha) G
+                    wm[row * WS + lane] = act ? alpha * test_T : 0.f;
+                    gm[row * WS + lane] = act ? dL_dalpha * oG[u] : 0.f;   // dL/dG * G = (o dL/dalpha) G
                     accum_q = act ? acc_new : accum_q;
                     last_q = act ? q : last_q;
                     last_alpha = act ? alpha : last_alpha;
@@ -399,7 +412,7 @@ static int launch_bwd_mma_t(const Camera& cam, const GeomView& g, const BinningV
                             float* dL_dconic, float* dL_dopacity, float* dL_dcolors, float* dL_dsemantics,
                             float* dL_ddepths, cudaStream_t stream, bool debug) {
     using Cfg = MmaCfg<S>;
-    size_t smem = (size_t)Cfg::BATCH * (4 * sizeof(float4) + NW * Cfg::KA * sizeof(float) + 2 * sizeof(float2) + 3 * sizeof(int)) +
+    size_t smem = (size_t)Cfg::BATCH * (4 * sizeof(float4) + NW * Cfg::KA * sizeof(float) + 2 * sizeof(float2) + 6 * sizeof(int)) +
                   (size_t)2 * NW * 16 * Cfg::WS * sizeof(float) + 8 * sizeof(uint32_t);
     if (!Cfg::B_IN_REGS) smem += (size_t)32 * NW * Cfg::DS * sizeof(float);
     auto k = blend_backward_mma_kernel<S, NW>;
@@ -407,7 +420,7 @@ static int launch_bwd_mma_t(const Camera& cam, const GeomView& g, const BinningV
     dim3 grid(cam.grid_x, cam.grid_y * (8 / NW), 1);
     prof_begin(ST_BLEND_BWD, stream);
     k<<<grid, 32 * NW, smem, stream>>>(img.ranges, b.point_list, cam.W, cam.H, cam.grid_x, bg, g.means2D, g.conic_opacity,
-                                   colors, g.depths, img.final_T, img.n_contrib, dL_color, dL_sem, dL_depth, dL_median,
+                                   colors, g.depths, img.final_T, img.n_contrib, b.strip_hits, dL_color, dL_sem, dL_depth, dL_median,
                                    dL_opacity, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolors, dL_dsemantics,
                                    dL_ddepths);
     prof_end(ST_BLEND_BWD, stream);

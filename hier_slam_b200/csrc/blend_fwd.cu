@@ -29,7 +29,7 @@ struct FwdCfg {
     static constexpr int SCH = (S % 4 == 0) ? 4 : (S % 2 == 0) ? 2 : 1;   // floats per cp.async of a semantic row
     // double-buffered staging: conic+opacity, feature rows, centres; ring of 3 id arrays; strip masks
     static constexpr size_t SMEM = (size_t)BATCH * (2 * sizeof(float4) + 2 * FS * sizeof(float) + 2 * sizeof(float2) +
-                                                    3 * sizeof(int) + sizeof(uint32_t));
+                                                    3 * sizeof(int) + sizeof(uint32_t)) + 2 * 8 * (BATCH / 32) * sizeof(uint32_t);
 };
 
 // Packed FP32 FMA (sm_100 FFMA2): two IEEE fused multiply-adds per issue slot, bit-identical to two FFMAs.
@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(256, (S <= 26 ? HS_FWD_OCC : 1)) blend_forward
     const float* __restrict__ semantics, const float4* __restrict__ conic_opacity, float* __restrict__ final_T,
     uint32_t* __restrict__ n_contrib, float* __restrict__ out_color, float* __restrict__ out_depth,
     float* __restrict__ out_median, float* __restrict__ out_semantic, float* __restrict__ out_opacity,
-    float* __restrict__ out_mask, int flags) {
+    float* __restrict__ out_mask, uint8_t* __restrict__ strip_hits, int flags) {
     using Cfg = FwdCfg<S>;
     constexpr int B = Cfg::BATCH;
     constexpr int FS = Cfg::FS;
@@ -65,6 +65,7 @@ __global__ void __launch_bounds__(256, (S <= 26 ? HS_FWD_OCC : 1)) blend_forward
     float2* s_xy2 = reinterpret_cast<float2*>(s_feat2 + 2 * B * FS); // [2][B]
     int* s_id3 = reinterpret_cast<int*>(s_xy2 + 2 * B);              // [3][B]
     uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_id3 + 3 * B);   // [B] bit w: Gaussian may touch warp w's strip
+    uint32_t* s_hit2 = s_mask + B;   // [2][B/32][8] bit j%32 of word (j/32, w): warp w blended Gaussian j of the batch
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
@@ -137,10 +138,24 @@ __global__ void __launch_bounds__(256, (S <= 26 ? HS_FWD_OCC : 1)) blend_forward
     gather_batch(0);
     __pipeline_commit();
 
-    for (int i = 0; i < rounds; i++) {
+    for (int i = 0; i <= rounds; i++) {
         __pipeline_wait_prior(0);
         // batch i has landed and the ids of batch i+1 are present; also the block-wide early-out vote
-        if (__syncthreads_count(done) == 256) break;
+        const bool all_done = __syncthreads_count(done) == 256;
+        if (i > 0) {
+            // which strips blended which entries of batch i-1: saved for the backward, which then visits exactly the
+            // (strip, Gaussian) pairs that contributed
+            const int np = min(B, total - (i - 1) * B);
+            if (tid < np) {
+                const uint32_t* h = s_hit2 + (((i - 1) & 1) * (B / 32) + (tid >> 5)) * 8;
+                uint32_t m = 0;
+#pragma unroll
+                for (int w8 = 0; w8 < 8; w8++) m |= ((h[w8] >> (tid & 31)) & 1u) << w8;
+                strip_hits[range.x + (i - 1) * B + tid] = (uint8_t)m;
+            }
+        }
+        if (all_done || i == rounds) break;
+        uint32_t* s_hit = s_hit2 + (i & 1) * (B / 32) * 8;
         const int nb = min(B, total - i * B);
         if (i + 1 < rounds) gather_batch(i + 1);
         fetch_ids(i + 2);
@@ -175,7 +190,8 @@ __global__ void __launch_bounds__(256, (S <= 26 ? HS_FWD_OCC : 1)) blend_forward
         for (int k0 = 0; k0 < nb; k0 += 32) {
             const int jl = k0 + (tid & 31);
             uint32_t bits = __ballot_sync(0xffffffffu, jl < nb && ((s_mask[jl] >> warp) & 1));
-            if (__all_sync(0xffffffffu, done)) break;
+            if (__all_sync(0xffffffffu, done)) bits = 0;
+            uint32_t hit_bits = 0;   // warp-uniform: entries of this group of 32 that some lane blended
 #pragma unroll 1
             while (bits) {
                 int jj[U];
@@ -202,6 +218,7 @@ __global__ void __launch_bounds__(256, (S <= 26 ? HS_FWD_OCC : 1)) blend_forward
                         v = false;
                     }
                     if (!__any_sync(0xffffffffu, v)) continue;   // warp-uniform
+                    hit_bits |= 1u << (jj[u] - k0);
                     const float w = v ? al[u] * T : 0.f;
                     const ulonglong2* f4 = reinterpret_cast<const ulonglong2*>(s_feat + jj[u] * FS);
                     float depth_j;
@@ -218,6 +235,7 @@ __global__ void __launch_bounds__(256, (S <= 26 ? HS_FWD_OCC : 1)) blend_forward
                     last_contributor = v ? i * B + jj[u] + 1 : last_contributor;
                 }
             }
+            if ((tid & 31) == 0) s_hit[(k0 >> 5) * 8 + warp] = hit_bits;
         }
     }
     __pipeline_wait_prior(0);
@@ -259,13 +277,13 @@ static int launch_fwd_t(const Camera& cam, const GeomView& g, const BinningView&
         HS_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k<<<grid, 256, smem, stream>>>(img.ranges, b.point_list, cam.W, cam.H, cam.grid_x, g.means2D, colors, g.depths,
                                        semantics, g.conic_opacity, img.final_T, img.n_contrib, out_color, out_depth,
-                                       out_median, out_semantic, out_opacity, out_mask, flags);
+                                       out_median, out_semantic, out_opacity, out_mask, b.strip_hits, flags);
     } else {
         auto k = blend_forward_kernel<S, false>;
         HS_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k<<<grid, 256, smem, stream>>>(img.ranges, b.point_list, cam.W, cam.H, cam.grid_x, g.means2D, colors, g.depths,
                                        semantics, g.conic_opacity, img.final_T, img.n_contrib, out_color, out_depth,
-                                       out_median, out_semantic, out_opacity, out_mask, flags);
+                                       out_median, out_semantic, out_opacity, out_mask, b.strip_hits, flags);
     }
     prof_end(ST_BLEND_FWD, stream);
     HS_LAUNCH_OK(stream, debug);
@@ -276,12 +294,6 @@ int launch_blend_forward(int S, const Camera& cam, const GeomView& g, const Binn
                          const float* colors, const float* semantics, float* out_color, float* out_semantic,
                          float* out_depth, float* out_median, float* out_opacity, float* out_mask, int flags,
                          cudaStream_t stream, bool debug) {
-    // The tensor-core forward (blend_fwd_mma.cu) is opt-in: on B200 the per-pixel alpha evaluation, not the channel
-    // blend, dominates the forward, and the SIMT blend below is faster at every measured S
-    // (c2, S = 26: 536 us vs 894 us; c5, S = 74: 438 us vs 943 us).
-    if ((flags & HS_FLAG_FWD_MMA) && S <= 74)
-        return launch_blend_forward_mma(S, cam, g, b, img, colors, semantics, out_color, out_semantic, out_depth,
-                                        out_median, out_opacity, out_mask, stream, debug);
 #define HS_FWD_CASE(SV)                                                                                      \
     case SV:                                                                                                 \
         return launch_fwd_t<SV>(cam, g, b, img, colors, semantics, out_color, out_semantic, out_depth,       \

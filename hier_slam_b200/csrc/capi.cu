@@ -91,13 +91,14 @@ int hs_image_state_layout(int H, int W, size_t off[3]) {
     off[2] = (size_t)v.ranges;
     return 0;
 }
-int hs_binning_state_layout(int R, size_t off[4]) {
+int hs_binning_state_layout(int R, size_t off[5]) {
     BinningView v;
     if (binning_view(nullptr, (size_t)R, &v)) return 2;
     off[0] = (size_t)v.point_list;
     off[1] = (size_t)v.point_list_unsorted;
     off[2] = (size_t)v.keys;
     off[3] = (size_t)v.keys_unsorted;
+    off[4] = (size_t)v.strip_hits;
     return 0;
 }
 

@@ -74,6 +74,7 @@ struct BinningView {
     uint32_t* point_list_unsorted; // u32[R]
     uint64_t* keys;                // u64[R] sorted (tile << 32 | depth bits)
     uint64_t* keys_unsorted;       // u64[R]
+    uint8_t* strip_hits;           // u8[R]  bit w: the forward blended this list entry into warp strip w (rows 2w, 2w+1)
     char* sort_temp;
     size_t sort_temp_bytes;
     size_t total_bytes;
@@ -105,10 +106,6 @@ int launch_blend_forward(int S, const Camera& cam, const GeomView& g, const Binn
                          const float* colors, const float* semantics, float* out_color, float* out_semantic,
                          float* out_depth, float* out_median, float* out_opacity, float* out_mask, int flags,
                          cudaStream_t stream, bool debug);
-int launch_blend_forward_mma(int S, const Camera& cam, const GeomView& g, const BinningView& b, const ImageView& img,
-                             const float* colors, const float* semantics, float* out_color, float* out_semantic,
-                             float* out_depth, float* out_median, float* out_opacity, float* out_mask,
-                             cudaStream_t stream, bool debug);
 int launch_blend_backward(int S, const Camera& cam, const GeomView& g, const BinningView& b, const ImageView& img,
                           const float* bg, const float* colors, const float* semantics, const float* dL_color,
                           const float* dL_sem, const float* dL_depth, const float* dL_median,
@@ -167,7 +164,6 @@ enum : int {
     HS_FLAG_SORT_CUB = 32,         // binning: reference-style scan + duplicate + global radix sort (CUB) instead of
                                    // the tile-bucket sort (identical sorted keys / lists / ranges)
     HS_FLAG_SEM_UNALIGNED = 16,    // internal: semantics base pointer is only 4-byte aligned (scalar cp.async)
-    HS_FLAG_FWD_MMA = 8,           // forward: opt into the tensor-core blend (slower than SIMT on B200; kept for study)
     HS_FLAG_BWD_SHUFFLE = 4,       // backward: SIMT warp-shuffle reduction instead of the tensor-core path
 };
 

@@ -39,7 +39,6 @@ extern "C" {
                                 gradient).  Default (0) reproduces the reference, whose kernel reads the semantic
                                 feature from a never-written scratch buffer (backward.cu:834, rasterizer_impl.cu:673). */
 #define HS_BWD_SIMT 4        /* backward: use the SIMT (warp-shuffle) blend backward instead of the tensor-core one */
-#define HS_FWD_MMA 8         /* forward: opt into the tensor-core (3xTF32 mma) blend; measured slower than the SIMT blend */
 #define HS_NO_CULL 2         /* forward: disable the conservative per-warp footprint test (results are identical) */
 #define HS_SORT_GLOBAL 32    /* hs_forward_geometry: reference-style binning (offsets scan, key duplication, one global
                                 radix sort) instead of the default per-tile bucket sort; sorted keys, tile lists and
@@ -124,10 +123,10 @@ long long hs_library_call_count(void);
 /* Test / debugging aid: byte offsets of the arrays inside the opaque state buffers.
  *   geom    : [depths f32[P], means2D f32[2P], conic_opacity f32[4P], tiles_touched u32[P], point_offsets u32[P]]
  *   image   : [final_T f32[N], n_contrib u32[N], ranges u32[2*tiles]]
- *   binning : [point_list u32[R], point_list_unsorted u32[R], keys u64[R], keys_unsorted u64[R]] */
+ *   binning : [point_list u32[R], point_list_unsorted u32[R], keys u64[R], keys_unsorted u64[R], strip_hits u8[R]] */
 int hs_geom_state_layout(int P, size_t offsets[5]);
 int hs_image_state_layout(int image_height, int image_width, size_t offsets[3]);
-int hs_binning_state_layout(int num_rendered, size_t offsets[4]);
+int hs_binning_state_layout(int num_rendered, size_t offsets[5]);
 
 #ifdef __cplusplus
 }

@@ -15,7 +15,6 @@ settings = pt.make_settings(GaussianRasterizationSettings, cfg)
 lib = _lib.load()
 for simt in (False, True):
     _C.BWD_SIMT = simt
-    _C.FWD_MMA = False
     for _ in range(3):
         f = pt.run_forward(_C, settings, scene); g = pt.run_backward(_C, settings, scene, f, grads)
     torch.cuda.synchronize()
@@ -26,15 +25,6 @@ for simt in (False, True):
     prof = _lib.profile_read(); lib.hs_profile_enable(0)
     print(json.dumps({"config": key, "bwd_simt": simt, **{k: round(v[0] / v[1] * 1e3, 1) for k, v in prof.items()}}))
 _C.BWD_SIMT = False
-_C.FWD_MMA = True
-fm = pt.run_forward(_C, settings, scene)
-_C.FWD_MMA = False
-fs = pt.run_forward(_C, settings, scene)
-P, H, W = scene["means3D"].shape[0], cfg.height, cfg.width
-sm = _C.state_views(P, H, W, fm["R"], fm["geomBuffer"], fm["binningBuffer"], fm["imgBuffer"])
-ss = _C.state_views(P, H, W, fs["R"], fs["geomBuffer"], fs["binningBuffer"], fs["imgBuffer"])
-print("fwd mma vs simt: n_contrib mismatches", pt.bits_equal(sm["n_contrib"], ss["n_contrib"]), "final_T", pt.bits_equal(sm["final_T"], ss["final_T"]),
-      {k: pt.image_err(fm[k], fs[k]) for k in ("color", "semantic", "depth", "median_depth", "final_opacity")})
 gm = pt.run_backward(_C, settings, scene, f, grads)
 _C.BWD_SIMT = True
 gs = pt.run_backward(_C, settings, scene, f, grads)
