@@ -225,27 +225,29 @@ __global__ void __launch_bounds__(32 * NW, (MmaCfg<S>::B_IN_REGS ? (16 / NW) : 1
         const float4* s_feat = s_feat2 + (i & 1) * B;
         const int* s_id = s_id3 + (i % 3) * B;
         const uint32_t* s_hit = s_hit3 + (i % 3) * B;
-        uint32_t valid_rows = 0;   // warp-uniform: rows (Gaussians of this round) this warp contributed to
-
-        for (int c0 = 0; c0 < nb_; c0 += 16) {
-                        // ---------------- phase 1: 16 Gaussians, back to front ------------------------------------------------
-            // (a) alpha of 8 Gaussians at a time, branch-free: eight independent dependency chains per lane (ILP);
-            // (b) the sequential transmittance / colour-behind recurrences, skipped per Gaussian by a warp vote.
-            // Entries of this chunk that the forward blended into this warp's strip (exactly the set with a
-            // contributing lane; every other entry has act == false in all lanes and is not even evaluated).
-            uint32_t todo = __ballot_sync(0xffffffffu, lane < 16 && c0 + lane < nb_ && ((s_hit[c0 + lane] >> strip) & 1u));
-            uint32_t act_mask = 0;
-#pragma unroll 1   // keep the loop rolled: the kernel must stay inside the instruction cache
-            while (todo) {
+        // Entries of this round that the forward blended into this warp's strip: exactly the entries with a contributing
+        // lane.  Every other entry has act == false in all lanes and is not even evaluated; the hit entries are packed
+        // into full 16-row MMA tiles, row r of a tile <-> entry `my_ent` of lane r.
+        uint32_t todo = __ballot_sync(0xffffffffu, lane < nb_ && ((s_hit[lane] >> strip) & 1u));
+        const uint32_t valid_rows = todo;   // rows of this warp's partial tile that get written this round
+#pragma unroll 1   // keep the loops rolled: the kernel must stay inside the instruction cache
+        while (todo) {
+            // ---------------- phase 1: up to 16 entries, back to front ------------------------------------------------
+            // (a) alpha of 8 entries at a time, branch-free: eight independent dependency chains per lane (ILP);
+            // (b) the sequential transmittance / colour-behind recurrences.
+            int my_ent = 0, nrow = 0;
+#pragma unroll 1
+            for (int half = 0; half < 2 && todo != 0; half++) {
                 float oG[8];
-                int rowv[8];
-                uint32_t abits = 0;
+                int ent[8];
+                uint32_t abits = 0, have_bits = 0;
 #pragma unroll
                 for (int u = 0; u < 8; u++) {
                     const bool have = todo != 0;
-                    rowv[u] = have ? __ffs(todo) - 1 : rowv[0];
+                    ent[u] = have ? __ffs(todo) - 1 : ent[0];
                     todo &= todo - 1;
-                    const int j = c0 + rowv[u];
+                    have_bits |= (have ? 1u : 0u) << u;
+                    const int j = ent[u];
                     const float2 xy = s_xy[j];
                     const float2 d = {xy.x - pixf.x, xy.y - pixf.y};
                     const float4 con_o = s_co[j];
@@ -257,13 +259,12 @@ __global__ void __launch_bounds__(32 * NW, (MmaCfg<S>::B_IN_REGS ? (16 / NW) : 1
                     oG[u] = og;
                     abits |= (active ? 1u : 0u) << u;
                 }
-                const uint32_t any_bits = __reduce_or_sync(0xffffffffu, abits);
 #pragma unroll
                 for (int u = 0; u < 8; u++) {
-                    if (!((any_bits >> u) & 1)) continue;   // warp-uniform
-                    const int row = rowv[u];
-                    const int j = c0 + row;
-                    act_mask |= 1u << row;
+                    if (!((have_bits >> u) & 1)) continue;   // warp-uniform
+                    const int row = nrow++;
+                    const int j = ent[u];
+                    my_ent = (lane == row) ? j : my_ent;
                     const bool act = (abits >> u) & 1;
                     const float alpha = min(0.99f, oG[u]);
                     // same IEEE division as the reference (backward.cu:815): the reconstructed transmittance decides
@@ -287,15 +288,13 @@ __global__ void __launch_bounds__(32 * NW, (MmaCfg<S>::B_IN_REGS ? (16 / NW) : 1
                 }
             }
             __syncwarp();
-            valid_rows |= act_mask << c0;
             // ---------------- phase 2: D[16 x 8] tiles on the tensor cores ---------------------------------------
-            const bool v0 = (act_mask >> qn) & 1, v1 = (act_mask >> (qn + 8)) & 1;
+            const bool v0 = qn < nrow, v1 = qn + 8 < nrow;
             float acc[NBF + 1][4];
 #pragma unroll
             for (int nb = 0; nb <= NBF; nb++)
 #pragma unroll
                 for (int r = 0; r < 4; r++) acc[nb][r] = 0.f;
-            if (act_mask != 0) {
 #pragma unroll
             for (int kb = 0; kb < 4; kb++) {
                 const int col = 8 * kb + qk;
@@ -330,17 +329,17 @@ __global__ void __launch_bounds__(32 * NW, (MmaCfg<S>::B_IN_REGS ? (16 / NW) : 1
                 mma_tf32(acc[NBF], __float_as_uint(tf32_lo(e0)), __float_as_uint(tf32_lo(e1)),
                          __float_as_uint(tf32_lo(e2)), __float_as_uint(tf32_lo(e3)), mb0, mb1);
             }
-            }
-            // D fragment: rows qn / qn+8, columns 2 qk, 2 qk + 1 of each n-tile -> this warp's private partial tile.
-            // Every row of the chunk is written (rows without contribution hold exact zeros: their A rows were zero),
-            // so the reduction below needs no per-warp validity tests.
-            float* pt = s_part + (size_t)(warp * B + c0) * KA + 2 * qk;
+            // D fragment: rows qn / qn+8, columns 2 qk, 2 qk + 1 of each n-tile -> row `entry` of this warp's private
+            // partial tile (rows this warp does not write are masked out of the reduction by s_valid).
+            const int e0 = __shfl_sync(0xffffffffu, my_ent, qn), e1 = __shfl_sync(0xffffffffu, my_ent, qn + 8);
+            float* pt0 = s_part + (size_t)(warp * B + e0) * KA + 2 * qk;
+            float* pt1 = s_part + (size_t)(warp * B + e1) * KA + 2 * qk;
 #pragma unroll
             for (int nb = 0; nb <= NBF; nb++) {
-                *reinterpret_cast<float2*>(pt + qn * KA + 8 * nb) = make_float2(acc[nb][0], acc[nb][1]);
-                *reinterpret_cast<float2*>(pt + (qn + 8) * KA + 8 * nb) = make_float2(acc[nb][2], acc[nb][3]);
+                if (v0) *reinterpret_cast<float2*>(pt0 + 8 * nb) = make_float2(acc[nb][0], acc[nb][1]);
+                if (v1) *reinterpret_cast<float2*>(pt1 + 8 * nb) = make_float2(acc[nb][2], acc[nb][3]);
             }
-            __syncwarp();  // wm / gm are rewritten by the next chunk
+            __syncwarp();  // wm / gm are rewritten by the next group
         }
         if (lane == 0) s_valid[warp] = valid_rows;
         __syncthreads();
@@ -349,9 +348,12 @@ __global__ void __launch_bounds__(32 * NW, (MmaCfg<S>::B_IN_REGS ? (16 / NW) : 1
         // consecutive threads own consecutive columns -> coalesced global atomics; the 8 moment columns of a row sit in
         // 8 consecutive lanes of one warp, so the closed-form 2D-mean / conic / opacity terms gather them by shuffle.
         const float cx = (float)(tile_x * HS_TILE_X) + 7.5f, cy = (float)(tile_y * HS_TILE_Y) + 7.5f;
-        uint32_t any_rows = 0;
+        uint32_t any_rows = 0, vrow[NW];
 #pragma unroll
-        for (int wv = 0; wv < NW; wv++) any_rows |= s_valid[wv];
+        for (int wv = 0; wv < NW; wv++) {
+            vrow[wv] = s_valid[wv];
+            any_rows |= vrow[wv];
+        }
         // pass A, feature columns: lane <-> column (destination pointer and row stride are fixed per lane, so the loop
         // body is divergence-free), warp <-> Gaussian row.
 #pragma unroll 1
@@ -364,7 +366,7 @@ __global__ void __launch_bounds__(32 * NW, (MmaCfg<S>::B_IN_REGS ? (16 / NW) : 1
                 if (c < NF) {
                     float p8[NW];
 #pragma unroll
-                    for (int wv = 0; wv < NW; wv++) p8[wv] = s_part[(size_t)(wv * B + j) * KA + c];
+                    for (int wv = 0; wv < NW; wv++) p8[wv] = ((vrow[wv] >> j) & 1u) ? s_part[(size_t)(wv * B + j) * KA + c] : 0.f;
 #pragma unroll
                     for (int st = 1; st < NW; st <<= 1)
 #pragma unroll
@@ -379,7 +381,8 @@ __global__ void __launch_bounds__(32 * NW, (MmaCfg<S>::B_IN_REGS ? (16 / NW) : 1
             const int j = e >> 3, m = e & 7;
             float p8[NW];
 #pragma unroll
-            for (int wv = 0; wv < NW; wv++) p8[wv] = s_part[(size_t)(wv * B + j) * KA + 8 * NBF + m];
+            for (int wv = 0; wv < NW; wv++)
+                p8[wv] = ((vrow[wv] >> j) & 1u) ? s_part[(size_t)(wv * B + j) * KA + 8 * NBF + m] : 0.f;
 #pragma unroll
             for (int st = 1; st < NW; st <<= 1)
 #pragma unroll
