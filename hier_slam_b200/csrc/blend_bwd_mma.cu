@@ -29,7 +29,7 @@ struct MmaCfg {
     static constexpr int KA = 8 * NBF + 8;           // + one n-tile of moments
     static constexpr bool B_IN_REGS = (NBF <= 4);    // dL fragments live in registers for S <= 27
     static constexpr int DS = 8 * NBF + ((8 - (8 * NBF) % 32 + 32) % 32);  // smem dL row stride == 8 (mod 32)
-    static constexpr int BATCH = B_IN_REGS ? 32 : 16;  // Gaussians staged per round (multiple of the 16-row MMA tile)
+    static constexpr int BATCH = B_IN_REGS ? 32 : 24;  // tile-list entries staged per round (<= 32: one ballot word; 24 keeps S = 74 inside 227 KB)
     static constexpr int WS = 36;                    // row stride of the per-warp w / g matrices (conflict-free)
 };
 
