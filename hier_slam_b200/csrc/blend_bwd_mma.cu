@@ -20,6 +20,10 @@
 #include "hs_common.cuh"
 #include <cuda_pipeline.h>
 
+#ifndef HS_BWD_U
+#define HS_BWD_U 2      // entries whose alpha is evaluated together (independent dependency chains per lane)
+#endif
+
 namespace hs {
 
 template <int S>
@@ -62,6 +66,7 @@ __global__ void __launch_bounds__(32 * NW, (MmaCfg<S>::B_IN_REGS ? (16 / NW) : 1
     using Cfg = MmaCfg<S>;
     constexpr int B = Cfg::BATCH, NF = Cfg::NF, NBF = Cfg::NBF, KA = Cfg::KA, WS = Cfg::WS, DS = Cfg::DS;
     constexpr bool BREG = Cfg::B_IN_REGS;
+    constexpr int U = HS_BWD_U;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // per-Gaussian staging is double-buffered and filled with cp.async one round ahead (ids two rounds ahead)
     float4* s_co2 = reinterpret_cast<float4*>(smem_raw);         // [2][B] conic + opacity
@@ -237,12 +242,12 @@ __global__ void __launch_bounds__(32 * NW, (MmaCfg<S>::B_IN_REGS ? (16 / NW) : 1
             // (b) the sequential transmittance / colour-behind recurrences.
             int my_ent = 0, nrow = 0;
 #pragma unroll 1
-            for (int half = 0; half < 2 && todo != 0; half++) {
-                float oG[8];
-                int ent[8];
+            for (int part = 0; part < 16 / U && todo != 0; part++) {
+                float oG[U];
+                int ent[U];
                 uint32_t abits = 0, have_bits = 0;
 #pragma unroll
-                for (int u = 0; u < 8; u++) {
+                for (int u = 0; u < U; u++) {
                     const bool have = todo != 0;
                     ent[u] = have ? __ffs(todo) - 1 : ent[0];
                     todo &= todo - 1;
@@ -260,7 +265,7 @@ __global__ void __launch_bounds__(32 * NW, (MmaCfg<S>::B_IN_REGS ? (16 / NW) : 1
                     abits |= (active ? 1u : 0u) << u;
                 }
 #pragma unroll
-                for (int u = 0; u < 8; u++) {
+                for (int u = 0; u < U; u++) {
                     if (!((have_bits >> u) & 1)) continue;   // warp-uniform
                     const int row = nrow++;
                     const int j = ent[u];
