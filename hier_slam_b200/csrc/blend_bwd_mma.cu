@@ -137,6 +137,7 @@ __global__ void __launch_bounds__(32 * NW, (MmaCfg<S>::B_IN_REGS ? (16 / NW) : 1
     float bg_dot_dpixel = 0;
 #pragma unroll
     for (int i = 0; i < 3; i++) bg_dot_dpixel += bg_color[i] * dL_rgb[i];
+    const bool bg_any = __any_sync(0xffffffffu, bg_dot_dpixel != 0.f);   // false for the black background SLAM uses
 
     // B operands (k = pixel, n = channel).  Fragment element (kb, nb, h): pixel 8 kb + lane%4 + 4 h, channel 8 nb + lane/4.
     const int qk = lane & 3, qn = lane >> 2;
@@ -281,7 +282,7 @@ __global__ void __launch_bounds__(32 * NW, (MmaCfg<S>::B_IN_REGS ? (16 / NW) : 1
                     q += dL_op;
                     const float acc_new = last_alpha * last_q + (1.f - last_alpha) * accum_q;
                     float dL_dalpha = (q - acc_new) * test_T;
-                    if (bg_dot_dpixel != 0.f) dL_dalpha -= __fdividef(T_final, 1.f - alpha) * bg_dot_dpixel;
+                    if (bg_any) dL_dalpha -= __fdividef(T_final, 1.f - alpha) * bg_dot_dpixel;   // warp-uniform branch
                     if (act && test_T > 0.5f && T < 0.5 && dL_median != 0.f)
                         atomicAdd(dL_ddepths + s_id[j], dL_median);   // the Gaussian that crossed T = 0.5 (quirk Q4)
                     wm[row * WS + lane] = act ? alpha * test_T : 0.f;

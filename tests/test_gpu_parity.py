@@ -224,6 +224,53 @@ def test_nonsemantic_against_live_reference():
         assert_grads_close(g[k], gr[k], k)
 
 
+@pytest.mark.parametrize("simt", [False, True])
+def test_nonzero_background(simt):
+    """Quirk Q5: the forward ignores bg, the backward keeps the bg term (backward.cu:874-877).  White-ish background,
+    both blend-backward kernels, against the CPU oracle and (when present) the live reference build."""
+    C, Settings = new_impl()
+    cfg = CONFIGS["small"]
+    cpu = make_scene(cfg, 11)
+    scene = {k: v.cuda() for k, v in cpu.items()}
+    bg = torch.tensor([0.3, 0.6, 0.9])
+    settings = pt.make_settings(Settings, cfg)._replace(bg=bg.cuda())
+    settings0 = pt.make_settings(Settings, cfg)
+    f, f0 = pt.run_forward(C, settings, scene), pt.run_forward(C, settings0, scene)
+    for k in ("color", "semantic", "depth", "median_depth", "final_opacity"):
+        assert pt.bits_equal(f[k], f0[k]) == 0, f"forward must ignore bg: {k}"
+    P, H, W = cpu["means3D"].shape[0], cfg.height, cfg.width
+    sv = {k: v.cpu() for k, v in C.state_views(P, H, W, f["R"], f["geomBuffer"], f["binningBuffer"],
+                                               f["imgBuffer"]).items()}
+    ugc = upstream_grads(cfg, 12)
+    ug = {k: v.cuda() for k, v in ugc.items()}
+    C.BWD_SIMT = simt
+    try:
+        g = pt.run_backward(C, settings, scene, f, ug)
+        g0 = pt.run_backward(C, settings0, scene, f, ug)
+    finally:
+        C.BWD_SIMT = False
+    assert pt.grad_err(g["means3D"], g0["means3D"])[0] > 1e-3, "bg term must change the geometry gradients"
+    view, proj, campos, tfx, tfy = camera_matrices(cfg)
+    geom = O.preprocess(cpu["means3D"], cpu["scales"], cpu["rotations"], cpu["opacities"], view, proj, W, H, tfx, tfy)
+    st = dict(geom=dict(means2D=sv["means2D"], conic_opacity=sv["conic_opacity"], depths=sv["depths"],
+                        cov3D=geom["cov3D"], radii=f["radii"].cpu()),
+              point_list=sv["point_list"].long(), ranges=sv["ranges"].long(), final_T=sv["final_T"],
+              n_contrib=sv["n_contrib"].long())
+    go = O.rasterize_backward(st, bg, cpu["means3D"], cpu["colors_precomp"], cpu["semantics_precomp"], cpu["scales"],
+                              cpu["rotations"], 1.0, None, view, proj, tfx, tfy, H, W, ugc["color"], ugc["semantic"],
+                              ugc["depth"], ugc["median_depth"], ugc["final_opacity"], sem_alpha_grad="ref")
+    for kn, ko in (("means3D", "dL_dmeans3D"), ("means2D", "dL_dmean2D"), ("colors", "dL_dcolors"),
+                   ("opacities", "dL_dopacity"), ("scales", "dL_dscales"), ("rotations", "dL_drotations"),
+                   ("semantics", "dL_dsemantics")):
+        assert_grads_close(g[kn].cpu(), go[ko].reshape(g[kn].shape), f"{kn} (bg != 0)")
+    ref = ref_loader.load_reference(26)
+    if ref is not None:
+        fr = pt.run_forward(ref._C, settings, scene)
+        gr = pt.run_backward(ref._C, settings, scene, fr, ug)
+        for k in g:
+            assert_grads_close(g[k], gr[k], f"{k} vs live reference (bg != 0)")
+
+
 def test_full_size_properties_c2():
     """BASELINE.json config 2 at full size (1200x680, 300K Gaussians, S=26): properties that need no oracle."""
     C, Settings = new_impl()
