@@ -87,9 +87,16 @@ def _forward(background, means3D, colors, semantics, opacity, scales, rotations,
         raise RuntimeError("semantics_precomp must have dimensions (num_points, S)")
     if not lib.hs_supports_semantic_channels(S):
         raise RuntimeError(f"semantic channel count S={S} is not instantiated in libhsraster (built: 0,16,26,74,102)")
-    if colors.numel() == 0 and P > 0:
-        raise RuntimeError("only precomputed colours are supported (the spherical-harmonics colour path of the "
-                           "reference, forward.cu:20-71, is never used by Hier-SLAM and is not implemented)")
+    use_sh = colors.numel() == 0
+    if use_sh and P > 0:
+        # spherical-harmonics colour path (reference forward.cu:20-71): sh is [P, M, 3]
+        if sh is None or sh.numel() == 0 or sh.dim() != 3 or sh.size(0) != P or sh.size(2) != 3:
+            raise RuntimeError("provide colors_precomp [P,3] or shs [P,M,3]")
+        if not (0 <= int(degree) <= 3) or sh.size(1) < (int(degree) + 1) ** 2:
+            raise RuntimeError(f"sh_degree {degree} needs 0 <= degree <= 3 and at least {(int(degree) + 1) ** 2} "
+                               f"coefficients per Gaussian, got {sh.size(1)}")
+        if campos is None or campos.numel() != 3:
+            raise RuntimeError("campos [3] is required by the spherical-harmonics colour path")
     fopt = dict(dtype=torch.float32, device=device)
     with torch.cuda.device(device):
         stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
@@ -102,7 +109,9 @@ def _forward(background, means3D, colors, semantics, opacity, scales, rotations,
             outs = (z(3), z(S) if semantic else None, z(1), z(1), z(1), z(1))
             return 0, outs, radii, empty, empty, empty
         means3D_c = _f32c(means3D, "means3D", device)
-        colors_c = _f32c(colors, "colors_precomp", device)
+        colors_c = None if use_sh else _f32c(colors, "colors_precomp", device)
+        sh_c = _f32c(sh, "shs", device) if use_sh else None
+        M = int(sh.size(1)) if use_sh else 0
         sem_c = _f32c(semantics, "semantics_precomp", device) if S else None
         opac_c = _f32c(opacity, "opacities", device)
         scales_c = _f32c(scales, "scales", device)
@@ -117,7 +126,8 @@ def _forward(background, means3D, colors, semantics, opacity, scales, rotations,
         R = ctypes.c_int(0)
         hint = ctypes.c_int(0)
         _lib.check(lib.hs_forward_geometry(ctypes.byref(cam), P, _ptr(means3D_c), _ptr(opac_c), _ptr(scales_c),
-                                           _ptr(rot_c), _ptr(cov_c), _ptr(radii), _ptr(geomBuffer), geom_bytes,
+                                           _ptr(rot_c), _ptr(cov_c), _ptr(sh_c), int(degree), M, _ptr(radii),
+                                           _ptr(geomBuffer), geom_bytes,
                                            _ptr(imgBuffer), img_bytes, _lib.HS_SORT_GLOBAL if SORT_GLOBAL else 0,
                                            ctypes.byref(R), ctypes.byref(hint), stream), "hs_forward_geometry")
         num_rendered = int(R.value)
@@ -170,6 +180,7 @@ def _backward(background, means3D, radii, colors, semantics, scales, rotations, 
     P = means3D.size(0)
     S = int(semantics.size(1)) if (semantic and semantics is not None and semantics.numel() > 0) else 0
     M = sh.size(1) if (sh is not None and sh.numel() != 0) else 0
+    use_sh = (colors is None or colors.numel() == 0) and M > 0
     fopt = dict(dtype=torch.float32, device=device)
     with torch.cuda.device(device):
         # atomically accumulated outputs: ONE zero fill
@@ -193,7 +204,7 @@ def _backward(background, means3D, radii, colors, semantics, scales, rotations, 
         have_scales = scales is not None and scales.numel() > 0
         dL_dscales = torch.empty(P, 3, **fopt) if have_scales else torch.zeros(P, 3, **fopt)
         dL_drotations = torch.empty(P, 4, **fopt) if have_scales else torch.zeros(P, 4, **fopt)
-        dL_dsh = torch.zeros(P, M, 3, **fopt)
+        dL_dsh = torch.empty(P, M, 3, **fopt) if use_sh else torch.zeros(P, M, 3, **fopt)
         if P != 0:
             stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
             cam, keep = _camera(background, scale_modifier, viewmatrix, projmatrix, tan_fovx, tan_fovy, H, W, campos,
@@ -203,7 +214,8 @@ def _backward(background, means3D, radii, colors, semantics, scales, rotations, 
                                   g(dL_dout_depth, "dL_dout_depth"), g(dL_dout_median_depth, "dL_dout_median_depth"),
                                   g(dL_dout_final_opacity, "dL_dout_final_opacity"))
             means3D_c = _f32c(means3D, "means3D", device)
-            colors_c = _f32c(colors, "colors_precomp", device)
+            colors_c = None if use_sh else _f32c(colors, "colors_precomp", device)
+            sh_c = _f32c(sh, "shs", device) if use_sh else None
             sem_c = _f32c(semantics, "semantics_precomp", device) if S else None
             scales_c = _f32c(scales, "scales", device) if have_scales else None
             rot_c = _f32c(rotations, "rotations", device) if have_scales else None
@@ -213,11 +225,13 @@ def _backward(background, means3D, radii, colors, semantics, scales, rotations, 
                 flags |= _lib.HS_BWD_SIMT
             _lib.check(lib.hs_backward(
                 ctypes.byref(cam), P, S, int(R), _ptr(means3D_c), _ptr(radii), _ptr(colors_c), _ptr(sem_c),
-                _ptr(scales_c), _ptr(rot_c), _ptr(cov_c), _ptr(geomBuffer), _ptr(binningBuffer), _ptr(imageBuffer),
+                _ptr(scales_c), _ptr(rot_c), _ptr(cov_c), _ptr(sh_c), int(degree), int(M), _ptr(geomBuffer),
+                _ptr(binningBuffer), _ptr(imageBuffer),
                 _ptr(gc), _ptr(gs), _ptr(gd), _ptr(gm), _ptr(go), _ptr(dL_dmeans2D), _ptr(dL_dconic),
                 _ptr(dL_dopacity), _ptr(dL_dcolors), _ptr(dL_dsemantics), _ptr(dL_ddepths), _ptr(dL_dmeans3D),
                 _ptr(dL_dcov3D), _ptr(dL_dscales) if have_scales else None,
-                _ptr(dL_drotations) if have_scales else None, flags, stream), "hs_backward")
+                _ptr(dL_drotations) if have_scales else None, _ptr(dL_dsh) if use_sh else None, flags, stream),
+                "hs_backward")
             del keep
     return dL_dmeans2D, dL_dcolors, dL_dsemantics, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations
 

@@ -58,13 +58,14 @@ def load() -> ctypes.CDLL:
     lib.hs_image_state_bytes.restype = c_size_t
     lib.hs_binning_state_bytes.argtypes = [c_int]
     lib.hs_binning_state_bytes.restype = c_size_t
-    lib.hs_forward_geometry.argtypes = [POINTER(HsCamera), c_int, vp, vp, vp, vp, vp, vp, vp, c_size_t, vp, c_size_t,
-                                        c_int, POINTER(c_int), POINTER(c_int), vp]
+    lib.hs_forward_geometry.argtypes = [POINTER(HsCamera), c_int, vp, vp, vp, vp, vp, vp, c_int, c_int, vp, vp,
+                                        c_size_t, vp, c_size_t, c_int, POINTER(c_int), POINTER(c_int), vp]
     lib.hs_forward_geometry.restype = c_int
     lib.hs_forward_render.argtypes = [POINTER(HsCamera), c_int, c_int, c_int, c_int, vp, vp, vp, vp, vp, c_size_t, vp,
                                       c_size_t, vp, vp, vp, vp, vp, vp, c_int, vp]
     lib.hs_forward_render.restype = c_int
-    lib.hs_backward.argtypes = [POINTER(HsCamera), c_int, c_int, c_int] + [vp] * 25 + [c_int, vp]
+    lib.hs_backward.argtypes = ([POINTER(HsCamera), c_int, c_int, c_int] + [vp] * 8 + [c_int, c_int] + [vp] * 19 +
+                                [c_int, vp])
     lib.hs_backward.restype = c_int
     lib.hs_mark_visible.argtypes = [c_int, vp, vp, vp, vp, vp]
     lib.hs_mark_visible.restype = c_int

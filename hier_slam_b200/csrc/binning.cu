@@ -107,6 +107,8 @@ int geom_view(char* base, size_t P, GeomView* v) {
     carve(p, v->conic_opacity, P);
     carve(p, v->tiles_touched, P);
     carve(p, v->point_offsets, P);
+    carve(p, v->rgb, 3 * P);
+    carve(p, v->clamped, P);
     v->scan_temp_bytes = 0;
     if (P > 0) {
         HS_CUDA_OK(cub::DeviceScan::InclusiveSum(nullptr, v->scan_temp_bytes, v->tiles_touched, v->point_offsets, (int)P));

@@ -103,9 +103,10 @@ int hs_binning_state_layout(int R, size_t off[5]) {
 }
 
 int hs_forward_geometry(const hs_camera* c, int P, const float* means3D, const float* opacities,
-                        const float* scales, const float* rotations, const float* cov3D_precomp, int* radii,
-                        void* geom_state, size_t geom_state_bytes, void* image_state, size_t image_state_bytes,
-                        int flags, int* num_rendered, int* binning_hint, void* stream_) {
+                        const float* scales, const float* rotations, const float* cov3D_precomp, const float* shs,
+                        int sh_degree, int sh_coeffs, int* radii, void* geom_state, size_t geom_state_bytes,
+                        void* image_state, size_t image_state_bytes, int flags, int* num_rendered, int* binning_hint,
+                        void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     Camera cam;
     if (make_camera(c, &cam)) return 1;
@@ -135,6 +136,14 @@ int hs_forward_geometry(const hs_camera* c, int P, const float* means3D, const f
         return 1;
     }
     const bool debug = c->debug != 0;
+    if (shs != nullptr) {
+        const int need = (sh_degree + 1) * (sh_degree + 1);
+        if (sh_degree < 0 || sh_degree > 3 || sh_coeffs < need || c->campos == nullptr) {
+            set_error("spherical harmonics: degree %d needs 0 <= degree <= 3, at least %d coefficients (got %d) and campos",
+                      sh_degree, need, sh_coeffs);
+            return 1;
+        }
+    }
     int* host = pinned_int();
     if (host == nullptr) {
         set_error("cudaHostAlloc failed");
@@ -146,6 +155,8 @@ int hs_forward_geometry(const hs_camera* c, int P, const float* means3D, const f
                                    stream, debug);
         if (rc) return rc;
         rc = launch_scan(P, g, stream, debug);
+        if (rc) return rc;
+        if (shs != nullptr) rc = launch_sh_forward(P, sh_degree, sh_coeffs, means3D, c->campos, shs, radii, g, stream, debug);
         if (rc) return rc;
         HS_CUDA_OK(cudaMemcpyAsync(host, g.point_offsets + (P - 1), sizeof(int), cudaMemcpyDeviceToHost, stream));
         HS_CUDA_OK(cudaStreamSynchronize(stream));
@@ -170,6 +181,8 @@ int hs_forward_geometry(const hs_camera* c, int P, const float* means3D, const f
                                stream, debug);
     if (rc) return rc;
     rc = launch_tile_scan(cam, img, stream, debug);
+    if (rc) return rc;
+    if (shs != nullptr) rc = launch_sh_forward(P, sh_degree, sh_coeffs, means3D, c->campos, shs, radii, g, stream, debug);
     if (rc) return rc;
     HS_CUDA_OK(cudaMemcpyAsync(host, img.info, 3 * sizeof(int), cudaMemcpyDeviceToHost, stream));
     HS_CUDA_OK(cudaStreamSynchronize(stream));
@@ -223,10 +236,11 @@ int hs_forward_render(const hs_camera* c, int P, int S, int R, int binning_hint,
             set_error("binning_state too small: %zu < %zu", binning_state_bytes, b.total_bytes);
             return 1;
         }
-        if (colors == nullptr || (S > 0 && semantics == nullptr)) {
-            set_error("colors / semantics must be provided (precomputed colours are the only supported colour path)");
+        if (S > 0 && semantics == nullptr) {
+            set_error("semantics must be provided when S > 0");
             return 1;
         }
+        if (colors == nullptr) colors = g.rgb;   // SH colour path: evaluated by hs_forward_geometry
     } else {
         b = BinningView{};
     }
@@ -250,12 +264,12 @@ int hs_forward_render(const hs_camera* c, int P, int S, int R, int binning_hint,
 
 int hs_backward(const hs_camera* c, int P, int S, int R, const float* means3D, const int* radii,
                 const float* colors, const float* semantics, const float* scales, const float* rotations,
-                const float* cov3D_precomp, const void* geom_state, const void* binning_state,
+                const float* cov3D_precomp, const float* shs, int sh_degree, int sh_coeffs, const void* geom_state, const void* binning_state,
                 const void* image_state, const float* dL_dout_color, const float* dL_dout_semantic,
                 const float* dL_dout_depth, const float* dL_dout_median_depth, const float* dL_dout_opacity,
                 float* dL_dmeans2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolors, float* dL_dsemantics,
                 float* dL_ddepths, float* dL_dmeans3D, float* dL_dcov3D, float* dL_dscales, float* dL_drotations,
-                int flags, void* stream_) {
+                float* dL_dsh, int flags, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     Camera cam;
     if (make_camera(c, &cam)) return 1;
@@ -273,6 +287,15 @@ int hs_backward(const hs_camera* c, int P, int S, int R, const float* means3D, c
     image_view((char*)image_state, N, tiles, &img);
     const bool debug = c->debug != 0;
     int rc = 0;
+    if (colors == nullptr) {
+        if (shs == nullptr || dL_dsh == nullptr || c->campos == nullptr) {
+            set_error("hs_backward: provide colors, or shs + dL_dsh + campos for the spherical-harmonics colour path");
+            return 1;
+        }
+        colors = g.rgb;
+    } else {
+        shs = nullptr;
+    }
     if (R > 0) {
         if (binning_view((char*)binning_state, (size_t)R, &b)) return 2;
         int kflags = 0;
@@ -283,9 +306,13 @@ int hs_backward(const hs_camera* c, int P, int S, int R, const float* means3D, c
                                    dL_dopacity, dL_dcolors, dL_dsemantics, dL_ddepths, kflags, stream, debug);
         if (rc) return rc;
     }
-    return launch_geom_backward(P, means3D, radii, scales, rotations, cov3D_precomp, cam, dL_dmeans2D, dL_dconic,
-                                dL_ddepths, dL_dmeans3D, dL_dcov3D, cov3D_precomp ? nullptr : dL_dscales,
-                                cov3D_precomp ? nullptr : dL_drotations, stream, debug);
+    rc = launch_geom_backward(P, means3D, radii, scales, rotations, cov3D_precomp, cam, dL_dmeans2D, dL_dconic,
+                              dL_ddepths, dL_dmeans3D, dL_dcov3D, cov3D_precomp ? nullptr : dL_dscales,
+                              cov3D_precomp ? nullptr : dL_drotations, stream, debug);
+    if (rc || shs == nullptr) return rc;
+    // colour gradient -> SH coefficients, and the view-direction term added to dL/dmean (backward.cu:20-139)
+    return launch_sh_backward(P, sh_degree, sh_coeffs, means3D, c->campos, shs, radii, g, dL_dcolors, dL_dmeans3D, dL_dsh,
+                              stream, debug);
 }
 
 int hs_profile_enable(int on) {

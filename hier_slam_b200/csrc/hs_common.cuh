@@ -55,6 +55,8 @@ struct GeomView {
     float4* conic_opacity;    // float4[P] (conic.x, conic.y, conic.z, opacity)
     uint32_t* tiles_touched;  // u32[P]
     uint32_t* point_offsets;  // u32[P]   inclusive scan of tiles_touched
+    float* rgb;               // f32[3P]  colours evaluated from spherical harmonics (SH colour path only)
+    uint8_t* clamped;         // u8[P]    bit c: colour channel c was clamped at 0 (SH colour path only)
     char* scan_temp;          // CUB scan temp
     size_t scan_temp_bytes;
     size_t total_bytes;
@@ -122,6 +124,11 @@ int launch_geom_backward(int P, const float* means3D, const int* radii, const fl
                          const float* dL_dmean2D, const float* dL_dconic, const float* dL_ddepths,
                          float* dL_dmeans3D, float* dL_dcov3D, float* dL_dscales, float* dL_drots,
                          cudaStream_t stream, bool debug);
+int launch_sh_forward(int P, int deg, int M, const float* means3D, const float* campos, const float* shs,
+                      const int* radii, const GeomView& g, cudaStream_t stream, bool debug);
+int launch_sh_backward(int P, int deg, int M, const float* means3D, const float* campos, const float* shs,
+                       const int* radii, const GeomView& g, const float* dL_dcolors, float* dL_dmeans3D, float* dL_dsh,
+                       cudaStream_t stream, bool debug);
 int launch_mark_visible(int P, const float* means3D, const float* view, const float* proj, bool* present,
                         cudaStream_t stream, bool debug);
 

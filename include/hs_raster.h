@@ -54,7 +54,7 @@ typedef struct hs_camera {
     const float* viewmatrix; /* device, 16 floats: world-to-camera, transposed ([1,4,4] made contiguous)      */
     const float* projmatrix; /* device, 16 floats: full projection, transposed                                */
     const float* bg;         /* device, 3 floats                                                              */
-    const float* campos;     /* device, 3 floats (only used by the SH colour path, which is not implemented)   */
+    const float* campos;     /* device, 3 floats (only used by the spherical-harmonics colour path)            */
     int prefiltered;
     int debug;
 } hs_camera;
@@ -73,11 +73,15 @@ size_t hs_binning_state_bytes(int num_rendered);
  * Writes radii[P] (int32, device), fills geom_state and the tile ranges inside image_state, and returns (HOST
  * pointers) the number of (Gaussian, tile) instances in *num_rendered and, in *binning_hint, an opaque value that
  * must be handed to hs_forward_render (it encodes the longest tile list; -1 with HS_SORT_GLOBAL).  Synchronises `stream` once (the only host sync of a forward+backward).
- * scales/rotations may be NULL iff cov3D_precomp is given, and vice versa.  flags: 0 or HS_SORT_GLOBAL. */
+ * scales/rotations may be NULL iff cov3D_precomp is given, and vice versa.  flags: 0 or HS_SORT_GLOBAL.
+ * shs (may be NULL): spherical-harmonics coefficients [P, sh_coeffs, 3]; when given, the view-dependent colours of
+ * degree sh_degree (0..3, reference forward.cu:20-71) are evaluated into geom_state and hs_forward_render /
+ * hs_backward are called with colors == NULL. */
 int hs_forward_geometry(const hs_camera* cam, int P, const float* means3D, const float* opacities,
-                        const float* scales, const float* rotations, const float* cov3D_precomp, int* radii,
-                        void* geom_state, size_t geom_state_bytes, void* image_state, size_t image_state_bytes,
-                        int flags, int* num_rendered, int* binning_hint, void* stream);
+                        const float* scales, const float* rotations, const float* cov3D_precomp, const float* shs,
+                        int sh_degree, int sh_coeffs, int* radii, void* geom_state, size_t geom_state_bytes,
+                        void* image_state, size_t image_state_bytes, int flags, int* num_rendered, int* binning_hint,
+                        void* stream);
 
 /* Stage 2 of the forward: instance scatter + per-tile sort (or key duplication, global sort and range
  * identification), alpha compositing.  num_rendered and binning_hint are the values stage 1 returned; image_state
@@ -94,15 +98,16 @@ int hs_forward_render(const hs_camera* cam, int P, int S, int num_rendered, int 
  * Accumulated outputs — MUST be zero-initialised by the caller: dL_dmeans2D[P,3], dL_dconic[P,4],
  * dL_dopacity[P], dL_dcolors[P,3], dL_dsemantics[P,S], dL_ddepths[P].
  * Plain outputs — fully written: dL_dmeans3D[P,3], dL_dcov3D[P,6], dL_dscales[P,3], dL_drotations[P,4]
- * (the last two may be NULL when cov3D_precomp is used). */
+ * (the last two may be NULL when cov3D_precomp is used); dL_dsh[P, sh_coeffs, 3] when colors == NULL and shs is given
+ * (spherical-harmonics colour path; its view-direction term is added to dL_dmeans3D). */
 int hs_backward(const hs_camera* cam, int P, int S, int num_rendered, const float* means3D, const int* radii,
                 const float* colors, const float* semantics, const float* scales, const float* rotations,
-                const float* cov3D_precomp, const void* geom_state, const void* binning_state,
+                const float* cov3D_precomp, const float* shs, int sh_degree, int sh_coeffs, const void* geom_state, const void* binning_state,
                 const void* image_state, const float* dL_dout_color, const float* dL_dout_semantic,
                 const float* dL_dout_depth, const float* dL_dout_median_depth, const float* dL_dout_opacity,
                 float* dL_dmeans2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolors, float* dL_dsemantics,
                 float* dL_ddepths, float* dL_dmeans3D, float* dL_dcov3D, float* dL_dscales, float* dL_drotations,
-                int flags, void* stream);
+                float* dL_dsh, int flags, void* stream);
 
 /* present[P] (bool, device) = view-space z > 0.2 (reference: rasterizer_impl.cu:54-66). */
 int hs_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,

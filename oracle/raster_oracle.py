@@ -554,6 +554,106 @@ def geom_backward(means3D, scales, rotations, scale_modifier, cov3D, radii, view
 # --------------------------------------------------------------------------------------
 # Entry points mirroring RAST/rasterize_points.cu:240-432 (semantic) and :35-215 (non-semantic)
 # --------------------------------------------------------------------------------------
+# ---------------------------------------------------------------------------------------------------
+# spherical-harmonics colour path (forward.cu:20-71, backward.cu:20-139, auxiliary.h:22-39,107-117)
+# ---------------------------------------------------------------------------------------------------
+SH_C0 = 0.28209479177387814
+SH_C1 = 0.4886025119029199
+SH_C2 = (1.0925484305920792, -1.0925484305920792, 0.31539156525252005, -1.0925484305920792, 0.5462742152960396)
+SH_C3 = (-0.5900435899266435, 2.890611442640554, -0.4570457994644658, 0.3731763325901154, -0.4570457994644658,
+         1.445305721320277, -0.5900435899266435)
+
+
+def _sh_unclamped(deg, dirs, sh):
+    """result of forward.cu:30-63 (+0.5) before the clamp; dirs [P,3] unit view directions, sh [P,M,3]."""
+    x, y, z = dirs[:, 0:1], dirs[:, 1:2], dirs[:, 2:3]
+    res = SH_C0 * sh[:, 0]
+    if deg > 0:
+        res = res - SH_C1 * y * sh[:, 1] + SH_C1 * z * sh[:, 2] - SH_C1 * x * sh[:, 3]
+        if deg > 1:
+            xx, yy, zz, xy, yz, xz = x * x, y * y, z * z, x * y, y * z, x * z
+            res = (res + SH_C2[0] * xy * sh[:, 4] + SH_C2[1] * yz * sh[:, 5] + SH_C2[2] * (2.0 * zz - xx - yy) * sh[:, 6]
+                   + SH_C2[3] * xz * sh[:, 7] + SH_C2[4] * (xx - yy) * sh[:, 8])
+            if deg > 2:
+                res = (res + SH_C3[0] * y * (3.0 * xx - yy) * sh[:, 9] + SH_C3[1] * xy * z * sh[:, 10]
+                       + SH_C3[2] * y * (4.0 * zz - xx - yy) * sh[:, 11]
+                       + SH_C3[3] * z * (2.0 * zz - 3.0 * xx - 3.0 * yy) * sh[:, 12]
+                       + SH_C3[4] * x * (4.0 * zz - xx - yy) * sh[:, 13] + SH_C3[5] * z * (xx - yy) * sh[:, 14]
+                       + SH_C3[6] * x * (xx - 3.0 * yy) * sh[:, 15])
+    return res + 0.5
+
+
+def sh_forward(deg, means3D, campos, shs, radii, dtype=torch.float32):
+    """computeColorFromSH (forward.cu:20-71): returns (rgb [P,3], clamped bool [P,3]); rows of culled Gaussians
+    (radii <= 0) are zero (the reference leaves them unwritten)."""
+    m, sh = means3D.to(dtype), shs.to(dtype)
+    d = m - campos.to(dtype)[None]
+    d = d / d.norm(dim=1, keepdim=True)
+    res = _sh_unclamped(deg, d, sh)
+    vis = (radii > 0)[:, None]
+    clamped = (res < 0) & vis
+    return torch.where(vis, res.clamp_min(0.0), torch.zeros_like(res)), clamped
+
+
+def sh_backward(deg, means3D, campos, shs, radii, clamped, dL_dcolors, dtype=torch.float32):
+    """computeColorFromSH backward (backward.cu:20-139): returns (dL_dsh [P,M,3], dL_dmeans contribution [P,3]).
+    The clamp passes no gradient (PyTorch rule, :30-35); the direction gradient goes through dnormvdv
+    (auxiliary.h:107-117).  Explicit restatement of the reference's formulas, not autograd."""
+    m, sh = means3D.to(dtype), shs.to(dtype)
+    P, M = sh.shape[0], sh.shape[1]
+    d0 = m - campos.to(dtype)[None]
+    d = d0 / d0.norm(dim=1, keepdim=True)
+    x, y, z = d[:, 0:1], d[:, 1:2], d[:, 2:3]
+    g = torch.where(clamped, torch.zeros_like(dL_dcolors.to(dtype)), dL_dcolors.to(dtype))
+    g = torch.where((radii > 0)[:, None], g, torch.zeros_like(g))
+    dsh = torch.zeros(P, M, 3, dtype=dtype)
+    dsh[:, 0] = SH_C0 * g
+    dx = torch.zeros(P, 3, dtype=dtype)
+    dy = torch.zeros(P, 3, dtype=dtype)
+    dz = torch.zeros(P, 3, dtype=dtype)
+    if deg > 0:
+        dsh[:, 1], dsh[:, 2], dsh[:, 3] = -SH_C1 * y * g, SH_C1 * z * g, -SH_C1 * x * g
+        dx, dy, dz = -SH_C1 * sh[:, 3], -SH_C1 * sh[:, 1], SH_C1 * sh[:, 2]
+        if deg > 1:
+            xx, yy, zz, xy, yz, xz = x * x, y * y, z * z, x * y, y * z, x * z
+            dsh[:, 4], dsh[:, 5] = SH_C2[0] * xy * g, SH_C2[1] * yz * g
+            dsh[:, 6], dsh[:, 7] = SH_C2[2] * (2.0 * zz - xx - yy) * g, SH_C2[3] * xz * g
+            dsh[:, 8] = SH_C2[4] * (xx - yy) * g
+            dx = dx + SH_C2[0] * y * sh[:, 4] + SH_C2[2] * 2.0 * -x * sh[:, 6] + SH_C2[3] * z * sh[:, 7] \
+                + SH_C2[4] * 2.0 * x * sh[:, 8]
+            dy = dy + SH_C2[0] * x * sh[:, 4] + SH_C2[1] * z * sh[:, 5] + SH_C2[2] * 2.0 * -y * sh[:, 6] \
+                + SH_C2[4] * 2.0 * -y * sh[:, 8]
+            dz = dz + SH_C2[1] * y * sh[:, 5] + SH_C2[2] * 2.0 * 2.0 * z * sh[:, 6] + SH_C2[3] * x * sh[:, 7]
+            if deg > 2:
+                dsh[:, 9] = SH_C3[0] * y * (3.0 * xx - yy) * g
+                dsh[:, 10] = SH_C3[1] * xy * z * g
+                dsh[:, 11] = SH_C3[2] * y * (4.0 * zz - xx - yy) * g
+                dsh[:, 12] = SH_C3[3] * z * (2.0 * zz - 3.0 * xx - 3.0 * yy) * g
+                dsh[:, 13] = SH_C3[4] * x * (4.0 * zz - xx - yy) * g
+                dsh[:, 14] = SH_C3[5] * z * (xx - yy) * g
+                dsh[:, 15] = SH_C3[6] * x * (xx - 3.0 * yy) * g
+                dx = dx + (SH_C3[0] * sh[:, 9] * 3.0 * 2.0 * xy + SH_C3[1] * sh[:, 10] * yz
+                           + SH_C3[2] * sh[:, 11] * -2.0 * xy + SH_C3[3] * sh[:, 12] * -3.0 * 2.0 * xz
+                           + SH_C3[4] * sh[:, 13] * (-3.0 * xx + 4.0 * zz - yy) + SH_C3[5] * sh[:, 14] * 2.0 * xz
+                           + SH_C3[6] * sh[:, 15] * 3.0 * (xx - yy))
+                dy = dy + (SH_C3[0] * sh[:, 9] * 3.0 * (xx - yy) + SH_C3[1] * sh[:, 10] * xz
+                           + SH_C3[2] * sh[:, 11] * (-3.0 * yy + 4.0 * zz - xx) + SH_C3[3] * sh[:, 12] * -3.0 * 2.0 * yz
+                           + SH_C3[4] * sh[:, 13] * -2.0 * xy + SH_C3[5] * sh[:, 14] * -2.0 * yz
+                           + SH_C3[6] * sh[:, 15] * -3.0 * 2.0 * xy)
+                dz = dz + (SH_C3[1] * sh[:, 10] * xy + SH_C3[2] * sh[:, 11] * 4.0 * 2.0 * yz
+                           + SH_C3[3] * sh[:, 12] * 3.0 * (2.0 * zz - xx - yy) + SH_C3[4] * sh[:, 13] * 4.0 * 2.0 * xz
+                           + SH_C3[5] * sh[:, 14] * (xx - yy))
+    ddir = torch.stack([(dx * g).sum(1), (dy * g).sum(1), (dz * g).sum(1)], 1)
+    sum2 = (d0 * d0).sum(1, keepdim=True)
+    inv32 = 1.0 / torch.sqrt(sum2 * sum2 * sum2)
+    vx, vy, vz = d0[:, 0:1], d0[:, 1:2], d0[:, 2:3]
+    gx, gy, gz = ddir[:, 0:1], ddir[:, 1:2], ddir[:, 2:3]
+    dmean = torch.cat([((sum2 - vx * vx) * gx - vy * vx * gy - vz * vx * gz) * inv32,
+                       (-vx * vy * gx + (sum2 - vy * vy) * gy - vz * vy * gz) * inv32,
+                       (-vx * vz * gx - vy * vz * gy + (sum2 - vz * vz) * gz) * inv32], 1)
+    return dsh, dmean
+
+
 def rasterize_forward(background, means3D, colors, semantics, opacity, scales, rotations, scale_modifier,
                       cov3D_precomp, viewmatrix, projmatrix, tanfovx, tanfovy, H, W,
                       dtype=torch.float32):

@@ -271,6 +271,57 @@ def test_nonzero_background(simt):
             assert_grads_close(g[k], gr[k], f"{k} vs live reference (bg != 0)")
 
 
+@pytest.mark.parametrize("deg,semantic", [(3, True), (1, False), (0, True)])
+def test_spherical_harmonics_colour_path(deg, semantic):
+    """shs instead of colors_precomp (forward.cu:20-71, backward.cu:20-139) through the public API,
+    against the CPU oracle (SH stage) + the precomputed-colour path (everything downstream), and against the live
+    reference build when present."""
+    import diff_gaussian_rasterization as dgr
+    cfg = CONFIGS["small"]
+    sc = make_scene(cfg, 9, device="cuda")
+    P, M = sc["means3D"].shape[0], 16
+    g = torch.Generator().manual_seed(31)
+    shs = (torch.randn(P, M, 3, generator=g) * 0.5).cuda()
+    campos = torch.tensor([0.05, -0.03, 0.02])
+    settings = pt.make_settings(dgr.GaussianRasterizationSettings, cfg)._replace(sh_degree=deg, campos=campos.cuda())
+    ug = upstream_grads(cfg, 13, device="cuda")
+    Raster = dgr.GaussianRasterizer_semantic if semantic else dgr.GaussianRasterizer
+    extra = dict(semantics_precomp=sc["semantics_precomp"]) if semantic else {}
+
+    def run(mod_raster, settings_, colour_kw):
+        leaves = {k: v.clone().requires_grad_(True) for k, v in colour_kw.items()}
+        m3 = sc["means3D"].clone().requires_grad_(True)
+        out = mod_raster(raster_settings=settings_)(means3D=m3, means2D=torch.zeros_like(m3), opacities=sc["opacities"],
+                                                    scales=sc["scales"], rotations=sc["rotations"], **leaves, **extra)
+        color, depth = out[0], (out[3] if semantic else out[2])
+        ((color * ug["color"]).sum() + (depth * ug["depth"]).sum()).backward()
+        return out, m3.grad, {k: v.grad for k, v in leaves.items()}
+
+    out_sh, dmean_sh, gl = run(Raster, settings, dict(shs=shs))
+    radii = out_sh[1]
+    # oracle SH stage, then the (already verified) precomputed-colour path on the same colours
+    rgb, clamped = O.sh_forward(deg, sc["means3D"].cpu(), campos, shs.cpu(), radii.cpu())
+    out_pc, dmean_pc, gp = run(Raster, settings, dict(colors_precomp=rgb.cuda()))
+    assert torch.equal(out_sh[1], out_pc[1])
+    vis = (radii > 0)
+    assert_images_close(out_sh[0], out_pc[0], "colour from SH")
+    dsh, dmean_dir = O.sh_backward(deg, sc["means3D"].cpu(), campos, shs.cpu(), radii.cpu(), clamped,
+                                   gp["colors_precomp"].cpu())
+    assert_grads_close(gl["shs"].cpu(), dsh, "dL/dsh")
+    assert_grads_close(dmean_sh.cpu(), dmean_pc.cpu() + dmean_dir, "dL/dmeans3D incl. view-direction term")
+    if deg > 0:
+        assert float(dmean_dir[vis.cpu()].abs().max()) > 0
+    ref = ref_loader.load_reference(26)
+    if ref is not None and (not semantic or True):
+        RefRaster = ref.GaussianRasterizer_semantic if semantic else ref.GaussianRasterizer
+        rsettings = pt.make_settings(ref.GaussianRasterizationSettings, cfg)._replace(sh_degree=deg, campos=campos.cuda())
+        out_r, dmean_r, gr = run(RefRaster, rsettings, dict(shs=shs))
+        assert torch.equal(out_sh[1], out_r[1])
+        assert_images_close(out_sh[0], out_r[0], "colour vs live reference")
+        assert_grads_close(gl["shs"], gr["shs"], "dL/dsh vs live reference")
+        assert_grads_close(dmean_sh, dmean_r, "dL/dmeans3D vs live reference")
+
+
 def test_full_size_properties_c2():
     """BASELINE.json config 2 at full size (1200x680, 300K Gaussians, S=26): properties that need no oracle."""
     C, Settings = new_impl()

@@ -240,3 +240,30 @@ def test_oracle_matches_reference_golden(path):
         res[mode] = errs
     # the reference matches the 'ref' restatement (quirk Q1: its scratch buffer was zero) to 1e-3 (north_star bar)
     assert max(res["ref"].values()) < 1e-3, res
+
+
+@pytest.mark.parametrize("deg", [0, 1, 2, 3])
+def test_sh_colour_backward_matches_autograd(deg):
+    """The explicit spherical-harmonics backward of the oracle (backward.cu:20-139 restated) against autograd of its
+    own forward in float64, including the clamp-at-zero rule and the view-direction term into dL/dmean."""
+    g = torch.Generator().manual_seed(20 + deg)
+    P, M = 200, 16
+    means = (torch.randn(P, 3, generator=g) * 2 + torch.tensor([0.0, 0.0, 4.0])).double()
+    campos = torch.tensor([0.3, -0.2, 0.1]).double()
+    shs = (torch.randn(P, M, 3, generator=g) * 0.6).double()
+    radii = torch.where(torch.rand(P, generator=g) < 0.9, 3, 0)
+    up = torch.randn(P, 3, generator=g).double()
+    m, sh = means.clone().requires_grad_(True), shs.clone().requires_grad_(True)
+    d = m - campos[None]
+    d = d / d.norm(dim=1, keepdim=True)
+    rgb_auto = O._sh_unclamped(deg, d, sh).clamp_min(0.0)
+    vis = (radii > 0)[:, None]
+    (torch.where(vis, rgb_auto, torch.zeros_like(rgb_auto)) * up).sum().backward()
+    rgb, clamped = O.sh_forward(deg, means, campos, shs, radii, dtype=torch.float64)
+    assert torch.allclose(rgb, torch.where(vis, rgb_auto.detach(), torch.zeros_like(rgb)), atol=1e-12)
+    assert bool(clamped.any()) and bool((~clamped).any())
+    dsh, dmean = O.sh_backward(deg, means, campos, shs, radii, clamped, up, dtype=torch.float64)
+    assert torch.allclose(dsh, sh.grad, atol=1e-10)
+    assert torch.allclose(dmean, m.grad if m.grad is not None else torch.zeros_like(dmean), atol=1e-10)
+    n = (deg + 1) ** 2
+    assert float(dsh[:, n:].abs().max()) == 0 if n < M else True
