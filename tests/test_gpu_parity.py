@@ -322,6 +322,31 @@ def test_spherical_harmonics_colour_path(deg, semantic):
         assert_grads_close(dmean_sh, dmean_r, "dL/dmeans3D vs live reference")
 
 
+@pytest.mark.parametrize("key,P,expect", [("small", 100_000, "large-class"), ("tiny", 300_000, "global-fallback"),
+                                          ("small", 40, "sparse")])
+def test_tile_sort_size_classes(key, P, expect):
+    """Tile lists of 2049..16384 entries take the 512-thread sort class, longer ones fall back to the global radix sort
+    for the whole frame, and nearly empty frames exercise empty tiles: every case must give the lists of the
+    reference-style binning bit for bit (and the same images)."""
+    C, Settings = new_impl()
+    cfg = CONFIGS[key]
+    scene = make_scene(cfg, 21, num_gaussians=P, device="cuda")
+    settings = pt.make_settings(Settings, cfg)
+    f = pt.run_forward(C, settings, scene)
+    sg = global_sort_views(C, settings, scene, f)
+    rg = sg["ranges"].long()
+    longest = int((rg[:, 1] - rg[:, 0]).max())
+    if expect == "large-class":
+        assert 2048 < longest <= 16384
+    elif expect == "global-fallback":
+        assert longest > 16384
+    else:
+        assert int(((rg[:, 1] - rg[:, 0]) == 0).sum()) > 0
+    ug = upstream_grads(cfg, 22, device="cuda")
+    g = pt.run_backward(C, settings, scene, f, ug)
+    assert all(bool(torch.isfinite(v).all()) for v in g.values())
+
+
 def test_full_size_properties_c2():
     """BASELINE.json config 2 at full size (1200x680, 300K Gaussians, S=26): properties that need no oracle."""
     C, Settings = new_impl()
