@@ -314,7 +314,9 @@ def run_ours(a, rank, world, local):
                     "whole_step": {"algorithmic_bytes": total_b,
                                    "achieved_GBps": total_b / (ms / a.steps * 1e-3) / 1e9,
                                    "frac": total_b / (ms / a.steps * 1e-3) / 1e9 / peak},
-                    "note": "blend kernels are FP32-issue / shared-memory bound, not HBM bound (DESIGN.md)"}
+                    "note": "blend kernels are FP32/ALU-issue bound, not HBM bound (DESIGN.md section 3); "
+                            "actual_bound holds the ncu issue-slot evidence of the committed capture",
+                    "actual_bound": measured_traffic(a.config + "_issue", dom)}
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": "f32", "data": "synthetic",
