@@ -174,7 +174,7 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
 def _backward(background, means3D, radii, colors, semantics, scales, rotations, scale_modifier, cov3D_precomp,
               viewmatrix, projmatrix, tan_fovx, tan_fovy, dL_dout_color, dL_dout_semantic, dL_dout_depth,
               dL_dout_median_depth, dL_dout_final_opacity, sh, degree, campos, geomBuffer, R, binningBuffer,
-              imageBuffer, debug, H: int, W: int, semantic: bool):
+              imageBuffer, debug, H: int, W: int, semantic: bool, pose_points=None):
     lib = _lib.load()
     device = means3D.device
     P = means3D.size(0)
@@ -205,6 +205,7 @@ def _backward(background, means3D, radii, colors, semantics, scales, rotations, 
         dL_dscales = torch.empty(P, 3, **fopt) if have_scales else torch.zeros(P, 3, **fopt)
         dL_drotations = torch.empty(P, 4, **fopt) if have_scales else torch.zeros(P, 4, **fopt)
         dL_dsh = torch.empty(P, M, 3, **fopt) if use_sh else torch.zeros(P, M, 3, **fopt)
+        dL_dpose = torch.zeros(3, 4, **fopt) if pose_points is not None else None
         if P != 0:
             stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
             cam, keep = _camera(background, scale_modifier, viewmatrix, projmatrix, tan_fovx, tan_fovy, H, W, campos,
@@ -220,6 +221,7 @@ def _backward(background, means3D, radii, colors, semantics, scales, rotations, 
             scales_c = _f32c(scales, "scales", device) if have_scales else None
             rot_c = _f32c(rotations, "rotations", device) if have_scales else None
             cov_c = _f32c(cov3D_precomp, "cov3D_precomp", device) if cov3D_precomp is not None else None
+            pose_c = _f32c(pose_points, "pose_points", device) if pose_points is not None else None
             flags = _lib.HS_SEM_ALPHA_EXACT if SEM_ALPHA_GRAD == "exact" else 0
             if BWD_SIMT:
                 flags |= _lib.HS_BWD_SIMT
@@ -230,9 +232,12 @@ def _backward(background, means3D, radii, colors, semantics, scales, rotations, 
                 _ptr(gc), _ptr(gs), _ptr(gd), _ptr(gm), _ptr(go), _ptr(dL_dmeans2D), _ptr(dL_dconic),
                 _ptr(dL_dopacity), _ptr(dL_dcolors), _ptr(dL_dsemantics), _ptr(dL_ddepths), _ptr(dL_dmeans3D),
                 _ptr(dL_dcov3D), _ptr(dL_dscales) if have_scales else None,
-                _ptr(dL_drotations) if have_scales else None, _ptr(dL_dsh) if use_sh else None, flags, stream),
-                "hs_backward")
+                _ptr(dL_drotations) if have_scales else None, _ptr(dL_dsh) if use_sh else None,
+                _ptr(pose_c), _ptr(dL_dpose), flags, stream), "hs_backward")
             del keep
+    if pose_points is not None:
+        return (dL_dmeans2D, dL_dcolors, dL_dsemantics, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales,
+                dL_drotations, dL_dpose)
     return dL_dmeans2D, dL_dcolors, dL_dsemantics, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations
 
 

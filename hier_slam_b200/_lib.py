@@ -64,7 +64,7 @@ def load() -> ctypes.CDLL:
     lib.hs_forward_render.argtypes = [POINTER(HsCamera), c_int, c_int, c_int, c_int, vp, vp, vp, vp, vp, c_size_t, vp,
                                       c_size_t, vp, vp, vp, vp, vp, vp, c_int, vp]
     lib.hs_forward_render.restype = c_int
-    lib.hs_backward.argtypes = ([POINTER(HsCamera), c_int, c_int, c_int] + [vp] * 8 + [c_int, c_int] + [vp] * 19 +
+    lib.hs_backward.argtypes = ([POINTER(HsCamera), c_int, c_int, c_int] + [vp] * 8 + [c_int, c_int] + [vp] * 21 +
                                 [c_int, vp])
     lib.hs_backward.restype = c_int
     lib.hs_mark_visible.argtypes = [c_int, vp, vp, vp, vp, vp]

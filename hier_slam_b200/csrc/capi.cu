@@ -269,7 +269,7 @@ int hs_backward(const hs_camera* c, int P, int S, int R, const float* means3D, c
                 const float* dL_dout_depth, const float* dL_dout_median_depth, const float* dL_dout_opacity,
                 float* dL_dmeans2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolors, float* dL_dsemantics,
                 float* dL_ddepths, float* dL_dmeans3D, float* dL_dcov3D, float* dL_dscales, float* dL_drotations,
-                float* dL_dsh, int flags, void* stream_) {
+                float* dL_dsh, const float* pose_points, float* dL_dpose, int flags, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     Camera cam;
     if (make_camera(c, &cam)) return 1;
@@ -287,6 +287,10 @@ int hs_backward(const hs_camera* c, int P, int S, int R, const float* means3D, c
     image_view((char*)image_state, N, tiles, &img);
     const bool debug = c->debug != 0;
     int rc = 0;
+    if (dL_dpose != nullptr && pose_points == nullptr) {
+        set_error("hs_backward: dL_dpose needs pose_points");
+        return 1;
+    }
     if (colors == nullptr) {
         if (shs == nullptr || dL_dsh == nullptr || c->campos == nullptr) {
             set_error("hs_backward: provide colors, or shs + dL_dsh + campos for the spherical-harmonics colour path");
@@ -308,11 +312,11 @@ int hs_backward(const hs_camera* c, int P, int S, int R, const float* means3D, c
     }
     rc = launch_geom_backward(P, means3D, radii, scales, rotations, cov3D_precomp, cam, dL_dmeans2D, dL_dconic,
                               dL_ddepths, dL_dmeans3D, dL_dcov3D, cov3D_precomp ? nullptr : dL_dscales,
-                              cov3D_precomp ? nullptr : dL_drotations, stream, debug);
+                              cov3D_precomp ? nullptr : dL_drotations, pose_points, dL_dpose, stream, debug);
     if (rc || shs == nullptr) return rc;
     // colour gradient -> SH coefficients, and the view-direction term added to dL/dmean (backward.cu:20-139)
     return launch_sh_backward(P, sh_degree, sh_coeffs, means3D, c->campos, shs, radii, g, dL_dcolors, dL_dmeans3D, dL_dsh,
-                              stream, debug);
+                              pose_points, dL_dpose, stream, debug);
 }
 
 int hs_profile_enable(int on) {

@@ -123,12 +123,12 @@ int launch_geom_backward(int P, const float* means3D, const int* radii, const fl
                          const float* rotations, const float* cov3D_precomp, const Camera& cam,
                          const float* dL_dmean2D, const float* dL_dconic, const float* dL_ddepths,
                          float* dL_dmeans3D, float* dL_dcov3D, float* dL_dscales, float* dL_drots,
-                         cudaStream_t stream, bool debug);
+                         const float* pose_points, float* dL_dpose, cudaStream_t stream, bool debug);
 int launch_sh_forward(int P, int deg, int M, const float* means3D, const float* campos, const float* shs,
                       const int* radii, const GeomView& g, cudaStream_t stream, bool debug);
 int launch_sh_backward(int P, int deg, int M, const float* means3D, const float* campos, const float* shs,
                        const int* radii, const GeomView& g, const float* dL_dcolors, float* dL_dmeans3D, float* dL_dsh,
-                       cudaStream_t stream, bool debug);
+                       const float* pose_points, float* dL_dpose, cudaStream_t stream, bool debug);
 int launch_mark_visible(int P, const float* means3D, const float* view, const float* proj, bool* present,
                         cudaStream_t stream, bool debug);
 

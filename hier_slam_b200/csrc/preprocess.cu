@@ -280,20 +280,21 @@ __global__ void __launch_bounds__(256) geom_backward_kernel(
     const float4* __restrict__ rotations, const float* __restrict__ cov3D_precomp, Camera cam,
     const float* __restrict__ dL_dmean2D, const float4* __restrict__ dL_dconic, const float* __restrict__ dL_ddepths,
     float* __restrict__ dL_dmeans3D, float* __restrict__ dL_dcov3D, float* __restrict__ dL_dscales,
-    float4* __restrict__ dL_drots) {
+    float4* __restrict__ dL_drots, const float* __restrict__ pose_points, float* __restrict__ dL_dpose) {
     __shared__ float s_view[16];
     __shared__ float s_proj[16];
+    __shared__ float s_pose[8][12];
     if (threadIdx.x < 16) s_view[threadIdx.x] = __ldg(cam.view + threadIdx.x);
     else if (threadIdx.x < 32) s_proj[threadIdx.x - 16] = __ldg(cam.proj + threadIdx.x - 16);
     __syncthreads();
     const int idx = blockIdx.x * 256 + threadIdx.x;
-    if (idx >= P) return;
+    const bool valid = idx < P;
     const bool has_scales = (cov3D_precomp == nullptr);
     float3 g_mean = {0.f, 0.f, 0.f};
     float g_cov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     float3 g_scale = {0.f, 0.f, 0.f};
     float4 g_rot = {0.f, 0.f, 0.f, 0.f};
-    if (radii[idx] > 0) {
+    if (valid && radii[idx] > 0) {
         const float3 mean = {means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]};
         float cov3D[6];
         float3 sc = {0.f, 0.f, 0.f};
@@ -418,16 +419,43 @@ __global__ void __launch_bounds__(256) geom_backward_kernel(
             g_rot.w = 2 * r * (dMt.m[0][1] - dMt.m[1][0]) + 2 * x * (dMt.m[2][0] + dMt.m[0][2]) + 2 * y * (dMt.m[1][2] + dMt.m[2][1]) - 4 * z * (dMt.m[1][1] + dMt.m[0][0]);
         }
     }
-    dL_dmeans3D[3 * idx] = g_mean.x;
-    dL_dmeans3D[3 * idx + 1] = g_mean.y;
-    dL_dmeans3D[3 * idx + 2] = g_mean.z;
+    if (valid) {
+        dL_dmeans3D[3 * idx] = g_mean.x;
+        dL_dmeans3D[3 * idx + 1] = g_mean.y;
+        dL_dmeans3D[3 * idx + 2] = g_mean.z;
 #pragma unroll
-    for (int k = 0; k < 6; k++) dL_dcov3D[(size_t)idx * 6 + k] = g_cov[k];
-    if (dL_dscales != nullptr) {
-        dL_dscales[3 * idx] = g_scale.x;
-        dL_dscales[3 * idx + 1] = g_scale.y;
-        dL_dscales[3 * idx + 2] = g_scale.z;
-        dL_drots[idx] = g_rot;
+        for (int k = 0; k < 6; k++) dL_dcov3D[(size_t)idx * 6 + k] = g_cov[k];
+        if (dL_dscales != nullptr) {
+            dL_dscales[3 * idx] = g_scale.x;
+            dL_dscales[3 * idx + 1] = g_scale.y;
+            dL_dscales[3 * idx + 2] = g_scale.z;
+            dL_drots[idx] = g_rot;
+        }
+    }
+    // Camera-pose gradient, pre-reduced here instead of by a [P,3]x[P,4] autograd matmul in the caller: when the means
+    // handed to the rasterizer are W [p_world; 1] (utils/slam_helpers.py:318-321), dL/dW[:3,:] = sum_i dL/dmean_i (x)
+    // [p_world_i, 1].  Warp shuffle -> shared memory -> 12 atomics per block (kernel-uniform branch).
+    if (dL_dpose != nullptr) {
+        float3 pw = {0.f, 0.f, 0.f};
+        if (valid) pw = {pose_points[3 * idx], pose_points[3 * idx + 1], pose_points[3 * idx + 2]};
+        float v[12] = {g_mean.x * pw.x, g_mean.x * pw.y, g_mean.x * pw.z, g_mean.x,
+                       g_mean.y * pw.x, g_mean.y * pw.y, g_mean.y * pw.z, g_mean.y,
+                       g_mean.z * pw.x, g_mean.z * pw.y, g_mean.z * pw.z, g_mean.z};
+#pragma unroll
+        for (int k = 0; k < 12; k++)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+        if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+            for (int k = 0; k < 12; k++) s_pose[threadIdx.x >> 5][k] = v[k];
+        }
+        __syncthreads();
+        if (threadIdx.x < 12) {
+            float t = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; w++) t += s_pose[w][threadIdx.x];
+            if (t != 0.f) atomicAdd(dL_dpose + threadIdx.x, t);
+        }
     }
 }
 
@@ -435,12 +463,13 @@ int launch_geom_backward(int P, const float* means3D, const int* radii, const fl
                          const float* rotations, const float* cov3D_precomp, const Camera& cam,
                          const float* dL_dmean2D, const float* dL_dconic, const float* dL_ddepths,
                          float* dL_dmeans3D, float* dL_dcov3D, float* dL_dscales, float* dL_drots,
-                         cudaStream_t stream, bool debug) {
+                         const float* pose_points, float* dL_dpose, cudaStream_t stream, bool debug) {
     if (P <= 0) return 0;
     prof_begin(ST_GEOM_BWD, stream);
     geom_backward_kernel<<<(P + 255) / 256, 256, 0, stream>>>(
         P, means3D, radii, scales, (const float4*)rotations, cov3D_precomp, cam, dL_dmean2D,
-        (const float4*)dL_dconic, dL_ddepths, dL_dmeans3D, dL_dcov3D, dL_dscales, (float4*)dL_drots);
+        (const float4*)dL_dconic, dL_ddepths, dL_dmeans3D, dL_dcov3D, dL_dscales, (float4*)dL_drots,
+        dL_dpose != nullptr ? pose_points : nullptr, dL_dpose);
     prof_end(ST_GEOM_BWD, stream);
     HS_LAUNCH_OK(stream, debug);
     return 0;

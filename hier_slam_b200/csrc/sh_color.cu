@@ -79,7 +79,9 @@ __global__ void __launch_bounds__(256) sh_backward_kernel(int P, int deg, int M,
                                                           const float* __restrict__ campos, const float* __restrict__ shs,
                                                           const int* __restrict__ radii, const uint8_t* __restrict__ clamped,
                                                           const float* __restrict__ dL_dcolors,
-                                                          float* __restrict__ dL_dmeans3D, float* __restrict__ dL_dsh) {
+                                                          float* __restrict__ dL_dmeans3D, float* __restrict__ dL_dsh,
+                                                          const float* __restrict__ pose_points,
+                                                          float* __restrict__ dL_dpose) {
     const int idx = blockIdx.x * 256 + threadIdx.x;
     if (idx >= P) return;
     float* out = dL_dsh + (size_t)idx * M * 3;
@@ -129,9 +131,18 @@ __global__ void __launch_bounds__(256) sh_backward_kernel(int P, int deg, int M,
     // through the normalisation of the direction (auxiliary.h:107-117)
     const float sum2 = d0.x * d0.x + d0.y * d0.y + d0.z * d0.z;
     const float inv32 = 1.0f / sqrtf(sum2 * sum2 * sum2);
-    dL_dmeans3D[3 * idx] += ((sum2 - d0.x * d0.x) * gx - d0.y * d0.x * gy - d0.z * d0.x * gz) * inv32;
-    dL_dmeans3D[3 * idx + 1] += (-d0.x * d0.y * gx + (sum2 - d0.y * d0.y) * gy - d0.z * d0.y * gz) * inv32;
-    dL_dmeans3D[3 * idx + 2] += (-d0.x * d0.z * gx - d0.y * d0.z * gy + (sum2 - d0.z * d0.z) * gz) * inv32;
+    const float3 dm = {((sum2 - d0.x * d0.x) * gx - d0.y * d0.x * gy - d0.z * d0.x * gz) * inv32,
+                       (-d0.x * d0.y * gx + (sum2 - d0.y * d0.y) * gy - d0.z * d0.y * gz) * inv32,
+                       (-d0.x * d0.z * gx - d0.y * d0.z * gy + (sum2 - d0.z * d0.z) * gz) * inv32};
+    dL_dmeans3D[3 * idx] += dm.x;
+    dL_dmeans3D[3 * idx + 1] += dm.y;
+    dL_dmeans3D[3 * idx + 2] += dm.z;
+    if (dL_dpose != nullptr) {   // the view-direction term also reaches the camera pose (rare path: plain atomics)
+        const float pw[4] = {pose_points[3 * idx], pose_points[3 * idx + 1], pose_points[3 * idx + 2], 1.f};
+        const float dmv[3] = {dm.x, dm.y, dm.z};
+        for (int r = 0; r < 3; r++)
+            for (int c = 0; c < 4; c++) atomicAdd(dL_dpose + 4 * r + c, dmv[r] * pw[c]);
+    }
 }
 
 int launch_sh_forward(int P, int deg, int M, const float* means3D, const float* campos, const float* shs,
@@ -144,10 +155,11 @@ int launch_sh_forward(int P, int deg, int M, const float* means3D, const float* 
 
 int launch_sh_backward(int P, int deg, int M, const float* means3D, const float* campos, const float* shs,
                        const int* radii, const GeomView& g, const float* dL_dcolors, float* dL_dmeans3D, float* dL_dsh,
-                       cudaStream_t stream, bool debug) {
+                       const float* pose_points, float* dL_dpose, cudaStream_t stream, bool debug) {
     if (P <= 0) return 0;
     sh_backward_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, deg, M, means3D, campos, shs, radii, g.clamped,
-                                                           dL_dcolors, dL_dmeans3D, dL_dsh);
+                                                           dL_dcolors, dL_dmeans3D, dL_dsh,
+                                                           dL_dpose != nullptr ? pose_points : nullptr, dL_dpose);
     HS_LAUNCH_OK(stream, debug);
     return 0;
 }

@@ -99,7 +99,11 @@ int hs_forward_render(const hs_camera* cam, int P, int S, int num_rendered, int 
  * dL_dopacity[P], dL_dcolors[P,3], dL_dsemantics[P,S], dL_ddepths[P].
  * Plain outputs — fully written: dL_dmeans3D[P,3], dL_dcov3D[P,6], dL_dscales[P,3], dL_drotations[P,4]
  * (the last two may be NULL when cov3D_precomp is used); dL_dsh[P, sh_coeffs, 3] when colors == NULL and shs is given
- * (spherical-harmonics colour path; its view-direction term is added to dL_dmeans3D). */
+ * (spherical-harmonics colour path; its view-direction term is added to dL_dmeans3D).
+ * Optional camera-pose pre-reduction (both NULL to skip): when means3D = W [p_world; 1] for a 3x4 pose W, pass
+ * pose_points = p_world [P,3]; dL_dpose[12] (row-major 3x4, zero-initialised by the caller) then accumulates
+ * dL/dW = sum_i dL_dmeans3D_i (x) [p_world_i, 1], reduced in the per-Gaussian kernel (warp shuffle, shared memory,
+ * 12 atomics per block) instead of by an autograd matmul over [P,3] in the caller. */
 int hs_backward(const hs_camera* cam, int P, int S, int num_rendered, const float* means3D, const int* radii,
                 const float* colors, const float* semantics, const float* scales, const float* rotations,
                 const float* cov3D_precomp, const float* shs, int sh_degree, int sh_coeffs, const void* geom_state, const void* binning_state,
@@ -107,7 +111,7 @@ int hs_backward(const hs_camera* cam, int P, int S, int num_rendered, const floa
                 const float* dL_dout_depth, const float* dL_dout_median_depth, const float* dL_dout_opacity,
                 float* dL_dmeans2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolors, float* dL_dsemantics,
                 float* dL_ddepths, float* dL_dmeans3D, float* dL_dcov3D, float* dL_dscales, float* dL_drotations,
-                float* dL_dsh, int flags, void* stream);
+                float* dL_dsh, const float* pose_points, float* dL_dpose, int flags, void* stream);
 
 /* present[P] (bool, device) = view-space z > 0.2 (reference: rasterizer_impl.cu:54-66). */
 int hs_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,

@@ -347,6 +347,54 @@ def test_tile_sort_size_classes(key, P, expect):
     assert all(bool(torch.isfinite(v).all()) for v in g.values())
 
 
+@pytest.mark.parametrize("semantic", [True, False])
+def test_fused_pose_step_matches_autograd_through_transform(semantic):
+    """hier_slam_b200.tracking.PoseRasterizer_semantic (pose gradient pre-reduced inside the per-Gaussian backward
+    kernel) against the reference's call pattern: torch transform of the means + GaussianRasterizer_semantic + autograd
+    (utils/slam_helpers.py:278-330)."""
+    import diff_gaussian_rasterization as dgr
+    from hier_slam_b200.scene import keyframe_poses
+    from hier_slam_b200.tracking import PoseRasterizer_semantic
+    cfg = CONFIGS["small"]
+    sc = make_scene(cfg, 17, device="cuda")
+    settings = pt.make_settings(dgr.GaussianRasterizationSettings, cfg)
+    ug = upstream_grads(cfg, 18, device="cuda")
+    w2c0 = keyframe_poses(1, seed=5)[0].cuda()
+    P = sc["means3D"].shape[0]
+
+    def loss_of(out):
+        color, radii, sem, depth, median, opac = out
+        l = (color * ug["color"]).sum() + (depth * ug["depth"]).sum() + (opac * ug["final_opacity"]).sum()
+        return l + (sem * ug["semantic"]).sum() if semantic else l
+
+    def leaves():
+        d = {k: v.clone().requires_grad_(True) for k, v in sc.items()}
+        d["w2c"] = w2c0.clone().requires_grad_(True)
+        return d
+    a = leaves()
+    pts4 = torch.cat((a["means3D"], torch.ones(P, 1, device="cuda")), 1)
+    means_cam = (a["w2c"] @ pts4.T).T[:, :3]
+    kw = dict(semantics_precomp=a["semantics_precomp"]) if semantic else {}
+    Raster = dgr.GaussianRasterizer_semantic if semantic else dgr.GaussianRasterizer
+    out = Raster(raster_settings=settings)(means3D=means_cam, means2D=torch.zeros_like(means_cam),
+                                           opacities=a["opacities"], colors_precomp=a["colors_precomp"],
+                                           scales=a["scales"], rotations=a["rotations"], **kw)
+    if not semantic:   # (color, radii, depth, median, opacity, mask) -> common order
+        out = (out[0], out[1], None, out[2], out[3], out[4])
+    loss_of(out).backward()
+    b = leaves()
+    out2 = PoseRasterizer_semantic(settings)(b["w2c"], b["means3D"], torch.zeros_like(b["means3D"]), b["opacities"],
+                                             b["colors_precomp"], b["scales"], b["rotations"],
+                                             b["semantics_precomp"] if semantic else None)
+    loss_of(out2).backward()
+    assert torch.equal(out[1], out2[1])
+    assert_images_close(out2[0], out[0], "colour")
+    assert_grads_close(b["w2c"].grad[:3], a["w2c"].grad[:3], "pose gradient", tol=1e-4)
+    assert float(b["w2c"].grad[3].abs().max()) == 0
+    for k in ("means3D", "opacities", "colors_precomp", "scales", "rotations") + (("semantics_precomp",) if semantic else ()):
+        assert_grads_close(b[k].grad, a[k].grad, k, tol=1e-4)
+
+
 def test_full_size_properties_c2():
     """BASELINE.json config 2 at full size (1200x680, 300K Gaussians, S=26): properties that need no oracle."""
     C, Settings = new_impl()

@@ -33,7 +33,7 @@ def quat_to_rot(q):
         torch.stack([2 * (x * z - r * y), 2 * (y * z + r * x), 1 - 2 * (x * x + y * y)])])
 
 
-def run(mod, cfg, frames, iters, dev="cuda"):
+def run(mod, cfg, frames, iters, dev="cuda", fused=False):
     Settings, Raster = mod.GaussianRasterizationSettings, mod.GaussianRasterizer_semantic
     sc = make_scene(cfg, 0, device=dev)
     P = sc["means3D"].shape[0]
@@ -48,8 +48,16 @@ def run(mod, cfg, frames, iters, dev="cuda"):
     gt_poses = keyframe_poses(frames, seed=2, max_angle_deg=1.0, max_trans=0.02).to(dev)
     ones = torch.ones(P, 1, device=dev)
 
+    if fused:   # pose as an input of the rasterizer, pose gradient pre-reduced in the backward kernel
+        from hier_slam_b200.tracking import PoseRasterizer_semantic
+        pose_raster = PoseRasterizer_semantic(settings)
+
     def render(w2c):
         pts = params["means3D"].detach()
+        if fused:
+            return pose_raster(w2c, pts, torch.zeros_like(pts), torch.sigmoid(params["logit_opacities"]),
+                               params["rgb_colors"], torch.exp(torch.tile(params["log_scales"], (1, 3))),
+                               F.normalize(params["unnorm_rotations"]), params["semantic"])
         tp = (w2c @ torch.cat((pts, ones), 1).T).T[:, :3]
         return raster(means3D=tp, means2D=torch.zeros_like(pts, requires_grad=True) + 0,
                       opacities=torch.sigmoid(params["logit_opacities"]), colors_precomp=params["rgb_colors"],
@@ -105,6 +113,10 @@ def main():
         run(ours, cfg, 1, 5)                       # warm-up
         res["ours"] = run(ours, cfg, a.frames, a.iters)
         print(json.dumps({"impl": "ours", "config": cfg.name, "workload": "c3 tracking", **res["ours"][0]}))
+        run(ours, cfg, 1, 5, fused=True)
+        res["fused"] = run(ours, cfg, a.frames, a.iters, fused=True)
+        print(json.dumps({"impl": "ours-fused-pose", "config": cfg.name, "workload": "c3 tracking", **res["fused"][0],
+                          "pose_trajectory_max_abs_diff_vs_unfused": float((res["fused"][1] - res["ours"][1]).abs().max())}))
     if a.impl in ("ref-cuda", "both"):
         from oracle import ref_loader
         ref = ref_loader.load_reference(cfg.num_semantic)
