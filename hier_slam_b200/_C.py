@@ -27,6 +27,39 @@ SORT_GLOBAL = os.environ.get("HS_SORT_GLOBAL", "0") == "1"   # reference-style g
 
 _contig_cache: dict = {}   # id(tensor) -> (weakref(tensor), version, contiguous copy)
 
+# -- gradient sinks ------------------------------------------------------------------------------------
+# A caller that keeps its parameters in one flat buffer (hier_slam_b200.mapping.FlatParams) can register, per
+# parameter tensor, the gradient buffer that belongs to it.  When `colors_precomp` / `semantics_precomp` of a
+# backward call ARE such parameters (same memory), the blend backward accumulates dL/dcolors and dL/dsemantics
+# straight into the registered buffers -- they are pure atomic accumulations anyway -- and returns None for them,
+# so autograd launches no AccumulateGrad add kernel and the call needs no [P, 3+S] zero fill.  With K keyframes per
+# mapping iteration the K gradients sum up in place.
+_grad_sinks: dict = {}     # data_ptr -> (weakref(param), grad buffer)
+
+
+def register_grad_sink(param: torch.Tensor, grad: torch.Tensor) -> None:
+    if not (param.is_cuda and grad.is_cuda and grad.dtype == torch.float32 and grad.is_contiguous()
+            and grad.shape == param.shape):
+        raise RuntimeError("gradient sink must be a contiguous float32 CUDA tensor of the parameter's shape")
+    _grad_sinks[param.data_ptr()] = (weakref.ref(param), grad)
+
+
+def clear_grad_sinks() -> None:
+    _grad_sinks.clear()
+
+
+def _sink_for(t: Optional[torch.Tensor]):
+    if t is None or not _grad_sinks or t.numel() == 0 or not t.is_contiguous():
+        return None
+    hit = _grad_sinks.get(t.data_ptr())
+    if hit is None:
+        return None
+    p = hit[0]()
+    if p is None or p.data_ptr() != t.data_ptr() or p.shape != t.shape or hit[1].device != t.device:
+        _grad_sinks.pop(t.data_ptr(), None)
+        return None
+    return hit[1]
+
 
 def _small_contig(t: torch.Tensor) -> torch.Tensor:
     """Contiguous float32 version of a small camera tensor, cached per tensor object + version
@@ -183,8 +216,10 @@ def _backward(background, means3D, radii, colors, semantics, scales, rotations, 
     use_sh = (colors is None or colors.numel() == 0) and M > 0
     fopt = dict(dtype=torch.float32, device=device)
     with torch.cuda.device(device):
-        # atomically accumulated outputs: ONE zero fill
-        nacc = 3 + 4 + 1 + 3 + S + 1
+        # atomically accumulated outputs: ONE zero fill (minus what goes straight into registered gradient sinks)
+        sink_c = _sink_for(colors) if not use_sh else None
+        sink_s = _sink_for(semantics) if S else None
+        nacc = 3 + 4 + 1 + (0 if sink_c is not None else 3) + (0 if sink_s is not None else S) + 1
         acc = torch.zeros(P * nacc, **fopt)
         o = 0
 
@@ -194,9 +229,9 @@ def _backward(background, means3D, radii, colors, semantics, scales, rotations, 
             o += P * cols
             return v
         dL_dconic = take(4).view(P, 2, 2)       # first: read back as float4 (needs 16-B alignment)
-        dL_dsemantics = take(S).view(P, S)
+        dL_dsemantics = sink_s if sink_s is not None else take(S).view(P, S)
         dL_dmeans2D = take(3).view(P, 3)
-        dL_dcolors = take(3).view(P, 3)
+        dL_dcolors = sink_c if sink_c is not None else take(3).view(P, 3)
         dL_dopacity = take(1).view(P, 1)
         dL_ddepths = take(1).view(P, 1)
         dL_dmeans3D = torch.empty(P, 3, **fopt)
@@ -235,6 +270,10 @@ def _backward(background, means3D, radii, colors, semantics, scales, rotations, 
                 _ptr(dL_drotations) if have_scales else None, _ptr(dL_dsh) if use_sh else None,
                 _ptr(pose_c), _ptr(dL_dpose), flags, stream), "hs_backward")
             del keep
+    if sink_c is not None:
+        dL_dcolors = None       # already accumulated into the registered gradient buffer
+    if sink_s is not None:
+        dL_dsemantics = None
     if pose_points is not None:
         return (dL_dmeans2D, dL_dcolors, dL_dsemantics, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales,
                 dL_drotations, dL_dpose)

@@ -21,7 +21,7 @@ import torch.distributed as dist
 class FlatParams:
     """Named fp32 leaves carved out of one flat buffer, with gradients carved out of one flat gradient buffer."""
 
-    def __init__(self, tensors: Dict[str, torch.Tensor]):
+    def __init__(self, tensors: Dict[str, torch.Tensor], direct_grads: bool = True):
         self.names: List[str] = list(tensors)
         self.shapes = {k: tuple(v.shape) for k, v in tensors.items()}
         sizes = [v.numel() for v in tensors.values()]
@@ -41,6 +41,11 @@ class FlatParams:
             leaf = self.flat[o:o + n].view(self.shapes[k]).requires_grad_(True)
             leaf.grad = self.flat_grad[o:o + n].view(self.shapes[k])
             self.leaves[k] = leaf
+            if direct_grads and leaf.is_cuda:
+                # the rasterizer's backward accumulates dL/dcolors and dL/dsemantics straight into this buffer when a
+                # leaf is handed to it unchanged (no autograd accumulate kernel, no [P, 3+S] zero fill per call)
+                from . import _C
+                _C.register_grad_sink(leaf, leaf.grad)
 
     def zero_grad(self) -> None:
         self.flat_grad.zero_()

@@ -536,3 +536,11 @@ def test_keyframe_parallel_mapping_gradient_sum():
         acc += p1.flat_grad
     assert_grads_close(total, acc, "sum of keyframe gradients", tol=1e-5)
     assert float(total.abs().max()) > 0
+    # gradient sinks (dL/dcolors, dL/dsemantics accumulated straight into the flat buffer) == plain autograd
+    from hier_slam_b200 import _C
+    _C.clear_grad_sinks()
+    plain = FlatParams(sc, direct_grads=False)
+    mapping_iteration(plain, losses, 0, 1)
+    assert_grads_close(total, plain.flat_grad, "direct accumulation vs autograd accumulation", tol=1e-5)
+    for k in ("colors_precomp", "semantics_precomp"):
+        assert float(plain.leaves[k].grad.abs().max()) > 0
