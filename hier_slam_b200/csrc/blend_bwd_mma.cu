@@ -157,9 +157,17 @@ __global__ void __launch_bounds__(32 * NW, (MmaCfg<S>::B_IN_REGS ? (16 / NW) : 1
     } else {
         float* my = s_dL + (size_t)(warp * 32) * DS;
         const int id = pixel_of(lane);
-        for (int c = 0; c < 8 * NBF; c++) {
-            const float* pl = plane_of(c);
-            my[lane * DS + c] = (pl != nullptr && id >= 0) ? __ldg(pl + id) : 0.f;
+        constexpr int LU = (8 * NBF) % 16 == 0 ? 16 : 8;   // independent loads in flight per lane
+#pragma unroll 1
+        for (int c0 = 0; c0 < 8 * NBF; c0 += LU) {
+            float v[LU];
+#pragma unroll
+            for (int u = 0; u < LU; u++) {
+                const float* pl = plane_of(c0 + u);
+                v[u] = (pl != nullptr && id >= 0) ? __ldg(pl + id) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < LU; u++) my[lane * DS + c0 + u] = v[u];
         }
     }
     // moment basis for this lane's fragment pixels: column qn of {1, x, y, x^2, xy, y^2, 0, 0}, tile-centred

@@ -18,6 +18,9 @@
 #ifndef HS_FWD_OCC
 #define HS_FWD_OCC 3    // CTAs per SM the narrow instantiations (S <= 26) are compiled for
 #endif
+#ifndef HS_FWD_OCC_WIDE
+#define HS_FWD_OCC_WIDE 1   // ... and S = 74 (2 CTAs per SM = 128 registers was measured slower: 427 vs 416 us at c5)
+#endif
 
 namespace hs {
 
@@ -48,7 +51,7 @@ __device__ __forceinline__ float2 unpack2(const unsigned long long v) {
 }
 
 template <int S, bool MASK>
-__global__ void __launch_bounds__(256, (S <= 26 ? HS_FWD_OCC : 1)) blend_forward_kernel(
+__global__ void __launch_bounds__(256, (S <= 26 ? HS_FWD_OCC : S <= 74 ? HS_FWD_OCC_WIDE : 1)) blend_forward_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H, int grid_x,
     const float2* __restrict__ means2D, const float* __restrict__ colors, const float* __restrict__ depths,
     const float* __restrict__ semantics, const float4* __restrict__ conic_opacity, float* __restrict__ final_T,
