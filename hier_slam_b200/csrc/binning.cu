@@ -263,18 +263,27 @@ __global__ void tile_ranges_kernel(int L, const uint64_t* __restrict__ keys, uin
 //      reference's (tests/test_gpu_parity.py).
 __global__ void __launch_bounds__(1024) tile_scan_kernel(int tiles, uint32_t* __restrict__ tile_count,
                                                          uint2* __restrict__ ranges, uint32_t* __restrict__ info) {
+    constexpr int IT = 4;   // consecutive tiles per thread: 4096 tiles per sweep, their loads are independent
     __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_small[32];
     __shared__ uint32_t s_carry;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_carry = 0;
     uint32_t my_max = 0, my_small = 0;
     __syncthreads();
-    for (int base = 0; base < tiles; base += 1024) {
-        const int t = base + tid;
-        const uint32_t c = t < tiles ? tile_count[(size_t)t * HS_CTR_STRIDE] : 0;
-        my_max = max(my_max, c);
-        my_small += (c > 0 && c <= HS_TILE_SORT_SMALL) ? 1u : 0u;
-        uint32_t incl = c;
+    for (int base = 0; base < tiles; base += 1024 * IT) {
+        const int t0 = base + tid * IT;
+        uint32_t c[IT];
+#pragma unroll
+        for (int k = 0; k < IT; k++) c[k] = (t0 + k < tiles) ? tile_count[(size_t)(t0 + k) * HS_CTR_STRIDE] : 0;
+        uint32_t sum = 0;
+#pragma unroll
+        for (int k = 0; k < IT; k++) {
+            sum += c[k];
+            my_max = max(my_max, c[k]);
+            my_small += (c[k] > 0 && c[k] <= HS_TILE_SORT_SMALL) ? 1u : 0u;
+        }
+        uint32_t incl = sum;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
@@ -293,10 +302,14 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(int tiles, uint32_t* __
         }
         __syncthreads();
         const uint32_t carry = s_carry;
-        const uint32_t start = carry + (warp > 0 ? s_warp[warp - 1] : 0) + incl - c;
-        if (t < tiles) {
-            ranges[t] = c > 0 ? make_uint2(start, start + c) : make_uint2(0u, 0u);
-            tile_count[(size_t)t * HS_CTR_STRIDE] = start;   // scatter cursor
+        uint32_t start = carry + (warp > 0 ? s_warp[warp - 1] : 0) + incl - sum;
+#pragma unroll
+        for (int k = 0; k < IT; k++) {
+            if (t0 + k < tiles) {
+                ranges[t0 + k] = c[k] > 0 ? make_uint2(start, start + c[k]) : make_uint2(0u, 0u);
+                tile_count[(size_t)(t0 + k) * HS_CTR_STRIDE] = start;   // scatter cursor
+            }
+            start += c[k];
         }
         __syncthreads();
         if (tid == 1023) s_carry = carry + s_warp[31];
@@ -307,7 +320,6 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(int tiles, uint32_t* __
         my_max = max(my_max, __shfl_xor_sync(0xffffffffu, my_max, o));
         my_small += __shfl_xor_sync(0xffffffffu, my_small, o);
     }
-    __shared__ uint32_t s_small[32];
     if (lane == 0) {
         s_warp[warp] = my_max;
         s_small[warp] = my_small;
