@@ -52,7 +52,14 @@ __device__ __forceinline__ float tf32_lo(const float x) {
 // NW = warps per CTA: a CTA owns a 16 x (2 NW) pixel slab of a tile (NW = 8: the whole tile; NW = 4: half a tile,
 // two CTAs walk the same Gaussian list).  Smaller CTAs give the register / shared-memory limited kernel a finer
 // occupancy granularity and cheaper barriers.
-template <int S, int NW>
+// The transmittance in front of an entry is reconstructed as T / (1 - alpha) (backward.cu:815).  A division is ~45 cycles
+// of dependent instructions on the loop-carried chain of this latency-bound loop, so the reciprocal of (1 - alpha) is
+// evaluated next to alpha (off the chain: rcp.approx + one Newton step) and the chain is
+//   EXACT_T  (a median-depth gradient is present: the reconstructed T decides which Gaussian receives it, quirk Q4):
+//            q = T r; rem = fma(-d, q, T); T' = fma(r, rem, q) -- the quotient-correction sequence of the IEEE division,
+//            bit-identical to T / d on d in [0.01, 1], T in (0, 1] (tools/micro/div_exact.cu: 2^33 pairs, 0 mismatches);
+//   !EXACT_T (every Hier-SLAM loss: no gradient reaches the median depth): T' = T r, one multiply per entry (<= 1 ulp).
+template <int S, int NW, bool EXACT_T>
 __global__ void __launch_bounds__(32 * NW, (MmaCfg<S>::B_IN_REGS ? (16 / NW) : 1)) blend_backward_mma_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H, int grid_x,
     const float* __restrict__ bg_color, const float2* __restrict__ means2D, const float4* __restrict__ conic_opacity,
@@ -252,7 +259,7 @@ __global__ void __launch_bounds__(32 * NW, (MmaCfg<S>::B_IN_REGS ? (16 / NW) : 1
             int my_ent = 0, nrow = 0;
 #pragma unroll 1
             for (int part = 0; part < 16 / U && todo != 0; part++) {
-                float oG[U];
+                float oG[U], rinv[U];
                 int ent[U];
                 uint32_t abits = 0, have_bits = 0;
 #pragma unroll
@@ -271,6 +278,12 @@ __global__ void __launch_bounds__(32 * NW, (MmaCfg<S>::B_IN_REGS ? (16 / NW) : 1
                     const bool active = have && (gi < last_contributor) && !(power > 0.0f) &&
                                         !(min(0.99f, og) < 1.0f / 255.0f);
                     oG[u] = og;
+                    {
+                        const float dd = 1.f - min(0.99f, og);
+                        float r0;
+                        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(dd));
+                        rinv[u] = EXACT_T ? fmaf(r0, fmaf(-dd, r0, 1.0f), r0) : r0;
+                    }
                     abits |= (active ? 1u : 0u) << u;
                 }
 #pragma unroll
@@ -283,7 +296,8 @@ __global__ void __launch_bounds__(32 * NW, (MmaCfg<S>::B_IN_REGS ? (16 / NW) : 1
                     const float alpha = min(0.99f, oG[u]);
                     // same IEEE division as the reference (backward.cu:815): the reconstructed transmittance decides
                     // which Gaussian receives the median-depth gradient, so it is kept bit-identical
-                    const float test_T = T / (1.f - alpha);
+                    float test_T = T * rinv[u];
+                    if (EXACT_T) test_T = fmaf(rinv[u], fmaf(alpha - 1.f, test_T, T), test_T);   // == T / (1 - alpha)
                     const float4 f = s_feat[j];
                     float q = f.x * dL_rgb[0] + f.y * dL_rgb[1] + f.z * dL_rgb[2];
                     q = fmaf(f.w, dL_depth, q);
@@ -291,7 +305,7 @@ __global__ void __launch_bounds__(32 * NW, (MmaCfg<S>::B_IN_REGS ? (16 / NW) : 1
                     const float acc_new = last_alpha * last_q + (1.f - last_alpha) * accum_q;
                     float dL_dalpha = (q - acc_new) * test_T;
                     if (bg_any) dL_dalpha -= __fdividef(T_final, 1.f - alpha) * bg_dot_dpixel;   // warp-uniform branch
-                    if (act && test_T > 0.5f && T < 0.5 && dL_median != 0.f)
+                    if (EXACT_T && act && test_T > 0.5f && T < 0.5 && dL_median != 0.f)
                         atomicAdd(dL_ddepths + s_id[j], dL_median);   // the Gaussian that crossed T = 0.5 (quirk Q4)
                     wm[row * WS + lane] = act ? alpha * test_T : 0.f;
                     gm[row * WS + lane] = act ? dL_dalpha * oG[u] : 0.f;   // dL/dG * G = (o dL/dalpha) G
@@ -422,7 +436,7 @@ __global__ void __launch_bounds__(32 * NW, (MmaCfg<S>::B_IN_REGS ? (16 / NW) : 1
     }
 }
 
-template <int S, int NW>
+template <int S, int NW, bool EXACT_T>
 static int launch_bwd_mma_t(const Camera& cam, const GeomView& g, const BinningView& b, const ImageView& img,
                             const float* bg, const float* colors, const float* dL_color, const float* dL_sem,
                             const float* dL_depth, const float* dL_median, const float* dL_opacity, float* dL_dmean2D,
@@ -432,7 +446,7 @@ static int launch_bwd_mma_t(const Camera& cam, const GeomView& g, const BinningV
     size_t smem = (size_t)Cfg::BATCH * (4 * sizeof(float4) + NW * Cfg::KA * sizeof(float) + 2 * sizeof(float2) + 6 * sizeof(int)) +
                   (size_t)2 * NW * 16 * Cfg::WS * sizeof(float) + 8 * sizeof(uint32_t);
     if (!Cfg::B_IN_REGS) smem += (size_t)32 * NW * Cfg::DS * sizeof(float);
-    auto k = blend_backward_mma_kernel<S, NW>;
+    auto k = blend_backward_mma_kernel<S, NW, EXACT_T>;
     HS_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(cam.grid_x, cam.grid_y * (8 / NW), 1);
     prof_begin(ST_BLEND_BWD, stream);
@@ -454,9 +468,13 @@ int launch_blend_backward_mma(int S, const Camera& cam, const GeomView& g, const
 #define HS_BWD_NW(SV) 8   /* measured on c2: whole-tile CTAs (1.44 ms) beat half-tile CTAs (1.59 ms) */
 #define HS_BWDM_CASE(SV)                                                                                        \
     case SV:                                                                                                    \
-        return launch_bwd_mma_t<SV, HS_BWD_NW(SV)>(cam, g, b, img, bg, colors, dL_color, dL_sem, dL_depth, dL_median, dL_opacity, \
-                                    dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolors, dL_dsemantics, dL_ddepths,  \
-                                    stream, debug);
+        if (dL_median != nullptr)                                                                               \
+            return launch_bwd_mma_t<SV, HS_BWD_NW(SV), true>(cam, g, b, img, bg, colors, dL_color, dL_sem, dL_depth, dL_median, \
+                                        dL_opacity, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolors, dL_dsemantics,     \
+                                        dL_ddepths, stream, debug);                                                    \
+        return launch_bwd_mma_t<SV, HS_BWD_NW(SV), false>(cam, g, b, img, bg, colors, dL_color, dL_sem, dL_depth, dL_median,   \
+                                    dL_opacity, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolors, dL_dsemantics,         \
+                                    dL_ddepths, stream, debug);
     switch (S) {
         HS_BWDM_CASE(0)
         HS_BWDM_CASE(16)

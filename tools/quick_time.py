@@ -25,6 +25,20 @@ for simt in (False, True):
     prof = _lib.profile_read(); lib.hs_profile_enable(0)
     print(json.dumps({"config": key, "bwd_simt": simt, **{k: round(v[0] / v[1] * 1e3, 1) for k, v in prof.items()}}))
 _C.BWD_SIMT = False
+# Hier-SLAM's own gradient pattern: colour, semantics, depth; median depth and silhouette receive no gradient
+gh = {k: (v if k in ("color", "semantic", "depth") else None) for k, v in grads.items()}
+for _ in range(3):
+    pt.run_backward(_C, settings, scene, f, gh, materialize=False)
+torch.cuda.synchronize()
+lib.hs_profile_enable(1); _lib.profile_read()
+for _ in range(iters):
+    g_h = pt.run_backward(_C, settings, scene, f, gh, materialize=False)
+torch.cuda.synchronize()
+prof = _lib.profile_read(); lib.hs_profile_enable(0)
+print(json.dumps({"config": key, "upstream": "colour+semantics+depth only", **{k: round(v[0] / v[1] * 1e3, 1) for k, v in prof.items()}}))
+gz = {k: (v if k in ("color", "semantic", "depth") else torch.zeros_like(v)) for k, v in grads.items()}
+g_z = pt.run_backward(_C, settings, scene, f, gz)
+print("fast-T vs exact-T:", {k: pt.grad_err(g_h[k], g_z[k])[0] for k in g_h})
 gm = pt.run_backward(_C, settings, scene, f, grads)
 _C.BWD_SIMT = True
 gs = pt.run_backward(_C, settings, scene, f, grads)
