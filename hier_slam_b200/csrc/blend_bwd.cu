@@ -288,7 +288,7 @@ int launch_blend_backward(int S, const Camera& cam, const GeomView& g, const Bin
     // non-semantic instantiation computes exactly the same gradients; dL_dsemantics keeps the caller's zeros.
     if (dL_sem == nullptr) S = 0;
     const bool exact = (flags & HS_FLAG_SEM_ALPHA_EXACT) != 0 && S > 0;
-    if (!exact && !(flags & HS_FLAG_BWD_SHUFFLE) && S <= 74)  // S = 102 would not fit in shared memory
+    if (!exact && !(flags & HS_FLAG_BWD_SHUFFLE) && (S <= 74 || S == 102))  // S = 102: two 51-channel passes
         return launch_blend_backward_mma(S, cam, g, b, img, bg, colors, dL_color, dL_sem, dL_depth, dL_median,
                                          dL_opacity, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolors, dL_dsemantics,
                                          dL_ddepths, stream, debug);

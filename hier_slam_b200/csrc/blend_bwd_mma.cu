@@ -69,7 +69,8 @@ __global__ void __launch_bounds__(32 * NW, (MmaCfg<S>::B_IN_REGS ? (16 / NW) : 1
     const float* __restrict__ dL_dpixels_sem, const float* __restrict__ dL_dpixel_depths,
     const float* __restrict__ dL_dpixel_medians, const float* __restrict__ dL_dpixel_opacitys,
     float* __restrict__ dL_dmean2D, float* __restrict__ dL_dconic2D, float* __restrict__ dL_dopacity,
-    float* __restrict__ dL_dcolors, float* __restrict__ dL_dsemantics, float* __restrict__ dL_ddepths) {
+    float* __restrict__ dL_dcolors, float* __restrict__ dL_dsemantics, float* __restrict__ dL_ddepths,
+    int sem_stride) {
     using Cfg = MmaCfg<S>;
     constexpr int B = Cfg::BATCH, NF = Cfg::NF, NBF = Cfg::NBF, KA = Cfg::KA, WS = Cfg::WS, DS = Cfg::DS;
     constexpr bool BREG = Cfg::B_IN_REGS;
@@ -196,7 +197,7 @@ __global__ void __launch_bounds__(32 * NW, (MmaCfg<S>::B_IN_REGS ? (16 / NW) : 1
     for (int k = 0; k < (NBF * 8 + 31) / 32; k++) {
         const int c = 32 * k + lane;
         feat_dst[k] = c < S ? dL_dsemantics + c : c < S + 3 ? dL_dcolors + (c - S) : c == S + 3 ? dL_ddepths : dL_dopacity;
-        feat_stride[k] = c < S ? S : c < S + 3 ? 3 : 1;
+        feat_stride[k] = c < S ? sem_stride : c < S + 3 ? 3 : 1;   // sem_stride: row length of dL_dsemantics (>= S)
     }
     float* wm = s_w + warp * 16 * WS;
     float* gm = s_g + warp * 16 * WS;
@@ -399,7 +400,7 @@ __global__ void __launch_bounds__(32 * NW, (MmaCfg<S>::B_IN_REGS ? (16 / NW) : 1
                     for (int st = 1; st < NW; st <<= 1)
 #pragma unroll
                         for (int wv = 0; wv + st < NW; wv += 2 * st) p8[wv] += p8[wv + st];
-                    atomicAdd(feat_dst[cb / 32] + id * feat_stride[cb / 32], p8[0]);
+                    if (p8[0] != 0.f) atomicAdd(feat_dst[cb / 32] + id * feat_stride[cb / 32], p8[0]);
                 }
             }
         }
@@ -420,7 +421,8 @@ __global__ void __launch_bounds__(32 * NW, (MmaCfg<S>::B_IN_REGS ? (16 / NW) : 1
             const float M0 = __shfl_sync(0xffffffffu, sum, base), M1 = __shfl_sync(0xffffffffu, sum, base + 1);
             const float M2 = __shfl_sync(0xffffffffu, sum, base + 2), M3 = __shfl_sync(0xffffffffu, sum, base + 3);
             const float M4 = __shfl_sync(0xffffffffu, sum, base + 4), M5 = __shfl_sync(0xffffffffu, sum, base + 5);
-            if (!((any_rows >> j) & 1) || m >= 6) continue;
+            if (!((any_rows >> j) & 1) || m >= 6 || M0 == 0.f && M1 == 0.f && M2 == 0.f && M3 == 0.f && M4 == 0.f && M5 == 0.f)
+                continue;   // all-zero moments: a channel-split pass without alpha gradients (S = 102), or nothing to add
             const size_t id = (size_t)s_id[j];
             const float2 xy = s_xy[j];
             const float4 co = s_co[j];
@@ -441,7 +443,7 @@ static int launch_bwd_mma_t(const Camera& cam, const GeomView& g, const BinningV
                             const float* bg, const float* colors, const float* dL_color, const float* dL_sem,
                             const float* dL_depth, const float* dL_median, const float* dL_opacity, float* dL_dmean2D,
                             float* dL_dconic, float* dL_dopacity, float* dL_dcolors, float* dL_dsemantics,
-                            float* dL_ddepths, cudaStream_t stream, bool debug) {
+                            float* dL_ddepths, int sem_stride, cudaStream_t stream, bool debug) {
     using Cfg = MmaCfg<S>;
     size_t smem = (size_t)Cfg::BATCH * (4 * sizeof(float4) + NW * Cfg::KA * sizeof(float) + 2 * sizeof(float2) + 6 * sizeof(int)) +
                   (size_t)2 * NW * 16 * Cfg::WS * sizeof(float) + 8 * sizeof(uint32_t);
@@ -453,7 +455,7 @@ static int launch_bwd_mma_t(const Camera& cam, const GeomView& g, const BinningV
     k<<<grid, 32 * NW, smem, stream>>>(img.ranges, b.point_list, cam.W, cam.H, cam.grid_x, bg, g.means2D, g.conic_opacity,
                                    colors, g.depths, img.final_T, img.n_contrib, b.strip_hits, dL_color, dL_sem, dL_depth, dL_median,
                                    dL_opacity, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolors, dL_dsemantics,
-                                   dL_ddepths);
+                                   dL_ddepths, sem_stride);
     prof_end(ST_BLEND_BWD, stream);
     HS_LAUNCH_OK(stream, debug);
     return 0;
@@ -471,10 +473,31 @@ int launch_blend_backward_mma(int S, const Camera& cam, const GeomView& g, const
         if (dL_median != nullptr)                                                                               \
             return launch_bwd_mma_t<SV, HS_BWD_NW(SV), true>(cam, g, b, img, bg, colors, dL_color, dL_sem, dL_depth, dL_median, \
                                         dL_opacity, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolors, dL_dsemantics,     \
-                                        dL_ddepths, stream, debug);                                                    \
+                                        dL_ddepths, SV, stream, debug);                                                \
         return launch_bwd_mma_t<SV, HS_BWD_NW(SV), false>(cam, g, b, img, bg, colors, dL_color, dL_sem, dL_depth, dL_median,   \
                                     dL_opacity, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolors, dL_dsemantics,         \
-                                    dL_ddepths, stream, debug);
+                                    dL_ddepths, SV, stream, debug);
+    if (S == 102) {
+        // Replica's flat 102-class map: two passes over 51 channels each.  The first carries everything that depends on
+        // the alpha gradients (colour, depth, silhouette, moments, median routing) plus dL/dsemantics[:, 0:51]; the second
+        // has no upstream gradient except the semantic planes 51..101, so its alpha gradients, moments and colour columns
+        // are exactly zero (skipped by the flush) and only dL/dsemantics[:, 51:102] is produced.  In the reference-observable
+        // mode the semantic channels never reach dL/dalpha (quirk Q1), which is what makes the split exact.
+        const size_t HW = (size_t)cam.W * cam.H;
+        int rc;
+        if (dL_median != nullptr)
+            rc = launch_bwd_mma_t<51, 8, true>(cam, g, b, img, bg, colors, dL_color, dL_sem, dL_depth, dL_median, dL_opacity,
+                                               dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolors, dL_dsemantics, dL_ddepths, 102,
+                                               stream, debug);
+        else
+            rc = launch_bwd_mma_t<51, 8, false>(cam, g, b, img, bg, colors, dL_color, dL_sem, dL_depth, dL_median, dL_opacity,
+                                                dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolors, dL_dsemantics, dL_ddepths, 102,
+                                                stream, debug);
+        if (rc || dL_sem == nullptr) return rc;
+        return launch_bwd_mma_t<51, 8, false>(cam, g, b, img, bg, colors, nullptr, dL_sem + 51 * HW, nullptr, nullptr, nullptr,
+                                              dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolors, dL_dsemantics + 51, dL_ddepths,
+                                              102, stream, debug);
+    }
     switch (S) {
         HS_BWDM_CASE(0)
         HS_BWDM_CASE(16)

@@ -102,7 +102,8 @@ def test_against_reference_golden(path):
 
 
 @pytest.mark.parametrize("key,S,semantic", [("tiny", 26, True), ("small", 26, True), ("tiny", 16, True),
-                                            ("small", 74, True), ("tiny", 102, True), ("small", 0, False)])
+                                            ("small", 74, True), ("tiny", 102, True), ("small", 102, True),
+                                            ("small", 0, False)])
 def test_against_cpu_oracle(key, S, semantic):
     C, Settings = new_impl()
     cfg = CONFIGS[key]
