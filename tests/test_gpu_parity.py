@@ -496,6 +496,16 @@ def test_public_api_autograd_and_edge_cases():
                                                   scales=far["scales"], rotations=far["rotations"],
                                                   semantics_precomp=far["semantics_precomp"])
     assert int((o[1] > 0).sum()) <= int((far["means3D"][:, 2] > 0.2).sum())
+    # debug=True: every launch is followed by a stream sync + error check (CHECK_CUDA of the reference); same results
+    dbg = pt.make_settings(dgr.GaussianRasterizationSettings, cfg, debug=True)
+    o_dbg = dgr.GaussianRasterizer_semantic(dbg)(means3D=sc["means3D"], means2D=sc["means3D"], opacities=sc["opacities"],
+                                                 colors_precomp=sc["colors_precomp"], scales=sc["scales"],
+                                                 rotations=sc["rotations"], semantics_precomp=sc["semantics_precomp"])
+    o_ref = dgr.GaussianRasterizer_semantic(settings)(means3D=sc["means3D"], means2D=sc["means3D"],
+                                                      opacities=sc["opacities"], colors_precomp=sc["colors_precomp"],
+                                                      scales=sc["scales"], rotations=sc["rotations"],
+                                                      semantics_precomp=sc["semantics_precomp"])
+    assert pt.bits_equal(o_dbg[0], o_ref[0]) == 0 and torch.equal(o_dbg[1], o_ref[1])
     # unsupported S is a loud error, not a fallback
     with pytest.raises(RuntimeError, match="not instantiated"):
         dgr.GaussianRasterizer_semantic(settings)(means3D=sc["means3D"], means2D=sc["means3D"],
