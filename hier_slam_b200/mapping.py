@@ -65,18 +65,58 @@ def allreduce_gradients(params: FlatParams, group=None) -> None:
         dist.all_reduce(params.flat_grad, op=dist.ReduceOp.SUM, group=group)
 
 
+_side_streams: Dict[int, List[torch.cuda.Stream]] = {}
+
+
 def mapping_iteration(params: FlatParams, keyframe_losses: Sequence[Callable[[Dict[str, torch.Tensor]], torch.Tensor]],
-                      rank: int = 0, world_size: int = 1, group=None) -> torch.Tensor:
+                      rank: int = 0, world_size: int = 1, group=None, streams: int = 2) -> torch.Tensor:
     """One data-parallel mapping iteration.
 
     keyframe_losses[k](leaves) renders keyframe k from the shared Gaussian leaves and returns its scalar loss.
     This rank evaluates keyframes k = rank, rank+G, ...; their gradients accumulate in params.flat_grad; the
-    buffer is then all-reduced.  Returns this rank's summed loss (detached)."""
+    buffer is then all-reduced.  Returns this rank's summed loss (detached).
+
+    With more than one local keyframe the keyframes alternate between `streams` CUDA streams: the forward of
+    keyframe k+1 (including its num_rendered read-back, which waits on its own stream only) overlaps the backward of
+    keyframe k, so the GPU is never idle behind the host sync and the tails of the blend kernels are filled.  The
+    renders are independent; the gradient buffer is only ever accumulated into (atomics in the blend backward,
+    autograd's stream-ordered AccumulateGrad for the rest)."""
     params.zero_grad()
-    total = torch.zeros((), device=params.flat.device)
-    for k in keyframes_of_rank(len(keyframe_losses), rank, world_size):
-        loss = keyframe_losses[k](params.leaves)
-        loss.backward()
-        total = total + loss.detach()
+    dev = params.flat.device
+    total = torch.zeros((), device=dev)
+    mine = keyframes_of_rank(len(keyframe_losses), rank, world_size)
+    use_streams = dev.type == "cuda" and streams > 1 and len(mine) > 1
+    if use_streams:
+        pool = _side_streams.setdefault(dev.index, [])
+        while len(pool) < streams:
+            pool.append(torch.cuda.Stream(dev))
+        main = torch.cuda.current_stream(dev)
+        for st in pool[:streams]:
+            st.wait_stream(main)              # zero_grad and every earlier use of the leaves
+        parts = []
+        # the leaves' AccumulateGrad nodes live on `main`; autograd orders them after the producing side stream (that
+        # is the intended behaviour here, so its advisory warning about the stream mismatch is switched off)
+        quiet = getattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch", None)
+        if quiet is not None:
+            quiet(False)
+        try:
+            for i, k in enumerate(mine):
+                st = pool[i % streams]
+                with torch.cuda.stream(st):
+                    loss = keyframe_losses[k](params.leaves)
+                    loss.backward()
+                    parts.append(loss.detach())
+        finally:
+            if quiet is not None:
+                quiet(True)
+        for st in pool[:streams]:
+            main.wait_stream(st)
+        for part in parts:
+            total = total + part
+    else:
+        for k in mine:
+            loss = keyframe_losses[k](params.leaves)
+            loss.backward()
+            total = total + loss.detach()
     allreduce_gradients(params, group)
     return total
