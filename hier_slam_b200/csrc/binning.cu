@@ -443,6 +443,10 @@ __device__ __forceinline__ void bitonic_first16(uint64_t* s, uint32_t n2, int ti
     }
 }
 
+#ifndef HS_SORT_T_SMALL
+#define HS_SORT_T_SMALL 128   // threads per CTA for tile lists of up to HS_TILE_SORT_SMALL entries
+#endif
+
 template <int T>
 __global__ void __launch_bounds__(T) tile_sort_kernel(const uint2* __restrict__ ranges, const uint64_t* __restrict__ seg,
                                                       uint32_t* __restrict__ point_list, uint64_t* __restrict__ keys,
@@ -502,7 +506,7 @@ int launch_tile_binning(int P, int R, int max_tile, int n_small, const Camera& c
     if (n_small > 0) {
         uint32_t cap = 16;
         while (cap < (uint32_t)max_tile && cap < small_cap) cap <<= 1;
-        tile_sort_kernel<128><<<tiles, 128, (cap + cap / 16) * sizeof(uint64_t), stream>>>(
+        tile_sort_kernel<HS_SORT_T_SMALL><<<tiles, HS_SORT_T_SMALL, (cap + cap / 16) * sizeof(uint64_t), stream>>>(
             img.ranges, b.keys_unsorted, b.point_list, b.keys, 0u, small_cap);
         count_launch();
     }
