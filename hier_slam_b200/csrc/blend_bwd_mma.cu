@@ -7,14 +7,16 @@
 //     moments[j][m]   = sum_pix g[j,pix] * phi_m(pix)               phi = {1, x, y, x^2, x y, y^2} (tile-centred)
 // with w = alpha * T_front and g = dL/dG * G.  The 2D-mean, conic and opacity gradients are closed-form functions of
 // the six moments (dx = x_j - x, so sum g dx^2 = x_j^2 M0 - 2 x_j M1 + M3, ...).  Each warp owns a 16x2 pixel strip:
-//   phase 1 (SIMT, one pixel per lane): walk 16 Gaussians back to front exactly like the reference (same alpha / T
-//            arithmetic), write w and g into two per-warp shared-memory matrices [16][32];
+//   phase 1 (SIMT, one pixel per lane): walk, back to front and with the reference's alpha / T arithmetic, the list
+//            entries that the forward blended into this strip (strip_hits: ~37 % of the (strip, entry) pairs), and write
+//            w and g into two per-warp shared-memory matrices [16][32] whose rows are packed (row r <-> r-th hit entry);
 //   phase 2 (tensor cores): D[16 Gaussians][8 channels] += A[16][8 pixels] * B[8 pixels][8 channels] with
 //            mma.sync.m16n8k8 TF32 and the 3xTF32 split (a_hi*b_hi + a_lo*b_hi + a_hi*b_lo, fp32 accumulate), so the
 //            result keeps fp32 accuracy (the moment basis is exactly representable in TF32, two products suffice);
-//   then     every warp stores its D tiles into a warp-private partial tile (no shared-memory atomics: fp32 atomicAdd on
-//            shared memory is a CAS loop), and once per round all 256 threads sum the 8 partials and flush each
-//            (tile, Gaussian, channel) ONCE to global memory with coalesced atomics.
+//   then     every warp scatters its D rows to the entries' rows of a warp-private partial tile (no shared-memory
+//            atomics: fp32 atomicAdd on shared memory is a CAS loop, ATOMS.CAST.SPIN), and once per round of 32 entries
+//            all 256 threads sum the partials of the warps that wrote a row and flush each (tile, Gaussian, channel)
+//            ONCE to global memory with coalesced atomics.
 // This replaces the (S+10)-value warp shuffle reduction of the SIMT version -- 64 % of a step in round 1 -- by
 // ~8 tensor instructions per (warp, Gaussian).
 #include "hs_common.cuh"
@@ -466,8 +468,8 @@ int launch_blend_backward_mma(int S, const Camera& cam, const GeomView& g, const
                               const float* dL_depth, const float* dL_median, const float* dL_opacity,
                               float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolors,
                               float* dL_dsemantics, float* dL_ddepths, cudaStream_t stream, bool debug) {
-// warps per CTA: half-tile CTAs while the dL fragments fit in registers, whole-tile CTAs (dL tile in smem) above
-#define HS_BWD_NW(SV) 8   /* measured on c2: whole-tile CTAs (1.44 ms) beat half-tile CTAs (1.59 ms) */
+// warps per CTA: whole-tile CTAs everywhere (half-tile CTAs, NW = 4, measured slower: 856 vs 804 us at c2)
+#define HS_BWD_NW(SV) 8
 #define HS_BWDM_CASE(SV)                                                                                        \
     case SV:                                                                                                    \
         if (dL_median != nullptr)                                                                               \
