@@ -7,8 +7,11 @@
 // bit.  What is new: every per-Gaussian operand of the inner loop, including the (4+S)-float feature row
 // [r g b depth s0..s(S-1)], is staged once per batch in shared memory and consumed with 128-bit broadcast
 // loads (the reference re-reads colour and semantic rows from global memory for every contributing pixel,
-// forward.cu:505-508); a conservative footprint box per Gaussian lets a whole warp (a 16x2 pixel strip) skip a
-// Gaussian with one shared load and four compares; and culled / finished tiles leave after one vote.
+// forward.cu:505-508), batches double-buffered with cp.async; a conservative footprint box per Gaussian gives an
+// 8-bit strip mask, and a warp (a 16x2 pixel strip) iterates only over the set bits of its ballot of 32 entries; the
+// inner loop has no divergent branch (non-contributing lanes blend with weight 0, votes are warp-uniform); channels
+// are blended in pairs with the packed FFMA2; and the strips that actually blended an entry are recorded
+// (strip_hits) so that the backward visits exactly those (strip, entry) pairs.
 #include "hs_common.cuh"
 #include <cuda_pipeline.h>
 

@@ -168,8 +168,6 @@ __device__ __forceinline__ float4 footprint_box(const float2 xy, const float4 co
 enum : int {
     HS_FLAG_SEM_ALPHA_EXACT = 1,   // semantic channels contribute to dL/dalpha (reference quirk Q1 off)
     HS_FLAG_NO_CULL = 2,           // disable the conservative per-warp footprint test
-    HS_FLAG_SORT_CUB = 32,         // binning: reference-style scan + duplicate + global radix sort (CUB) instead of
-                                   // the tile-bucket sort (identical sorted keys / lists / ranges)
     HS_FLAG_SEM_UNALIGNED = 16,    // internal: semantics base pointer is only 4-byte aligned (scalar cp.async)
     HS_FLAG_BWD_SHUFFLE = 4,       // backward: SIMT warp-shuffle reduction instead of the tensor-core path
 };
