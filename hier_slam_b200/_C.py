@@ -104,6 +104,20 @@ def _camera(background, scale_modifier, viewmatrix, projmatrix, tan_fovx, tan_fo
     return cam, keep
 
 
+_BUILT_S = (16, 26, 74, 102)   # semantic channel counts instantiated in libhsraster (hs_supports_semantic_channels)
+
+
+def _padded_channels(S: int) -> int:
+    """Kernels are instantiated for the channel counts Hier-SLAM ships (config.h:18: 16 / 26 / 74 / 102).  Any other
+    S <= 102 (another label tree) runs on the next larger instantiation with zero-padded columns: the extra channels
+    blend zeros, receive zero upstream gradients and are sliced away again."""
+    for b in _BUILT_S:
+        if S <= b:
+            return b
+    raise RuntimeError(f"semantic channel count S={S} is not instantiated in libhsraster (built: 0,16,26,74,102; "
+                       f"other values up to 102 are zero-padded)")
+
+
 def _forward(background, means3D, colors, semantics, opacity, scales, rotations, scale_modifier, cov3D_precomp,
              viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height, image_width, sh, degree, campos, prefiltered,
              debug, semantic: bool):
@@ -188,10 +202,14 @@ def rasterize_gaussians_semantic(background, means3D, colors, semantics, opacity
                                  cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height,
                                  image_width, sh, degree, campos, prefiltered, debug):
     """reference: RasterizeGaussiansCUDA_semantic, rasterize_points.cu:240-336."""
+    S = int(semantics.size(1)) if (semantics is not None and semantics.dim() == 2 and semantics.numel() > 0) else 0
+    Sp = _padded_channels(S) if S > 0 else 0
+    if Sp != S:
+        semantics = torch.nn.functional.pad(semantics, (0, Sp - S))
     n, o, radii, gb, bb, ib = _forward(background, means3D, colors, semantics, opacity, scales, rotations,
                                        scale_modifier, cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy,
                                        image_height, image_width, sh, degree, campos, prefiltered, debug, True)
-    return n, o[0], o[1], o[2], o[3], o[4], radii, gb, bb, ib
+    return n, o[0], (o[1][:S] if Sp != S else o[1]), o[2], o[3], o[4], radii, gb, bb, ib
 
 
 def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp,
@@ -293,22 +311,32 @@ def rasterize_gaussians_backward_semantic(background, means3D, radii, colors, se
                                           scale_modifier, cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy,
                                           dL_dout_color, dL_dout_semantic, dL_dout_depth, dL_dout_median_depth,
                                           dL_dout_final_opacity, sh, degree, campos, geomBuffer, R, binningBuffer,
-                                          imageBuffer, debug, image_height=None, image_width=None):
+                                          imageBuffer, debug, image_height=None, image_width=None, pose_points=None):
     """reference: RasterizeGaussiansBackwardCUDA_semantic, rasterize_points.cu:339-432.  H and W are taken from
     dL_dout_color like the reference does (:369-370); the two optional trailing arguments supply them when the
-    caller passes None for unmaterialised gradients."""
+    caller passes None for unmaterialised gradients.  pose_points (extension, hier_slam_b200.tracking): world-frame
+    means; the tuple then ends with dL_dpose [3,4]."""
     H, W = _hw(imageBuffer, (dL_dout_color, dL_dout_semantic, dL_dout_depth, dL_dout_median_depth,
                              dL_dout_final_opacity), image_height, image_width)
-    return _backward(background, means3D, radii, colors, semantics, scales, rotations, scale_modifier, cov3D_precomp,
-                     viewmatrix, projmatrix, tan_fovx, tan_fovy, dL_dout_color, dL_dout_semantic, dL_dout_depth,
-                     dL_dout_median_depth, dL_dout_final_opacity, sh, degree, campos, geomBuffer, R, binningBuffer,
-                     imageBuffer, debug, H, W, True)
+    S = int(semantics.size(1)) if (semantics is not None and semantics.dim() == 2 and semantics.numel() > 0) else 0
+    Sp = _padded_channels(S) if S > 0 else 0
+    if Sp != S:   # zero-padded instantiation (see _padded_channels): the forward state was produced with Sp channels
+        semantics = torch.nn.functional.pad(semantics, (0, Sp - S))
+        if dL_dout_semantic is not None:
+            dL_dout_semantic = torch.cat((dL_dout_semantic, dL_dout_semantic.new_zeros(Sp - S, H, W)), 0)
+    r = _backward(background, means3D, radii, colors, semantics, scales, rotations, scale_modifier, cov3D_precomp,
+                  viewmatrix, projmatrix, tan_fovx, tan_fovy, dL_dout_color, dL_dout_semantic, dL_dout_depth,
+                  dL_dout_median_depth, dL_dout_final_opacity, sh, degree, campos, geomBuffer, R, binningBuffer,
+                  imageBuffer, debug, H, W, True, pose_points=pose_points)
+    if Sp != S and r[2] is not None:
+        r = r[:2] + (r[2][:, :S],) + r[3:]
+    return r
 
 
 def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rotations, scale_modifier, cov3D_precomp,
                                  viewmatrix, projmatrix, tan_fovx, tan_fovy, dL_dout_color, dL_dout_depth,
                                  dL_dout_median_depth, dL_dout_final_opacity, sh, degree, campos, geomBuffer, R,
-                                 binningBuffer, imageBuffer, debug, image_height=None, image_width=None):
+                                 binningBuffer, imageBuffer, debug, image_height=None, image_width=None, pose_points=None):
     """reference: RasterizeGaussiansBackwardCUDA, rasterize_points.cu:119-215.
     Returns (dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations)."""
     H, W = _hw(imageBuffer, (dL_dout_color, dL_dout_depth, dL_dout_median_depth, dL_dout_final_opacity),
@@ -316,8 +344,8 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
     r = _backward(background, means3D, radii, colors, None, scales, rotations, scale_modifier, cov3D_precomp,
                   viewmatrix, projmatrix, tan_fovx, tan_fovy, dL_dout_color, None, dL_dout_depth,
                   dL_dout_median_depth, dL_dout_final_opacity, sh, degree, campos, geomBuffer, R, binningBuffer,
-                  imageBuffer, debug, H, W, False)
-    return r[0], r[1], r[3], r[4], r[5], r[6], r[7], r[8]
+                  imageBuffer, debug, H, W, False, pose_points=pose_points)
+    return (r[0], r[1], r[3], r[4], r[5], r[6], r[7], r[8]) + ((r[9],) if pose_points is not None else ())
 
 
 def mark_visible(means3D, viewmatrix, projmatrix):

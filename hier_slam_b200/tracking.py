@@ -53,11 +53,21 @@ class _RasterizePose(torch.autograd.Function):
         rs = ctx.rs
         (w2c, means_world, means_cam, colors, semantics, scales, rotations, radii, gb, bb, ib) = ctx.saved_tensors
         e = torch.Tensor([])
-        (d_means2D, d_colors, d_sem, d_opac, d_means_cam, _d_cov, _d_sh, d_scales, d_rots, d_pose) = _C._backward(
-            rs.bg, means_cam, radii, colors, semantics if ctx.semantic else None, scales, rotations, rs.scale_modifier,
-            None, rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, g_color, g_sem if ctx.semantic else None,
-            g_depth, g_median, g_opacity, e, rs.sh_degree, rs.campos, gb, ctx.num_rendered, bb, ib, rs.debug,
-            rs.image_height, rs.image_width, ctx.semantic, pose_points=means_world)
+        if ctx.semantic:
+            (d_means2D, d_colors, d_sem, d_opac, d_means_cam, _d_cov, _d_sh, d_scales, d_rots, d_pose) = \
+                _C.rasterize_gaussians_backward_semantic(
+                    rs.bg, means_cam, radii, colors, semantics, scales, rotations, rs.scale_modifier, e, rs.viewmatrix,
+                    rs.projmatrix, rs.tanfovx, rs.tanfovy, g_color, g_sem, g_depth, g_median, g_opacity, e, rs.sh_degree,
+                    rs.campos, gb, ctx.num_rendered, bb, ib, rs.debug, rs.image_height, rs.image_width,
+                    pose_points=means_world)
+        else:
+            d_sem = None
+            (d_means2D, d_colors, d_opac, d_means_cam, _d_cov, _d_sh, d_scales, d_rots, d_pose) = \
+                _C.rasterize_gaussians_backward(
+                    rs.bg, means_cam, radii, colors, scales, rotations, rs.scale_modifier, e, rs.viewmatrix,
+                    rs.projmatrix, rs.tanfovx, rs.tanfovy, g_color, g_depth, g_median, g_opacity, e, rs.sh_degree,
+                    rs.campos, gb, ctx.num_rendered, bb, ib, rs.debug, rs.image_height, rs.image_width,
+                    pose_points=means_world)
         g_w2c = torch.zeros_like(w2c)
         g_w2c[:3, :] = d_pose
         g_world = d_means_cam @ w2c[:3, :3] if ctx.needs_input_grad[1] else None

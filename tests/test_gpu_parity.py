@@ -506,13 +506,22 @@ def test_public_api_autograd_and_edge_cases():
                                                       scales=sc["scales"], rotations=sc["rotations"],
                                                       semantics_precomp=sc["semantics_precomp"])
     assert pt.bits_equal(o_dbg[0], o_ref[0]) == 0 and torch.equal(o_dbg[1], o_ref[1])
-    # unsupported S is a loud error, not a fallback
+    # a channel count without its own instantiation runs zero-padded on the next larger one: same colour image, and
+    # semantic planes / gradients equal to the padded call's first channels
+    sem5 = sc["semantics_precomp"][:, :5].contiguous().requires_grad_(True)
+    o5 = dgr.GaussianRasterizer_semantic(settings)(means3D=sc["means3D"], means2D=sc["means3D"], opacities=sc["opacities"],
+                                                   colors_precomp=sc["colors_precomp"], scales=sc["scales"],
+                                                   rotations=sc["rotations"], semantics_precomp=sem5)
+    assert o5[2].shape == (5, cfg.height, cfg.width) and pt.bits_equal(o5[0], o_ref[0]) == 0
+    assert pt.bits_equal(o5[2], o_ref[2][:5]) == 0
+    (o5[2] * o5[2].detach()).sum().backward()
+    assert sem5.grad.shape == sem5.shape and float(sem5.grad.abs().max()) > 0
+    # more channels than the largest instantiation is a loud error, not a fallback
     with pytest.raises(RuntimeError, match="not instantiated"):
         dgr.GaussianRasterizer_semantic(settings)(means3D=sc["means3D"], means2D=sc["means3D"],
                                                   opacities=sc["opacities"], colors_precomp=sc["colors_precomp"],
                                                   scales=sc["scales"], rotations=sc["rotations"],
-                                                  semantics_precomp=sc["semantics_precomp"][:, :5].contiguous())
-
+                                                  semantics_precomp=torch.rand(sc["means3D"].shape[0], 120, device="cuda"))
 
 def test_keyframe_parallel_mapping_gradient_sum():
     """SURVEY.md section 8e criterion on one GPU: the flat gradient buffer after a K-keyframe mapping iteration
