@@ -327,6 +327,15 @@ int hs_profile_read(float total_ms[8], int count[8]) { return prof_read(total_ms
 long long hs_kernel_launch_count(void) { return launches(); }
 long long hs_library_call_count(void) { return lib_calls(); }
 
+int hs_masked_l1(const float* pred, const float* target, const unsigned char* mask, int channels, size_t pixels,
+                 float* loss, float* grad, void* stream_) {
+    if (pred == nullptr || target == nullptr || loss == nullptr || grad == nullptr) {
+        set_error("hs_masked_l1: NULL argument");
+        return 1;
+    }
+    return launch_masked_l1(pred, target, mask, channels, pixels, loss, grad, (cudaStream_t)stream_);
+}
+
 int hs_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
                     unsigned char* present, void* stream_) {
     return launch_mark_visible(P, means3D, viewmatrix, projmatrix, (bool*)present, (cudaStream_t)stream_, false);

@@ -129,6 +129,8 @@ int launch_sh_forward(int P, int deg, int M, const float* means3D, const float* 
 int launch_sh_backward(int P, int deg, int M, const float* means3D, const float* campos, const float* shs,
                        const int* radii, const GeomView& g, const float* dL_dcolors, float* dL_dmeans3D, float* dL_dsh,
                        const float* pose_points, float* dL_dpose, cudaStream_t stream, bool debug);
+int launch_masked_l1(const float* pred, const float* target, const uint8_t* mask, int C, size_t HW, float* loss,
+                     float* grad, cudaStream_t stream);
 int launch_mark_visible(int P, const float* means3D, const float* view, const float* proj, bool* present,
                         cudaStream_t stream, bool debug);
 

@@ -113,6 +113,13 @@ int hs_backward(const hs_camera* cam, int P, int S, int num_rendered, const floa
                 float* dL_ddepths, float* dL_dmeans3D, float* dL_dcov3D, float* dL_dscales, float* dL_drotations,
                 float* dL_dsh, const float* pose_points, float* dL_dpose, int flags, void* stream);
 
+/* Extension (first step of the fused loss epilogue): masked L1 image loss and its gradient in one pass.
+ * loss[0] (device, zero-initialised by the caller) += sum over channels c and masked pixels p of |pred[c,p] - target[c,p]|;
+ * grad[c,p] = mask[p] * sign(pred - target).  mask: [pixels] bytes (non-zero = use), NULL = every pixel.
+ * Replaces `torch.abs(gt - x)[mask].sum()` of the reference's losses (scripts/hierslam.py:780-796). */
+int hs_masked_l1(const float* pred, const float* target, const unsigned char* mask, int channels, size_t pixels,
+                 float* loss, float* grad, void* stream);
+
 /* present[P] (bool, device) = view-space z > 0.2 (reference: rasterizer_impl.cu:54-66). */
 int hs_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
                     unsigned char* present, void* stream);

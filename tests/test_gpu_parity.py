@@ -396,6 +396,29 @@ def test_fused_pose_step_matches_autograd_through_transform(semantic):
         assert_grads_close(b[k].grad, a[k].grad, k, tol=1e-4)
 
 
+def test_masked_l1_sum_matches_boolean_indexing():
+    """hier_slam_b200.losses.masked_l1_sum == torch.abs(gt - x)[mask].sum() (the reference's loss form,
+    scripts/hierslam.py:780-796), value and gradient, with and without a mask."""
+    from hier_slam_b200.losses import masked_l1_sum
+    g = torch.Generator().manual_seed(41)
+    H, W = 123, 77
+    for C in (1, 3):
+        x = torch.randn(C, H, W, generator=g).cuda().requires_grad_(True)
+        x2 = x.detach().clone().requires_grad_(True)
+        gt = torch.randn(C, H, W, generator=g).cuda()
+        gt[0, 5, 5] = float(x[0, 5, 5])                       # an exact zero of the difference
+        mask = (torch.rand(1, H, W, generator=g) < 0.6).cuda()
+        for m in (mask, None):
+            for t in (x, x2):
+                t.grad = None
+            a = masked_l1_sum(x, gt, m)
+            b = torch.abs(gt - x2)[m.expand(C, -1, -1)].sum() if m is not None else torch.abs(gt - x2).sum()
+            (2.5 * a).backward()
+            (2.5 * b).backward()
+            assert abs(float(a) - float(b)) <= 1e-4 * abs(float(b))
+            assert torch.equal(x.grad, x2.grad)
+
+
 def test_full_size_properties_c2():
     """BASELINE.json config 2 at full size (1200x680, 300K Gaussians, S=26): properties that need no oracle."""
     C, Settings = new_impl()
