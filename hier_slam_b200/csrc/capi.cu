@@ -336,6 +336,17 @@ int hs_masked_l1(const float* pred, const float* target, const unsigned char* ma
     return launch_masked_l1(pred, target, mask, channels, pixels, loss, grad, (cudaStream_t)stream_);
 }
 
+int hs_hier_cross_entropy(const float* sem, const int* labels, int levels, const int* level_begin,
+                          const float* level_scale, size_t pixels, float* loss, float* grad, void* stream_) {
+    if (sem == nullptr || labels == nullptr || level_begin == nullptr || level_scale == nullptr || loss == nullptr ||
+        grad == nullptr) {
+        set_error("hs_hier_cross_entropy: NULL argument");
+        return 1;
+    }
+    return launch_hier_cross_entropy(sem, labels, levels, level_begin, level_scale, pixels, loss, grad,
+                                     (cudaStream_t)stream_);
+}
+
 int hs_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
                     unsigned char* present, void* stream_) {
     return launch_mark_visible(P, means3D, viewmatrix, projmatrix, (bool*)present, (cudaStream_t)stream_, false);

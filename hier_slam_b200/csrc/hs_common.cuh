@@ -8,6 +8,7 @@
 #define HS_TILE_X 16          // reference: cuda_rasterizer/config.h:16  (BLOCK_X)
 #define HS_TILE_Y 16          // reference: cuda_rasterizer/config.h:17  (BLOCK_Y)
 #define HS_TILE_PIX 256
+#define HS_MAX_LEVELS 8        // levels of the hierarchical semantic encoding (hs_hier_cross_entropy)
 #define HS_ALIGN 256          // every array inside an opaque state buffer is 256-B aligned
 #define HS_CTR_STRIDE 32          // per-tile counters sit 128 B apart: L2 atomics serialise per line, not per word
 #define HS_TILE_SORT_SMALL 2048   // tile lists up to this length are sorted by 256-thread CTAs
@@ -131,6 +132,8 @@ int launch_sh_backward(int P, int deg, int M, const float* means3D, const float*
                        const float* pose_points, float* dL_dpose, cudaStream_t stream, bool debug);
 int launch_masked_l1(const float* pred, const float* target, const uint8_t* mask, int C, size_t HW, float* loss,
                      float* grad, cudaStream_t stream);
+int launch_hier_cross_entropy(const float* sem, const int* labels, int L, const int* level_begin, const float* level_scale,
+                              size_t HW, float* loss, float* grad, cudaStream_t stream);
 int launch_mark_visible(int P, const float* means3D, const float* view, const float* proj, bool* present,
                         cudaStream_t stream, bool debug);
 

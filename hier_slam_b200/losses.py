@@ -49,3 +49,46 @@ def masked_l1_sum(pred: torch.Tensor, target: torch.Tensor, mask: torch.Tensor |
     """sum over channels and masked pixels of |pred - target|  ==  torch.abs(target - pred)[mask_expanded].sum().
     pred / target: [C,H,W] float32 CUDA; mask: [H,W] or [1,H,W] bool (None = all pixels).  Gradient flows to pred."""
     return _MaskedL1Sum.apply(pred, target, mask)
+
+
+class _HierCE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, sem, labels, level_sizes, weights):
+        lib = _lib.load()
+        if not sem.is_cuda or sem.dtype != torch.float32 or sem.dim() != 3:
+            raise RuntimeError("sem must be a float32 CUDA tensor [S,H,W] (no CPU fallback)")
+        L = len(level_sizes)
+        if labels.dim() != 3 or labels.shape[0] < L or labels.shape[1:] != sem.shape[1:]:
+            raise RuntimeError("labels must be [levels,H,W] with at least len(level_sizes) levels")
+        if sum(level_sizes) > sem.shape[0] or L > 8:
+            raise RuntimeError("level_sizes must sum to at most S and have at most 8 levels")
+        s = sem.contiguous()
+        lab = labels[:L].to(torch.int32).contiguous()
+        HW = s[0].numel()
+        counts = (lab >= 0).reshape(L, -1).sum(1).clamp_min(1).tolist()     # torch's mean over the non-ignored pixels
+        begin = (ctypes.c_int * (L + 1))(*([0] + [sum(level_sizes[:i + 1]) for i in range(L)]))
+        scale = (ctypes.c_float * L)(*[float(weights[i]) / counts[i] for i in range(L)])
+        loss = torch.zeros((), dtype=torch.float32, device=s.device)
+        grad = torch.zeros_like(s) if sum(level_sizes) < s.shape[0] else torch.empty_like(s)
+        with torch.cuda.device(s.device):
+            stream = ctypes.c_void_p(torch.cuda.current_stream(s.device).cuda_stream)
+            _lib.check(lib.hs_hier_cross_entropy(ctypes.c_void_p(s.data_ptr()), ctypes.c_void_p(lab.data_ptr()), L, begin,
+                                                 scale, HW, ctypes.c_void_p(loss.data_ptr()),
+                                                 ctypes.c_void_p(grad.data_ptr()), stream), "hs_hier_cross_entropy")
+        ctx.save_for_backward(grad)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        return grad * g, None, None, None
+
+
+def hierarchical_cross_entropy(sem: torch.Tensor, labels: torch.Tensor, level_sizes, weights=None) -> torch.Tensor:
+    """sum_l weights[l] * CrossEntropyLoss()(sem[begin_l:end_l].permute(1,2,0).view(-1, n_l), labels[l].view(-1))
+    -- the inter-level loss of scripts/hierslam.py:955-1000 -- for the planar semantic map [S,H,W] the rasterizer
+    returns, in one kernel, with the gradient written in the same planar layout.  labels: [levels,H,W] integer
+    (negative = ignored, like torch's ignore_index)."""
+    level_sizes = [int(v) for v in level_sizes]
+    weights = [1.0] * len(level_sizes) if weights is None else [float(w) for w in weights]
+    return _HierCE.apply(sem, labels, level_sizes, weights)

@@ -120,6 +120,14 @@ int hs_backward(const hs_camera* cam, int P, int S, int num_rendered, const floa
 int hs_masked_l1(const float* pred, const float* target, const unsigned char* mask, int channels, size_t pixels,
                  float* loss, float* grad, void* stream);
 
+/* Extension: hierarchical cross-entropy of the tree-encoded semantic map (scripts/hierslam.py:955-1000).  sem[S,pixels]
+ * planar (the rasterizer's out_semantic); labels[levels,pixels] int32 (device; negative = ignored); level l owns the
+ * channels [level_begin[l], level_begin[l+1]) (HOST array of levels+1 ints); level_scale[l] (HOST) = weight_l / number of
+ * non-ignored pixels.  loss[0] (device, zeroed by the caller) += sum_l level_scale[l] * sum_p CE; grad[c,p] = d loss / d sem
+ * for every channel below level_begin[levels] (at most 8 levels). */
+int hs_hier_cross_entropy(const float* sem, const int* labels, int levels, const int* level_begin,
+                          const float* level_scale, size_t pixels, float* loss, float* grad, void* stream);
+
 /* present[P] (bool, device) = view-space z > 0.2 (reference: rasterizer_impl.cu:54-66). */
 int hs_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
                     unsigned char* present, void* stream);

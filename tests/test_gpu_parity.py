@@ -419,6 +419,29 @@ def test_masked_l1_sum_matches_boolean_indexing():
             assert torch.equal(x.grad, x2.grad)
 
 
+def test_hierarchical_cross_entropy_matches_torch():
+    """hier_slam_b200.losses.hierarchical_cross_entropy == the inter-level loss of scripts/hierslam.py:955-1000
+    (per level: permute + view + torch.nn.CrossEntropyLoss), value and gradient, incl. ignored labels."""
+    from hier_slam_b200.losses import hierarchical_cross_entropy
+    g = torch.Generator().manual_seed(43)
+    H, W, sizes = 61, 83, [4, 5, 5, 6, 6]
+    S = sum(sizes)
+    sem = (3 * torch.randn(S, H, W, generator=g)).cuda().requires_grad_(True)
+    sem2 = sem.detach().clone().requires_grad_(True)
+    labels = torch.stack([torch.randint(0, n, (H, W), generator=g) for n in sizes]).cuda()
+    labels[1, :7] = -100                                     # ignored rows in one level
+    a = hierarchical_cross_entropy(sem, labels, sizes, weights=[1.0, 1.0, 2.0, 1.0, 0.5])
+    ce = torch.nn.CrossEntropyLoss()
+    b, beg = 0.0, 0
+    for l, (n, w) in enumerate(zip(sizes, [1.0, 1.0, 2.0, 1.0, 0.5])):
+        b = b + w * ce(sem2[beg:beg + n].permute(1, 2, 0).reshape(-1, n), labels[l].reshape(-1).long())
+        beg += n
+    (1.7 * a).backward()
+    (1.7 * b).backward()
+    assert abs(float(a) - float(b)) <= 2e-5 * abs(float(b))
+    assert_grads_close(sem.grad, sem2.grad, "d loss / d sem", tol=2e-5)
+
+
 def test_full_size_properties_c2():
     """BASELINE.json config 2 at full size (1200x680, 300K Gaussians, S=26): properties that need no oracle."""
     C, Settings = new_impl()
