@@ -22,6 +22,9 @@
 #include "hs_common.cuh"
 #include <cuda_pipeline.h>
 
+#ifndef HS_BWD_OCC_S0
+#define HS_BWD_OCC_S0 3   // CTAs per SM the S = 0 instantiation (tracking, non-semantic maps) is compiled for: 85 registers, 605 -> 521 us at c2
+#endif
 #ifndef HS_BWD_U
 #define HS_BWD_U 2      // entries whose alpha is evaluated together (independent dependency chains per lane)
 #endif
@@ -62,7 +65,7 @@ __device__ __forceinline__ float tf32_lo(const float x) {
 //            bit-identical to T / d on d in [0.01, 1], T in (0, 1] (tools/micro/div_exact.cu: 2^33 pairs, 0 mismatches);
 //   !EXACT_T (every Hier-SLAM loss: no gradient reaches the median depth): T' = T r, one multiply per entry (<= 1 ulp).
 template <int S, int NW, bool EXACT_T>
-__global__ void __launch_bounds__(32 * NW, (MmaCfg<S>::B_IN_REGS ? (16 / NW) : 1)) blend_backward_mma_kernel(
+__global__ void __launch_bounds__(32 * NW, (MmaCfg<S>::B_IN_REGS ? (S == 0 ? HS_BWD_OCC_S0 : 2) * (8 / NW) : 1)) blend_backward_mma_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H, int grid_x,
     const float* __restrict__ bg_color, const float2* __restrict__ means2D, const float4* __restrict__ conic_opacity,
     const float* __restrict__ colors, const float* __restrict__ depths, const float* __restrict__ final_Ts,
