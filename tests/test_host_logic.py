@@ -75,3 +75,25 @@ def test_get_higher_msb_matches_documented_key_widths():
     assert 32 + O.get_higher_msb(75 * 43) == 44
     assert 32 + O.get_higher_msb(40 * 30) == 43
     assert 32 + O.get_higher_msb(20 * 15) == 41
+
+
+def test_padded_channel_counts():
+    """Channel counts without their own kernel instantiation map to the next larger one (zero-padded); more than the
+    largest instantiation is an error, not a fallback."""
+    from hier_slam_b200 import _C
+    assert [_C._padded_channels(s) for s in (1, 5, 16, 17, 26, 27, 74, 75, 102)] == [16, 16, 16, 26, 26, 74, 74, 102, 102]
+    with pytest.raises(RuntimeError, match="not instantiated"):
+        _C._padded_channels(103)
+
+
+def test_flat_params_cpu_has_no_gradient_sinks():
+    """FlatParams on CPU tensors (the gloo tests) must not register CUDA gradient sinks; leaves alias the flat buffers."""
+    import torch
+    from hier_slam_b200 import _C
+    from hier_slam_b200.mapping import FlatParams, keyframes_of_rank
+    before = len(_C._grad_sinks)
+    p = FlatParams({"a": torch.ones(5, 3), "b": torch.zeros(7)})
+    assert len(_C._grad_sinks) == before
+    p.leaves["a"].grad.fill_(2.0)
+    assert float(p.flat_grad[:15].sum()) == 30.0 and p.flat.numel() % 64 == 0
+    assert keyframes_of_rank(8, 1, 4) == [1, 5]
