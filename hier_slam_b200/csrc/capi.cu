@@ -347,6 +347,19 @@ int hs_hier_cross_entropy(const float* sem, const int* labels, int levels, const
                                      (cudaStream_t)stream_);
 }
 
+int hs_leaf_cross_entropy(const float* sem, const int* labels, const float* weight, const float* bias, int channels,
+                          int classes, size_t pixels, float scale, float* loss, float* lse, float* grad_sem,
+                          int flags, float* grad_weight, float* grad_bias, void* stream_) {
+    if (sem == nullptr || labels == nullptr || weight == nullptr || loss == nullptr || lse == nullptr ||
+        grad_sem == nullptr) {
+        set_error("hs_leaf_cross_entropy: NULL argument");
+        return 1;
+    }
+    return launch_leaf_cross_entropy(sem, labels, weight, bias, channels, classes, pixels, scale, loss, lse, grad_sem,
+                                     flags & HS_LEAF_ACCUMULATE, grad_weight, grad_bias, (flags & HS_LEAF_TF32) != 0,
+                                     (cudaStream_t)stream_);
+}
+
 int hs_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
                     unsigned char* present, void* stream_) {
     return launch_mark_visible(P, means3D, viewmatrix, projmatrix, (bool*)present, (cudaStream_t)stream_, false);

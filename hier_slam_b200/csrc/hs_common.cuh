@@ -134,6 +134,9 @@ int launch_masked_l1(const float* pred, const float* target, const uint8_t* mask
                      float* grad, cudaStream_t stream);
 int launch_hier_cross_entropy(const float* sem, const int* labels, int L, const int* level_begin, const float* level_scale,
                               size_t HW, float* loss, float* grad, cudaStream_t stream);
+int launch_leaf_cross_entropy(const float* sem, const int* labels, const float* weight, const float* bias, int S, int L,
+                              size_t HW, float scale, float* loss, float* lse, float* grad_sem, int accumulate,
+                              float* grad_weight, float* grad_bias, int single_tf32, cudaStream_t stream);
 int launch_mark_visible(int P, const float* means3D, const float* view, const float* proj, bool* present,
                         cudaStream_t stream, bool debug);
 

@@ -1,4 +1,5 @@
-"""Loss helpers next to the rasterizer (first step): `masked_l1_sum`.
+"""Loss kernels next to the rasterizer: `masked_l1_sum`, `hierarchical_cross_entropy`,
+`leaf_cross_entropy`, `tree_semantic_loss`.
 
 Hier-SLAM's tracking and mapping losses are `torch.abs(gt - x)[mask].sum()` (scripts/hierslam.py:780-796); the boolean
 indexing costs a nonzero() with a host sync in the forward and an index_put_ in the backward.  `masked_l1_sum` computes
@@ -6,6 +7,7 @@ the same value and the same gradient with one kernel over the image (hs_masked_l
 from __future__ import annotations
 
 import ctypes
+import os
 
 import torch
 
@@ -92,3 +94,128 @@ def hierarchical_cross_entropy(sem: torch.Tensor, labels: torch.Tensor, level_si
     level_sizes = [int(v) for v in level_sizes]
     weights = [1.0] * len(level_sizes) if weights is None else [float(w) for w in weights]
     return _HierCE.apply(sem, labels, level_sizes, weights)
+
+
+# HS_LEAF_TF32=1: one TF32 product per contraction in the leaf loss (torch's default convolution precision) instead of the
+# fp32-accurate 3xTF32 split
+LEAF_TF32 = os.environ.get("HS_LEAF_TF32", "0") == "1"
+
+
+def _stream(dev):
+    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _run_hier(lib, s, lab, level_sizes, weights, loss, grad):
+    """hs_hier_cross_entropy on contiguous sem [S,H,W] / int32 labels [L,H,W]; writes grad[: sum(level_sizes)]."""
+    L = len(level_sizes)
+    counts = (lab >= 0).reshape(L, -1).sum(1).clamp_min(1).tolist()     # torch's mean over the non-ignored pixels
+    begin = (ctypes.c_int * (L + 1))(*([0] + [sum(level_sizes[:i + 1]) for i in range(L)]))
+    scale = (ctypes.c_float * L)(*[float(weights[i]) / counts[i] for i in range(L)])
+    _lib.check(lib.hs_hier_cross_entropy(ctypes.c_void_p(s.data_ptr()), ctypes.c_void_p(lab.data_ptr()), L, begin, scale,
+                                         s[0].numel(), ctypes.c_void_p(loss.data_ptr()), ctypes.c_void_p(grad.data_ptr()),
+                                         _stream(s.device)), "hs_hier_cross_entropy")
+
+
+def _run_leaf(lib, s, lab, w2, bias, loss_weight, num_valid, loss, grad, accumulate, want_wgrad):
+    """hs_leaf_cross_entropy; returns (grad_weight [L,S] or None, grad_bias [L] or None)."""
+    L, S = w2.shape
+    if S != s.shape[0]:
+        raise RuntimeError(f"weight has {S} input channels, the semantic map has {s.shape[0]}")
+    if not 1 <= S <= 79:
+        raise RuntimeError("leaf_cross_entropy supports 1 <= S <= 79 semantic channels")
+    if num_valid is None:
+        num_valid = int(((lab >= 0) & (lab < L)).sum())                 # host sync; pass num_valid to avoid it
+    HW = s[0].numel()
+    lse = torch.empty(HW, dtype=torch.float32, device=s.device)
+    gw = torch.zeros(L, S, dtype=torch.float32, device=s.device) if want_wgrad else None
+    gb = torch.zeros(L, dtype=torch.float32, device=s.device) if (want_wgrad and bias is not None) else None
+    p = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
+    _lib.check(lib.hs_leaf_cross_entropy(p(s), p(lab), p(w2), p(bias), int(S), int(L), HW,
+                                         float(loss_weight) / max(int(num_valid), 1), p(loss), p(lse), p(grad),
+                                         (1 if accumulate else 0) | (2 if LEAF_TF32 else 0), p(gw), p(gb),
+                                         _stream(s.device)),
+               "hs_leaf_cross_entropy")
+    return gw, gb
+
+
+def _leaf_args(sem, weight, bias):
+    if not sem.is_cuda or sem.dtype != torch.float32 or sem.dim() != 3:
+        raise RuntimeError("sem must be a float32 CUDA tensor [S,H,W] (no CPU fallback)")
+    if weight.dim() not in (2, 4) or weight.dtype != torch.float32 or weight.device != sem.device:
+        raise RuntimeError("weight must be the float32 Conv2d weight [classes,S,1,1] (or [classes,S]) on sem's device")
+    w2 = weight.detach().reshape(weight.shape[0], -1).contiguous()
+    b = None if bias is None else bias.detach().to(torch.float32).contiguous()
+    return sem.detach().contiguous(), w2, b
+
+
+class _LeafCE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, sem, labels, weight, bias, loss_weight, num_valid):
+        lib = _lib.load()
+        s, w2, b = _leaf_args(sem, weight, bias)
+        if labels.shape != sem.shape[1:]:
+            raise RuntimeError("labels must be [H,W]")
+        lab = labels.to(torch.int32).contiguous()
+        loss = torch.zeros((), dtype=torch.float32, device=s.device)
+        grad = torch.empty_like(s)
+        with torch.cuda.device(s.device):
+            gw, gb = _run_leaf(lib, s, lab, w2, b, loss_weight, num_valid, loss, grad, False,
+                               ctx.needs_input_grad[2] or (bias is not None and ctx.needs_input_grad[3]))
+        ctx.wshape = weight.shape
+        ctx.save_for_backward(grad, gw, gb)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        grad, gw, gb = ctx.saved_tensors
+        return (grad * g, None, None if gw is None else (gw * g).view(ctx.wshape), None if gb is None else gb * g,
+                None, None)
+
+
+def leaf_cross_entropy(sem: torch.Tensor, labels: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None = None,
+                       loss_weight: float = 1.0, num_valid: int | None = None) -> torch.Tensor:
+    """loss_weight * CrossEntropyLoss()(conv2d(sem[None], weight, bias)[0].view(classes, -1).T, labels.view(-1)) -- the
+    leaf ("cross-level") loss of scripts/hierslam.py:975-984 / :1009-1016 with MLP_func = Conv2d(S, classes, 1) -- in two
+    kernels that never materialise the [classes,H,W] logits.  Gradients flow to sem, weight and bias.
+    labels: [H,W] integer (negative = ignored); num_valid: number of non-ignored pixels if the caller knows it (saves
+    a host sync)."""
+    return _LeafCE.apply(sem, labels, weight, bias, float(loss_weight), num_valid)
+
+
+class _TreeLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, sem, labels, weight, bias, level_sizes, level_weight, leaf_weight, num_valid):
+        lib = _lib.load()
+        s, w2, b = _leaf_args(sem, weight, bias)
+        nl = len(level_sizes)
+        if labels.dim() != 3 or labels.shape[0] != nl + 1 or labels.shape[1:] != sem.shape[1:]:
+            raise RuntimeError("labels must be [len(level_sizes) + 1, H, W]: one map per tree level, then the leaf map")
+        if sum(level_sizes) > s.shape[0] or nl > 8:
+            raise RuntimeError("level_sizes must sum to at most S and have at most 8 levels")
+        lab = labels.to(torch.int32).contiguous()
+        loss = torch.zeros((), dtype=torch.float32, device=s.device)
+        grad = torch.zeros_like(s) if sum(level_sizes) < s.shape[0] else torch.empty_like(s)
+        with torch.cuda.device(s.device):
+            _run_hier(lib, s, lab[:nl], level_sizes, [level_weight] * nl, loss, grad)
+            gw, gb = _run_leaf(lib, s, lab[nl], w2, b, leaf_weight, num_valid, loss, grad, True,
+                               ctx.needs_input_grad[2] or (bias is not None and ctx.needs_input_grad[3]))
+        ctx.wshape = weight.shape
+        ctx.save_for_backward(grad, gw, gb)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        grad, gw, gb = ctx.saved_tensors
+        return (grad * g, None, None if gw is None else (gw * g).view(ctx.wshape), None if gb is None else gb * g,
+                None, None, None, None)
+
+
+def tree_semantic_loss(sem: torch.Tensor, labels: torch.Tensor, level_sizes, weight: torch.Tensor,
+                       bias: torch.Tensor | None = None, level_weight: float = 1.0, leaf_weight: float = 5.0,
+                       num_valid: int | None = None) -> torch.Tensor:
+    """Hier-SLAM's whole semantic mapping loss (scripts/hierslam.py:955-984): level_weight * sum over the tree levels of
+    the per-level cross-entropy + leaf_weight * the leaf cross-entropy behind the 1x1 convolution (weight_sem = [1, 5]).
+    labels: [levels + 1, H, W] like curr_data['semantic_label_gt'] (last map = leaf labels).  One gradient image is
+    produced: the leaf kernels accumulate onto what the level kernel wrote."""
+    return _TreeLoss.apply(sem, labels, weight, bias, [int(v) for v in level_sizes], float(level_weight),
+                           float(leaf_weight), num_valid)

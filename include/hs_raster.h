@@ -128,6 +128,22 @@ int hs_masked_l1(const float* pred, const float* target, const unsigned char* ma
 int hs_hier_cross_entropy(const float* sem, const int* labels, int levels, const int* level_begin,
                           const float* level_scale, size_t pixels, float* loss, float* grad, void* stream);
 
+/* Extension: leaf-level loss of the tree encoding -- a 1x1 convolution from the S rendered channels to the leaf classes
+ * followed by cross-entropy (scripts/hierslam.py:975-984, :1009-1016; MLP_func = Conv2d(S, classes, 1), :1756) -- with
+ * all three gradients, without ever materialising the [classes,pixels] logits.  sem[S,pixels] planar; labels[pixels]
+ * int32 (device; negative or >= classes = ignored); weight[classes,S] row-major (the Conv2d weight); bias[classes] or
+ * NULL; scale (HOST) = loss weight / number of non-ignored pixels.  loss[0] (device, zeroed by the caller) += scale *
+ * sum_p CE; lse[pixels] (device scratch) receives the per-pixel logsumexp; grad_sem[S,pixels] = (or += with
+ * HS_LEAF_ACCUMULATE) d loss / d sem; grad_weight[classes,S] and grad_bias[classes] (device, zeroed by the caller;
+ * grad_weight NULL = skip both) += d loss / d weight, d loss / d bias.  1 <= S <= 79.  The contractions run on the
+ * tensor cores as 3xTF32 (fp32-accurate); HS_LEAF_TF32 selects a single TF32 product (what torch's convolution does
+ * with its default allow_tf32). */
+#define HS_LEAF_ACCUMULATE 1
+#define HS_LEAF_TF32 2
+int hs_leaf_cross_entropy(const float* sem, const int* labels, const float* weight, const float* bias, int channels,
+                          int classes, size_t pixels, float scale, float* loss, float* lse, float* grad_sem,
+                          int flags, float* grad_weight, float* grad_bias, void* stream);
+
 /* present[P] (bool, device) = view-space z > 0.2 (reference: rasterizer_impl.cu:54-66). */
 int hs_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
                     unsigned char* present, void* stream);

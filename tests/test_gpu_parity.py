@@ -442,6 +442,74 @@ def test_hierarchical_cross_entropy_matches_torch():
     assert_grads_close(sem.grad, sem2.grad, "d loss / d sem", tol=2e-5)
 
 
+def _torch_leaf_loss(sem, labels, weight, bias):
+    """the reference's leaf loss (scripts/hierslam.py:975-984): MLP_func = Conv2d(S, classes, 1), then CrossEntropyLoss"""
+    logits = torch.nn.functional.conv2d(sem.unsqueeze(0), weight, bias)
+    logits = logits.squeeze(0).view(logits.shape[1], -1).permute(1, 0)
+    return torch.nn.CrossEntropyLoss()(logits, labels.view(-1).long())
+
+
+@pytest.fixture
+def float32_convolutions():
+    """cuDNN's default allow_tf32 = True makes torch's convolution (forward AND backward) only ~1e-3 accurate; the torch
+    side of the leaf-loss comparisons must be a float32 reference."""
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32 = tf32
+
+
+@pytest.mark.parametrize("S,L,H,W,use_bias", [(26, 102, 61, 83, True), (16, 41, 37, 45, True), (26, 102, 16, 16, False),
+                                              (74, 550, 33, 47, True), (7, 5, 20, 13, True), (31, 130, 29, 31, True)])
+def test_leaf_cross_entropy_matches_torch(S, L, H, W, use_bias, float32_convolutions):
+    """hier_slam_b200.losses.leaf_cross_entropy == Conv2d(S, L, 1) + CrossEntropyLoss in torch (float32): value and the
+    gradients w.r.t. the semantic map, the convolution weight and its bias; ragged image sizes, ignored labels."""
+    from hier_slam_b200.losses import leaf_cross_entropy
+    g = torch.Generator().manual_seed(47 + S)
+    sem = (2 * torch.randn(S, H, W, generator=g)).cuda().requires_grad_(True)
+    weight = (0.5 * torch.randn(L, S, 1, 1, generator=g)).cuda().requires_grad_(True)
+    bias = torch.randn(L, generator=g).cuda().requires_grad_(True) if use_bias else None
+    labels = torch.randint(0, L, (H, W), generator=g).cuda()
+    labels[3, :9] = -100
+    ref_leaves = [t.detach().clone().requires_grad_(True) for t in (sem, weight)] + \
+                 ([bias.detach().clone().requires_grad_(True)] if use_bias else [None])
+    a = leaf_cross_entropy(sem, labels, weight, bias, loss_weight=5.0)
+    b = 5.0 * _torch_leaf_loss(ref_leaves[0], labels, ref_leaves[1], ref_leaves[2])
+    (1.3 * a).backward()
+    (1.3 * b).backward()
+    assert abs(float(a.detach()) - float(b.detach())) <= 2e-5 * abs(float(b.detach()))
+    assert_grads_close(sem.grad, ref_leaves[0].grad, "d loss / d sem", tol=2e-5)
+    assert_grads_close(weight.grad, ref_leaves[1].grad, "d loss / d weight", tol=2e-5)
+    if use_bias:
+        assert_grads_close(bias.grad, ref_leaves[2].grad, "d loss / d bias", tol=2e-5)
+
+
+def test_tree_semantic_loss_matches_torch(float32_convolutions):
+    """tree_semantic_loss == 1.0 * sum of the per-level CE + 5.0 * leaf CE behind the 1x1 conv (scripts/hierslam.py:955-984)"""
+    from hier_slam_b200.losses import tree_semantic_loss
+    g = torch.Generator().manual_seed(53)
+    H, W, sizes, L = 45, 70, [4, 5, 5, 6, 6], 102
+    S = sum(sizes)
+    sem = (2 * torch.randn(S, H, W, generator=g)).cuda().requires_grad_(True)
+    conv = torch.nn.Conv2d(S, L, kernel_size=1).cuda()
+    labels = torch.stack([torch.randint(0, n, (H, W), generator=g) for n in sizes + [L]]).cuda()
+    a = tree_semantic_loss(sem, labels, sizes, conv.weight, conv.bias)
+    a.backward()
+    got = [sem.grad.clone(), conv.weight.grad.clone(), conv.bias.grad.clone()]
+    sem.grad = None
+    conv.zero_grad()
+    ce = torch.nn.CrossEntropyLoss()
+    b, beg = 0.0, 0
+    for l, n in enumerate(sizes):
+        b = b + ce(sem[beg:beg + n].permute(1, 2, 0).reshape(-1, n), labels[l].reshape(-1).long())
+        beg += n
+    b = b + 5.0 * _torch_leaf_loss(sem, labels[-1], conv.weight, conv.bias)
+    b.backward()
+    assert abs(float(a.detach()) - float(b.detach())) <= 2e-5 * abs(float(b.detach()))
+    for x, y, what in zip(got, (sem.grad, conv.weight.grad, conv.bias.grad), ("sem", "weight", "bias")):
+        assert_grads_close(x, y, "d loss / d " + what, tol=2e-5)
+
+
 def test_full_size_properties_c2():
     """BASELINE.json config 2 at full size (1200x680, 300K Gaussians, S=26): properties that need no oracle."""
     C, Settings = new_impl()
