@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("HS_LIB", os.path.join(HERE, "libhsraster.so"))
 EXPORTED_SYMBOLS = [
     "hs_abi_version", "hs_last_error", "hs_supports_semantic_channels", "hs_geom_state_bytes",
     "hs_image_state_bytes", "hs_binning_state_bytes", "hs_forward_geometry", "hs_forward_render",
-    "hs_backward", "hs_mark_visible", "hs_masked_l1", "hs_hier_cross_entropy", "hs_leaf_cross_entropy",
+    "hs_backward", "hs_mark_visible", "hs_masked_l1", "hs_hier_cross_entropy", "hs_leaf_cross_entropy", "hs_l1_ssim",
     "hs_geom_state_layout", "hs_image_state_layout",
     "hs_binning_state_layout", "hs_profile_enable", "hs_profile_read", "hs_kernel_launch_count",
     "hs_library_call_count",
@@ -74,6 +74,8 @@ def load() -> ctypes.CDLL:
     lib.hs_hier_cross_entropy.restype = c_int
     lib.hs_leaf_cross_entropy.argtypes = [vp, vp, vp, vp, c_int, c_int, c_size_t, c_float, vp, vp, vp, c_int, vp, vp, vp]
     lib.hs_leaf_cross_entropy.restype = c_int
+    lib.hs_l1_ssim.argtypes = [vp, vp, c_int, c_int, c_int, POINTER(c_float), c_float, c_float, vp, vp, vp, vp]
+    lib.hs_l1_ssim.restype = c_int
     lib.hs_mark_visible.argtypes = [c_int, vp, vp, vp, vp, vp]
     lib.hs_mark_visible.restype = c_int
     lib.hs_geom_state_layout.argtypes = [c_int, POINTER(c_size_t)]

@@ -347,6 +347,16 @@ int hs_hier_cross_entropy(const float* sem, const int* labels, int levels, const
                                      (cudaStream_t)stream_);
 }
 
+int hs_l1_ssim(const float* pred, const float* target, int channels, int height, int width, const float* window11,
+               float l1_scale, float ssim_scale, float* loss, float* scratch, float* grad, void* stream_) {
+    if (pred == nullptr || target == nullptr || window11 == nullptr || loss == nullptr || scratch == nullptr) {
+        set_error("hs_l1_ssim: NULL argument");
+        return 1;
+    }
+    return launch_l1_ssim(pred, target, channels, height, width, window11, l1_scale, ssim_scale, loss, scratch, grad,
+                          (cudaStream_t)stream_);
+}
+
 int hs_leaf_cross_entropy(const float* sem, const int* labels, const float* weight, const float* bias, int channels,
                           int classes, size_t pixels, float scale, float* loss, float* lse, float* grad_sem,
                           int flags, float* grad_weight, float* grad_bias, void* stream_) {

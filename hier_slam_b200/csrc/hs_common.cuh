@@ -134,6 +134,8 @@ int launch_masked_l1(const float* pred, const float* target, const uint8_t* mask
                      float* grad, cudaStream_t stream);
 int launch_hier_cross_entropy(const float* sem, const int* labels, int L, const int* level_begin, const float* level_scale,
                               size_t HW, float* loss, float* grad, cudaStream_t stream);
+int launch_l1_ssim(const float* pred, const float* target, int C, int H, int W, const float* window11, float l1_scale,
+                   float ssim_scale, float* loss, float* scratch, float* grad, cudaStream_t stream);
 int launch_leaf_cross_entropy(const float* sem, const int* labels, const float* weight, const float* bias, int S, int L,
                               size_t HW, float scale, float* loss, float* lse, float* grad_sem, int accumulate,
                               float* grad_weight, float* grad_bias, int single_tf32, cudaStream_t stream);

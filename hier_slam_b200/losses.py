@@ -1,5 +1,5 @@
 """Loss kernels next to the rasterizer: `masked_l1_sum`, `hierarchical_cross_entropy`,
-`leaf_cross_entropy`, `tree_semantic_loss`.
+`leaf_cross_entropy`, `tree_semantic_loss`, `l1_ssim_loss`.
 
 Hier-SLAM's tracking and mapping losses are `torch.abs(gt - x)[mask].sum()` (scripts/hierslam.py:780-796); the boolean
 indexing costs a nonzero() with a host sync in the forward and an index_put_ in the backward.  `masked_l1_sum` computes
@@ -219,3 +219,51 @@ def tree_semantic_loss(sem: torch.Tensor, labels: torch.Tensor, level_sizes, wei
     produced: the leaf kernels accumulate onto what the level kernel wrote."""
     return _TreeLoss.apply(sem, labels, weight, bias, [int(v) for v in level_sizes], float(level_weight),
                            float(leaf_weight), num_valid)
+
+
+_WINDOW11 = None
+
+
+def _window11():
+    """the normalised 11-tap Gaussian (sigma 1.5) of utils/slam_external.py:55-57, rounded to float32 the same way"""
+    global _WINDOW11
+    if _WINDOW11 is None:
+        from math import exp
+        gauss = torch.tensor([exp(-(x - 5) ** 2 / float(2 * 1.5 ** 2)) for x in range(11)], dtype=torch.float32)
+        _WINDOW11 = (ctypes.c_float * 11)(*(gauss / gauss.sum()).tolist())
+    return _WINDOW11
+
+
+class _L1SSIM(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, target, l1_weight, ssim_weight):
+        lib = _lib.load()
+        if not pred.is_cuda:
+            raise RuntimeError("l1_ssim_loss is CUDA-only (no CPU fallback)")
+        if pred.dtype != torch.float32 or target.dtype != torch.float32 or pred.shape != target.shape or pred.dim() != 3:
+            raise RuntimeError("pred and target must be float32 tensors of the same shape [C,H,W]")
+        p, t = pred.detach().contiguous(), target.detach().contiguous()
+        C, H, W = p.shape
+        n = p.numel()
+        loss = torch.full((), float(ssim_weight), dtype=torch.float32, device=p.device)
+        scratch = torch.empty(3 * n, dtype=torch.float32, device=p.device)
+        grad = torch.empty_like(p)
+        with torch.cuda.device(p.device):
+            _lib.check(lib.hs_l1_ssim(ctypes.c_void_p(p.data_ptr()), ctypes.c_void_p(t.data_ptr()), C, H, W, _window11(),
+                                      float(l1_weight) / n, -float(ssim_weight) / n, ctypes.c_void_p(loss.data_ptr()),
+                                      ctypes.c_void_p(scratch.data_ptr()), ctypes.c_void_p(grad.data_ptr()),
+                                      _stream(p.device)), "hs_l1_ssim")
+        ctx.save_for_backward(grad)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        return grad * g, None, None, None
+
+
+def l1_ssim_loss(pred: torch.Tensor, target: torch.Tensor, l1_weight: float = 0.8, ssim_weight: float = 0.2) -> torch.Tensor:
+    """l1_weight * |pred - target|.mean() + ssim_weight * (1 - calc_ssim(pred, target)) -- the colour loss of mapping
+    (scripts/hierslam.py:936, utils/slam_external.py:55-97) -- value and gradient w.r.t. pred in two kernels instead of
+    ten depthwise 11x11 convolutions.  pred / target: [C,H,W] float32 CUDA."""
+    return _L1SSIM.apply(pred, target, float(l1_weight), float(ssim_weight))

@@ -128,6 +128,16 @@ int hs_masked_l1(const float* pred, const float* target, const unsigned char* ma
 int hs_hier_cross_entropy(const float* sem, const int* labels, int levels, const int* level_begin,
                           const float* level_scale, size_t pixels, float* loss, float* grad, void* stream);
 
+/* Extension: the colour loss of mapping, l1_weight * mean|pred - target| + ssim_weight * (1 - SSIM)
+ * (scripts/hierslam.py:936; SSIM of utils/slam_external.py:55-97: 11-tap Gaussian window, zero padding, c1 = 0.01^2,
+ * c2 = 0.03^2, mean over channels and pixels), and its gradient.  pred / target: [channels,height,width] planar (device);
+ * window11: the 11 normalised 1-D window taps (HOST); loss[0] (device, zeroed by the caller) += l1_scale * sum|pred -
+ * target| + ssim_scale * sum(ssim map) -- the caller passes l1_scale = l1_weight / n, ssim_scale = -ssim_weight / n and
+ * adds the constant ssim_weight; scratch: 3 * channels * height * width floats (device); grad[channels,height,width] =
+ * d loss / d pred (NULL = forward only). */
+int hs_l1_ssim(const float* pred, const float* target, int channels, int height, int width, const float* window11,
+               float l1_scale, float ssim_scale, float* loss, float* scratch, float* grad, void* stream);
+
 /* Extension: leaf-level loss of the tree encoding -- a 1x1 convolution from the S rendered channels to the leaf classes
  * followed by cross-entropy (scripts/hierslam.py:975-984, :1009-1016; MLP_func = Conv2d(S, classes, 1), :1756) -- with
  * all three gradients, without ever materialising the [classes,pixels] logits.  sem[S,pixels] planar; labels[pixels]

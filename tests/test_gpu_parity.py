@@ -510,6 +510,38 @@ def test_tree_semantic_loss_matches_torch(float32_convolutions):
         assert_grads_close(x, y, "d loss / d " + what, tol=2e-5)
 
 
+def _torch_ssim(img1, img2):
+    """SSIM as Hier-SLAM computes it (utils/slam_external.py:55-97): depthwise 11x11 Gaussian window (sigma 1.5), zero
+    padding, c1 = 0.01^2, c2 = 0.03^2, mean over everything -- restated with torch ops as the float32 reference."""
+    from math import exp
+    g1 = torch.tensor([exp(-(x - 5) ** 2 / float(2 * 1.5 ** 2)) for x in range(11)])
+    g1 = (g1 / g1.sum()).unsqueeze(1)
+    C = img1.shape[0]
+    win = g1.mm(g1.t()).float()[None, None].expand(C, 1, 11, 11).contiguous().to(img1.device)
+    f = lambda x: torch.nn.functional.conv2d(x, win, padding=5, groups=C)
+    mu1, mu2 = f(img1), f(img2)
+    s1, s2, s12 = f(img1 * img1) - mu1 * mu1, f(img2 * img2) - mu2 * mu2, f(img1 * img2) - mu1 * mu2
+    m = ((2 * mu1 * mu2 + 0.01 ** 2) * (2 * s12 + 0.03 ** 2)) / ((mu1 * mu1 + mu2 * mu2 + 0.01 ** 2) * (s1 + s2 + 0.03 ** 2))
+    return m.mean()
+
+
+@pytest.mark.parametrize("H,W", [(61, 83), (16, 32), (7, 5), (120, 167)])
+def test_l1_ssim_loss_matches_torch(H, W, float32_convolutions):
+    """hier_slam_b200.losses.l1_ssim_loss == 0.8 * |im - gt|.mean() + 0.2 * (1 - calc_ssim(im, gt)) (scripts/hierslam.py:936),
+    value and gradient, on ragged image sizes (tiles are 32x16) and sizes smaller than the window."""
+    from hier_slam_b200.losses import l1_ssim_loss
+    g = torch.Generator().manual_seed(59 + H)
+    gt = torch.rand(3, H, W, generator=g).cuda()
+    im = (gt + 0.2 * torch.randn(3, H, W, generator=g).cuda()).clamp(0, 1).requires_grad_(True)
+    im2 = im.detach().clone().requires_grad_(True)
+    a = l1_ssim_loss(im, gt)
+    b = 0.8 * torch.abs(im2 - gt).mean() + 0.2 * (1.0 - _torch_ssim(im2, gt))
+    (1.5 * a).backward()
+    (1.5 * b).backward()
+    assert abs(float(a.detach()) - float(b.detach())) <= 1e-5 * abs(float(b.detach()))
+    assert_grads_close(im.grad, im2.grad, "d loss / d im", tol=1e-5)
+
+
 def test_full_size_properties_c2():
     """BASELINE.json config 2 at full size (1200x680, 300K Gaussians, S=26): properties that need no oracle."""
     C, Settings = new_impl()
