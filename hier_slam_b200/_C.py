@@ -41,7 +41,15 @@ def register_grad_sink(param: torch.Tensor, grad: torch.Tensor) -> None:
     if not (param.is_cuda and grad.is_cuda and grad.dtype == torch.float32 and grad.is_contiguous()
             and grad.shape == param.shape):
         raise RuntimeError("gradient sink must be a contiguous float32 CUDA tensor of the parameter's shape")
+    for k in [k for k, v in _grad_sinks.items() if v[0]() is None]:     # parameters that are gone release their buffers
+        del _grad_sinks[k]
     _grad_sinks[param.data_ptr()] = (weakref.ref(param), grad)
+
+
+def unregister_grad_sink(param: torch.Tensor) -> None:
+    hit = _grad_sinks.get(param.data_ptr())
+    if hit is not None and hit[0]() is param:
+        del _grad_sinks[param.data_ptr()]
 
 
 def clear_grad_sinks() -> None:

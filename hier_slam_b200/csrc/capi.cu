@@ -347,6 +347,40 @@ int hs_hier_cross_entropy(const float* sem, const int* labels, int levels, const
                                      (cudaStream_t)stream_);
 }
 
+int hs_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, int segments,
+                 const unsigned long long* segment_end, const double* segment_lr, double beta1, double beta2, double eps,
+                 int step, void* stream_) {
+    if (param == nullptr || grad == nullptr || exp_avg == nullptr || exp_avg_sq == nullptr || segment_end == nullptr ||
+        segment_lr == nullptr) {
+        set_error("hs_adam_step: NULL argument");
+        return 1;
+    }
+    return launch_adam_flat(param, grad, exp_avg, exp_avg_sq, n, segments, segment_end, segment_lr, beta1, beta2, eps, step,
+                            (cudaStream_t)stream_);
+}
+
+size_t hs_compact_scratch_bytes(int P) { return compact_scratch_bytes(P); }
+
+int hs_compact_plan(const unsigned char* keep, int P, void* scratch, void* stream_) {
+    if (P > 0 && (keep == nullptr || scratch == nullptr)) {
+        set_error("hs_compact_plan: NULL argument");
+        return 1;
+    }
+    return launch_compact_plan(keep, P, (unsigned*)scratch, (cudaStream_t)stream_);
+}
+
+int hs_compact_gather(const float* src, float* dst, const void* scratch, int P, int rows, int segments,
+                      const unsigned long long* src_offset, const unsigned long long* dst_offset, const int* width,
+                      void* stream_) {
+    if (rows > 0 && (src == nullptr || dst == nullptr || scratch == nullptr || src_offset == nullptr ||
+                     dst_offset == nullptr || width == nullptr)) {
+        set_error("hs_compact_gather: NULL argument");
+        return 1;
+    }
+    return launch_compact_gather(src, dst, (const unsigned*)scratch, P, rows, segments, src_offset, dst_offset, width,
+                                 (cudaStream_t)stream_);
+}
+
 int hs_l1_ssim(const float* pred, const float* target, int channels, int height, int width, const float* window11,
                float l1_scale, float ssim_scale, float* loss, float* scratch, float* grad, void* stream_) {
     if (pred == nullptr || target == nullptr || window11 == nullptr || loss == nullptr || scratch == nullptr) {

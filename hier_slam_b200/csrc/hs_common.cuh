@@ -8,6 +8,7 @@
 #define HS_TILE_X 16          // reference: cuda_rasterizer/config.h:16  (BLOCK_X)
 #define HS_TILE_Y 16          // reference: cuda_rasterizer/config.h:17  (BLOCK_Y)
 #define HS_TILE_PIX 256
+#define HS_MAX_SEGMENTS 16     // parameter tensors in one flat buffer (hs_adam_step, hs_compact_gather)
 #define HS_MAX_LEVELS 8        // levels of the hierarchical semantic encoding (hs_hier_cross_entropy)
 #define HS_ALIGN 256          // every array inside an opaque state buffer is 256-B aligned
 #define HS_CTR_STRIDE 32          // per-tile counters sit 128 B apart: L2 atomics serialise per line, not per word
@@ -134,6 +135,14 @@ int launch_masked_l1(const float* pred, const float* target, const uint8_t* mask
                      float* grad, cudaStream_t stream);
 int launch_hier_cross_entropy(const float* sem, const int* labels, int L, const int* level_begin, const float* level_scale,
                               size_t HW, float* loss, float* grad, cudaStream_t stream);
+int launch_adam_flat(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, int n_seg,
+                     const unsigned long long* seg_end, const double* seg_lr, double beta1, double beta2, double eps, int step,
+                     cudaStream_t stream);
+size_t compact_scratch_bytes(int P);
+int launch_compact_plan(const uint8_t* keep, int P, unsigned* scratch, cudaStream_t stream);
+int launch_compact_gather(const float* src, float* dst, const unsigned* scratch, int P, int rows, int n_seg,
+                          const unsigned long long* src_off, const unsigned long long* dst_off, const int* width,
+                          cudaStream_t stream);
 int launch_l1_ssim(const float* pred, const float* target, int C, int H, int W, const float* window11, float l1_scale,
                    float ssim_scale, float* loss, float* scratch, float* grad, cudaStream_t stream);
 int launch_leaf_cross_entropy(const float* sem, const int* labels, const float* weight, const float* bias, int S, int L,

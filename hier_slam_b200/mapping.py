@@ -22,30 +22,55 @@ class FlatParams:
     """Named fp32 leaves carved out of one flat buffer, with gradients carved out of one flat gradient buffer."""
 
     def __init__(self, tensors: Dict[str, torch.Tensor], direct_grads: bool = True):
-        self.names: List[str] = list(tensors)
-        self.shapes = {k: tuple(v.shape) for k, v in tensors.items()}
-        sizes = [v.numel() for v in tensors.values()]
+        dev = next(iter(tensors.values())).device
+        self._allocate({k: tuple(v.shape) for k, v in tensors.items()}, dev, direct_grads)
+        for k, v in tensors.items():
+            o, n = self.offsets[k], v.numel()
+            self.flat[o:o + n].copy_(v.detach().reshape(-1).float())
+
+    @classmethod
+    def empty(cls, shapes: Dict[str, tuple], device, direct_grads: bool = True) -> "FlatParams":
+        """Zero-initialised buffers and leaves for the given shapes (used by pruning: hier_slam_b200.optim)."""
+        self = cls.__new__(cls)
+        self._allocate({k: tuple(v) for k, v in shapes.items()}, torch.device(device), direct_grads)
+        return self
+
+    def _allocate(self, shapes: Dict[str, tuple], dev, direct_grads: bool) -> None:
+        self.names: List[str] = list(shapes)
+        self.shapes = dict(shapes)
+        self.direct_grads = direct_grads
+        sizes = [int(torch.Size(shapes[k]).numel()) for k in self.names]
         # 64-float (256-B) aligned segments so every view can be consumed with vector loads
         self.offsets = {}
         off = 0
         for k, n in zip(self.names, sizes):
             self.offsets[k] = off
             off += (n + 63) // 64 * 64
-        dev = next(iter(tensors.values())).device
         self.flat = torch.zeros(off, dtype=torch.float32, device=dev)
         self.flat_grad = torch.zeros(off, dtype=torch.float32, device=dev)
         self.leaves: Dict[str, torch.Tensor] = {}
-        for k, v in tensors.items():
-            o, n = self.offsets[k], v.numel()
-            self.flat[o:o + n].copy_(v.detach().reshape(-1).float())
+        for k, n in zip(self.names, sizes):
+            o = self.offsets[k]
             leaf = self.flat[o:o + n].view(self.shapes[k]).requires_grad_(True)
             leaf.grad = self.flat_grad[o:o + n].view(self.shapes[k])
             self.leaves[k] = leaf
-            if direct_grads and leaf.is_cuda:
+            if direct_grads and leaf.is_cuda and n > 0:
                 # the rasterizer's backward accumulates dL/dcolors and dL/dsemantics straight into this buffer when a
                 # leaf is handed to it unchanged (no autograd accumulate kernel, no [P, 3+S] zero fill per call)
                 from . import _C
                 _C.register_grad_sink(leaf, leaf.grad)
+
+    def release(self) -> None:
+        """Drop the gradient-sink registrations of the leaves (a replaced parameter set must not keep its buffers alive)."""
+        if self.direct_grads:
+            from . import _C
+            for leaf in self.leaves.values():
+                if leaf.is_cuda:
+                    _C.unregister_grad_sink(leaf)
+
+    def segment_ends(self) -> List[int]:
+        """exclusive end (in floats, padding included) of every tensor's segment of the flat buffers, in name order"""
+        return [self.offsets[k] for k in self.names[1:]] + [self.flat.numel()]
 
     def zero_grad(self) -> None:
         self.flat_grad.zero_()

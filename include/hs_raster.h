@@ -128,6 +128,27 @@ int hs_masked_l1(const float* pred, const float* target, const unsigned char* ma
 int hs_hier_cross_entropy(const float* sem, const int* labels, int levels, const int* level_begin,
                           const float* level_scale, size_t pixels, float* loss, float* grad, void* stream);
 
+/* Extension (parameter maintenance): torch.optim.Adam's update (scripts/hierslam.py:411-417;
+ * torch/optim/adam.py::_multi_tensor_adam, no weight decay / amsgrad) for every parameter tensor in ONE pass over flat
+ * buffers.  param / grad / exp_avg / exp_avg_sq: n floats each (device, n a multiple of 4); segment s covers the floats
+ * [segment_end[s-1], segment_end[s]) (HOST arrays, ends ascending and multiples of 4, at most 16 segments) and has the
+ * learning rate segment_lr[s]; step = the 1-based step count (bias correction).  Learning rates, betas and eps are
+ * doubles because torch derives its float scalars (1 - beta, lr / bias_correction, ...) from Python doubles. */
+int hs_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, int segments,
+                 const unsigned long long* segment_end, const double* segment_lr, double beta1, double beta2, double eps,
+                 int step, void* stream);
+
+/* Extension: Gaussian pruning (utils/slam_external.py:142-164 remove_points: `tensor[to_keep]` on every parameter and both
+ * Adam moments).  hs_compact_plan turns keep[P] (device bytes, non-zero = keep) into an ordered source-row list inside
+ * scratch (hs_compact_scratch_bytes(P) bytes, device); afterwards the unsigned at scratch[ceil(P/1024)] is the number of
+ * kept rows.  hs_compact_gather copies, for every segment s (rows of width[s] floats starting at src_offset[s] floats in
+ * src), the kept rows in their original order to dst + dst_offset[s].  Bit-exact, order-preserving. */
+size_t hs_compact_scratch_bytes(int P);
+int hs_compact_plan(const unsigned char* keep, int P, void* scratch, void* stream);
+int hs_compact_gather(const float* src, float* dst, const void* scratch, int P, int rows, int segments,
+                      const unsigned long long* src_offset, const unsigned long long* dst_offset, const int* width,
+                      void* stream);
+
 /* Extension: the colour loss of mapping, l1_weight * mean|pred - target| + ssim_weight * (1 - SSIM)
  * (scripts/hierslam.py:936; SSIM of utils/slam_external.py:55-97: 11-tap Gaussian window, zero padding, c1 = 0.01^2,
  * c2 = 0.03^2, mean over channels and pixels), and its gradient.  pred / target: [channels,height,width] planar (device);

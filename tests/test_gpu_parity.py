@@ -542,6 +542,72 @@ def test_l1_ssim_loss_matches_torch(H, W, float32_convolutions):
     assert_grads_close(im.grad, im2.grad, "d loss / d im", tol=1e-5)
 
 
+def test_flat_adam_matches_torch_adam():
+    """hier_slam_b200.optim.FlatAdam == torch.optim.Adam with Hier-SLAM's parameter groups (scripts/hierslam.py:411-417:
+    one group per tensor, per-name learning rates incl. 0, eps = 1e-15): parameters and both moments after 6 steps."""
+    from hier_slam_b200.mapping import FlatParams
+    from hier_slam_b200.optim import FlatAdam
+    g = torch.Generator().manual_seed(61)
+    P = 5003
+    shapes = {"means3D": (P, 3), "rgb_colors": (P, 3), "unnorm_rotations": (P, 4), "logit_opacities": (P, 1),
+              "log_scales": (P, 1), "semantic": (P, 26)}
+    lrs = {"means3D": 1e-4, "rgb_colors": 2.5e-3, "unnorm_rotations": 1e-3, "logit_opacities": 5e-2, "log_scales": 0.0,
+           "semantic": 2.5e-3}
+    init = {k: torch.randn(*v, generator=g).cuda() for k, v in shapes.items()}
+    fp = FlatParams({k: v.clone() for k, v in init.items()})
+    ours = FlatAdam(fp, lrs, eps=1e-15)
+    ref_params = {k: torch.nn.Parameter(v.clone()) for k, v in init.items()}
+    ref = torch.optim.Adam([{"params": [v], "name": k, "lr": lrs[k]} for k, v in ref_params.items()], lr=0.0, eps=1e-15)
+    for it in range(6):
+        ours.zero_grad()
+        ref.zero_grad()
+        for k in shapes:
+            gr = (10.0 ** (it - 3)) * torch.randn(*shapes[k], generator=g).cuda()
+            if it == 2 and k == "semantic":
+                gr.zero_()                                  # an all-zero gradient step
+            fp.leaves[k].grad.copy_(gr)
+            ref_params[k].grad = gr.clone()
+        ours.step()
+        ref.step()
+    worst = 0.0
+    for k in shapes:
+        st = ref.state[ref_params[k]]
+        m, v = ours.state(k)
+        for a, b, what in ((fp.leaves[k].detach(), ref_params[k].detach(), "param"), (m, st["exp_avg"], "exp_avg"),
+                           (v, st["exp_avg_sq"], "exp_avg_sq")):
+            assert torch.allclose(a, b, rtol=2e-6, atol=1e-12), f"{k} {what}: max abs diff {float((a - b).abs().max()):.3e}"
+            worst = max(worst, float(((a - b).abs() / b.abs().clamp_min(1e-30)).max()))
+    assert worst < 1e-4
+    assert torch.equal(fp.leaves["log_scales"].detach(), init["log_scales"])     # lr = 0 leaves the parameter alone
+
+
+def test_flat_adam_prune_matches_boolean_indexing():
+    """FlatAdam.prune == remove_points (utils/slam_external.py:142-164): tensor[to_keep] on every parameter and moment."""
+    from hier_slam_b200.mapping import FlatParams
+    from hier_slam_b200.optim import FlatAdam
+    g = torch.Generator().manual_seed(67)
+    for P in (1, 1023, 1024, 1025, 70001):
+        shapes = {"means3D": (P, 3), "unnorm_rotations": (P, 4), "logit_opacities": (P, 1), "semantic": (P, 26)}
+        init = {k: torch.randn(*v, generator=g).cuda() for k, v in shapes.items()}
+        fp = FlatParams({k: v.clone() for k, v in init.items()})
+        opt = FlatAdam(fp, {k: 1e-3 for k in shapes})
+        for k in shapes:
+            fp.leaves[k].grad.copy_(torch.randn(*shapes[k], generator=g).cuda())
+        opt.step()
+        before = {k: (fp.leaves[k].detach().clone(),) + tuple(t.clone() for t in opt.state(k)) for k in shapes}
+        for keep in ((torch.rand(P, generator=g) < 0.7).cuda(), torch.zeros(P, dtype=torch.bool).cuda(),
+                     torch.ones(P, dtype=torch.bool).cuda()):
+            o2 = FlatAdam(FlatParams({k: before[k][0].clone() for k in shapes}), {k: 1e-3 for k in shapes})
+            o2.exp_avg.copy_(opt.exp_avg)
+            o2.exp_avg_sq.copy_(opt.exp_avg_sq)
+            new = o2.prune(keep)
+            for k in shapes:
+                m, v = o2.state(k)
+                assert torch.equal(new.leaves[k].detach(), before[k][0][keep])
+                assert torch.equal(m, before[k][1][keep]) and torch.equal(v, before[k][2][keep])
+                assert new.leaves[k].grad is not None and new.leaves[k].grad.shape == new.leaves[k].shape
+
+
 def test_full_size_properties_c2():
     """BASELINE.json config 2 at full size (1200x680, 300K Gaussians, S=26): properties that need no oracle."""
     C, Settings = new_impl()

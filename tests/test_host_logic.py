@@ -97,3 +97,28 @@ def test_flat_params_cpu_has_no_gradient_sinks():
     p.leaves["a"].grad.fill_(2.0)
     assert float(p.flat_grad[:15].sum()) == 30.0 and p.flat.numel() % 64 == 0
     assert keyframes_of_rank(8, 1, 4) == [1, 5]
+
+
+def test_flat_params_empty_layout_and_segments():
+    """FlatParams.empty (used by pruning) lays segments out like the constructor: 64-float aligned, leaves alias the flat
+    buffers, segment_ends() are the Adam segment boundaries; zero-row tensors are legal."""
+    import torch
+    from hier_slam_b200.mapping import FlatParams
+    a = FlatParams({"x": torch.ones(5, 3), "y": torch.zeros(70, 1), "z": torch.ones(2, 26)})
+    b = FlatParams.empty({"x": (5, 3), "y": (70, 1), "z": (2, 26)}, "cpu")
+    assert a.offsets == b.offsets == {"x": 0, "y": 64, "z": 192}
+    assert a.segment_ends() == b.segment_ends() == [64, 192, 256]
+    assert all(e % 4 == 0 for e in b.segment_ends()) and b.flat.numel() == 256
+    b.leaves["z"].grad.fill_(1.0)
+    assert float(b.flat_grad.sum()) == 52.0 and float(b.flat.sum()) == 0.0
+    e = FlatParams.empty({"x": (0, 3), "y": (0, 1)}, "cpu")
+    assert e.flat.numel() == 0 and e.leaves["x"].shape == (0, 3)
+    b.release()                                   # no CUDA sinks registered: a no-op
+
+
+def test_flat_adam_is_cuda_only():
+    import torch
+    from hier_slam_b200.mapping import FlatParams
+    from hier_slam_b200.optim import FlatAdam
+    with pytest.raises(RuntimeError, match="CUDA-only"):
+        FlatAdam(FlatParams({"x": torch.ones(5, 3)}), {"x": 1e-3})
