@@ -192,3 +192,24 @@ class GaussianRasterizer_semantic(nn.Module):
                                             e if semantics_precomp is None else semantics_precomp, opacities,
                                             e if scales is None else scales, e if rotations is None else rotations,
                                             e if cov3D_precomp is None else cov3D_precomp, self.raster_settings)
+
+
+# ------------------------------------------------------------------------------------------------------
+# forward-only depth + silhouette
+# ------------------------------------------------------------------------------------------------------
+@torch.no_grad()
+def render_depth_silhouette(raster_settings, means3D, opacities, scales, rotations):
+    """Depth and silhouette of the current map without gradients, colours or semantic channels: what densification
+    (scripts/hierslam.py:1307-1352 add_new_gaussians_semantic_newrender: only `rendered_depth` and
+    `rendered_final_opcity` of the full semantic render are used) and the evaluation masks need.  Runs the S = 0
+    instantiation of the pipeline (4 blended channels instead of 4 + S, no [S,H,W] output) and keeps no autograd state.
+    Returns (depth [1,H,W], silhouette [1,H,W], median_depth [1,H,W], radii [P]); bit-identical to the corresponding
+    outputs of GaussianRasterizer_semantic on the same inputs."""
+    rs = raster_settings
+    e = torch.empty(0)
+    m = means3D.detach()
+    (_, _color, depth, median_depth, final_opacity, _mask, radii, _g, _b, _i) = _C.rasterize_gaussians(
+        rs.bg, m, m, opacities.detach(), scales.detach(), rotations.detach(), rs.scale_modifier, e, rs.viewmatrix,
+        rs.projmatrix, rs.tanfovx, rs.tanfovy, rs.image_height, rs.image_width, e, rs.sh_degree, rs.campos, rs.prefiltered,
+        rs.debug)
+    return depth, final_opacity, median_depth, radii

@@ -608,6 +608,24 @@ def test_flat_adam_prune_matches_boolean_indexing():
                 assert new.leaves[k].grad is not None and new.leaves[k].grad.shape == new.leaves[k].shape
 
 
+def test_render_depth_silhouette_is_bit_identical_to_the_semantic_render():
+    """hier_slam_b200.rasterizer.render_depth_silhouette (forward-only densification render) returns exactly
+    the depth / silhouette / median depth / radii of the full semantic render and keeps no autograd graph."""
+    from hier_slam_b200.rasterizer import render_depth_silhouette
+    C, Settings = new_impl()
+    for key in ("c1", "c4"):
+        cfg = CONFIGS[key]
+        scene = make_scene(cfg, 5, num_gaussians=min(cfg.num_gaussians, 40000), device="cuda")
+        settings = pt.make_settings(Settings, cfg)
+        f = pt.run_forward(C, settings, scene)
+        leaves = {k: v.clone().requires_grad_(True) for k, v in scene.items()}
+        depth, sil, median, radii = render_depth_silhouette(settings, leaves["means3D"], leaves["opacities"],
+                                                            leaves["scales"], leaves["rotations"])
+        assert torch.equal(depth, f["depth"]) and torch.equal(sil, f["final_opacity"])
+        assert torch.equal(median, f["median_depth"]) and torch.equal(radii, f["radii"])
+        assert not depth.requires_grad and not sil.requires_grad
+
+
 def test_full_size_properties_c2():
     """BASELINE.json config 2 at full size (1200x680, 300K Gaussians, S=26): properties that need no oracle."""
     C, Settings = new_impl()
