@@ -27,6 +27,61 @@ SORT_GLOBAL = os.environ.get("HS_SORT_GLOBAL", "0") == "1"   # reference-style g
 
 _contig_cache: dict = {}   # id(tensor) -> (weakref(tensor), version, contiguous copy)
 
+
+# -- sync-free binning ----------------------------------------------------------------------------------
+class BinningCapacity:
+    """Sizes for a forward without the `num_rendered` read-back (HS_ASYNC_BINNING, include/hs_raster.h): the binning buffer
+    is allocated for `instances` (Gaussian, tile) pairs and the per-tile sort for lists of at most `longest_tile`
+    entries; `num_rendered` handed to autograd is then the capacity.  Nothing synchronises, so the forward can be
+    captured in a CUDA graph.  A frame that does not fit renders EMPTY and raises its overflow flag: check
+    `overflowed()` (one host sync) before using results, and repeat synchronously with a larger capacity."""
+
+    def __init__(self, instances: int, longest_tile: int):
+        self.instances = max(int(instances), 1)
+        self.longest_tile = max(1, min(int(longest_tile), 16384))
+        self.infos: list = []      # int32[4] device views {instances, longest list, short lists, overflow}, one per forward
+
+    @classmethod
+    def from_info(cls, info: torch.Tensor, slack: float = 1.3, extra_instances: int = 65536,
+                  extra_tile: int = 256) -> "BinningCapacity":
+        """capacity with head-room from the counts of a forward (`binning_info` of its image buffer; host sync)"""
+        r, longest = (int(v) for v in info[:2].tolist())
+        return cls(int(r * slack) + extra_instances, int(longest * slack) + extra_tile)
+
+    def overflowed(self) -> bool:
+        if not self.infos:
+            return False
+        return bool(torch.stack([i[3] for i in self.infos]).any())
+
+    def clear(self) -> None:
+        self.infos.clear()
+
+
+_capacity: Optional[BinningCapacity] = None
+
+
+class async_binning:
+    """with async_binning(capacity): every forward inside runs without a host sync (see BinningCapacity)."""
+
+    def __init__(self, capacity: Optional[BinningCapacity]):
+        self.capacity = capacity
+
+    def __enter__(self):
+        global _capacity
+        self.prev, _capacity = _capacity, self.capacity
+        return self.capacity
+
+    def __exit__(self, *exc):
+        global _capacity
+        _capacity = self.prev
+        return False
+
+
+def binning_info(imgBuffer: torch.Tensor, H: int, W: int) -> torch.Tensor:
+    """int32[4] view {num_rendered, longest tile list, short lists, capacity overflow} into a forward's image buffer"""
+    off = _lib.load().hs_image_state_info_offset(int(H), int(W))
+    return imgBuffer[off:off + 16].view(torch.int32)
+
 # -- gradient sinks ------------------------------------------------------------------------------------
 # A caller that keeps its parameters in one flat buffer (hier_slam_b200.mapping.FlatParams) can register, per
 # parameter tensor, the gradient buffer that belongs to it.  When `colors_precomp` / `semantics_precomp` of a
@@ -178,14 +233,18 @@ def _forward(background, means3D, colors, semantics, opacity, scales, rotations,
         geomBuffer = torch.empty(geom_bytes, **byte)
         img_bytes = lib.hs_image_state_bytes(H, W)
         imgBuffer = torch.empty(img_bytes, **byte)
-        R = ctypes.c_int(0)
-        hint = ctypes.c_int(0)
+        cap = None if SORT_GLOBAL else _capacity
+        R = ctypes.c_int(cap.instances if cap is not None else 0)
+        hint = ctypes.c_int(cap.longest_tile if cap is not None else 0)
+        gflags = _lib.HS_SORT_GLOBAL if SORT_GLOBAL else (_lib.HS_ASYNC_BINNING if cap is not None else 0)
         _lib.check(lib.hs_forward_geometry(ctypes.byref(cam), P, _ptr(means3D_c), _ptr(opac_c), _ptr(scales_c),
                                            _ptr(rot_c), _ptr(cov_c), _ptr(sh_c), int(degree), M, _ptr(radii),
                                            _ptr(geomBuffer), geom_bytes,
-                                           _ptr(imgBuffer), img_bytes, _lib.HS_SORT_GLOBAL if SORT_GLOBAL else 0,
+                                           _ptr(imgBuffer), img_bytes, gflags,
                                            ctypes.byref(R), ctypes.byref(hint), stream), "hs_forward_geometry")
-        num_rendered = int(R.value)
+        num_rendered = int(R.value)          # capacity mode: the capacity (the counts stay on the device)
+        if cap is not None:
+            cap.infos.append(binning_info(imgBuffer, H, W))
         bin_bytes = lib.hs_binning_state_bytes(num_rendered)
         binningBuffer = torch.empty(bin_bytes, **byte)
         out_color = torch.empty(3, H, W, **fopt)

@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("HS_LIB", os.path.join(HERE, "libhsraster.so"))
 # every symbol include/hs_raster.h declares (tests check that the library exports all of them)
 EXPORTED_SYMBOLS = [
     "hs_abi_version", "hs_last_error", "hs_supports_semantic_channels", "hs_geom_state_bytes",
-    "hs_image_state_bytes", "hs_binning_state_bytes", "hs_forward_geometry", "hs_forward_render",
+    "hs_image_state_bytes", "hs_binning_state_bytes", "hs_image_state_info_offset", "hs_forward_geometry", "hs_forward_render",
     "hs_backward", "hs_mark_visible", "hs_masked_l1", "hs_hier_cross_entropy", "hs_leaf_cross_entropy", "hs_l1_ssim", "hs_adam_step",
     "hs_compact_scratch_bytes", "hs_compact_plan", "hs_compact_gather",
     "hs_geom_state_layout", "hs_image_state_layout",
@@ -27,6 +27,7 @@ HS_SEM_ALPHA_EXACT = 1
 HS_NO_CULL = 2
 HS_BWD_SIMT = 4
 HS_SORT_GLOBAL = 32
+HS_ASYNC_BINNING = 64
 
 
 class HsCamera(Structure):
@@ -60,6 +61,8 @@ def load() -> ctypes.CDLL:
     lib.hs_image_state_bytes.restype = c_size_t
     lib.hs_binning_state_bytes.argtypes = [c_int]
     lib.hs_binning_state_bytes.restype = c_size_t
+    lib.hs_image_state_info_offset.argtypes = [c_int, c_int]
+    lib.hs_image_state_info_offset.restype = c_size_t
     lib.hs_forward_geometry.argtypes = [POINTER(HsCamera), c_int, vp, vp, vp, vp, vp, vp, c_int, c_int, vp, vp,
                                         c_size_t, vp, c_size_t, c_int, POINTER(c_int), POINTER(c_int), vp]
     lib.hs_forward_geometry.restype = c_int

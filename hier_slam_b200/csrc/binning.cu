@@ -261,12 +261,17 @@ __global__ void tile_ranges_kernel(int L, const uint64_t* __restrict__ keys, uin
 //      STABLE sort over a list that is generated in Gaussian order.  All words of a segment are distinct, so the
 //      result does not depend on the scatter order: point_list and the sorted keys are bit-identical to the
 //      reference's (tests/test_gpu_parity.py).
+// Capacity mode (r_cap > 0, HS_ASYNC_BINNING): the host does not read the counts back but has sized the binning buffer
+// for r_cap instances and the per-tile sort for lists of at most tile_cap entries.  If the frame needs more, info[3] is
+// raised, every range is cleared (the frame renders empty, memory-safely) and the caller repeats the call synchronously.
 __global__ void __launch_bounds__(1024) tile_scan_kernel(int tiles, uint32_t* __restrict__ tile_count,
-                                                         uint2* __restrict__ ranges, uint32_t* __restrict__ info) {
+                                                         uint2* __restrict__ ranges, uint32_t* __restrict__ info,
+                                                         uint32_t r_cap, uint32_t tile_cap) {
     constexpr int IT = 4;   // consecutive tiles per thread: 4096 tiles per sweep, their loads are independent
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_small[32];
     __shared__ uint32_t s_carry;
+    __shared__ uint32_t s_overflow;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_carry = 0;
     uint32_t my_max = 0, my_small = 0;
@@ -334,12 +339,19 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(int tiles, uint32_t* __
         info[0] = s_carry;   // num_rendered
         info[1] = m;         // longest tile list
         info[2] = ns;        // non-empty tiles with at most HS_TILE_SORT_SMALL entries
+        s_overflow = (r_cap > 0 && (s_carry > r_cap || m > tile_cap)) ? 1u : 0u;
+        info[3] = s_overflow;
     }
+    __syncthreads();
+    if (s_overflow)
+        for (int t = tid; t < tiles; t += 1024) ranges[t] = make_uint2(0u, 0u);
 }
 
-int launch_tile_scan(const Camera& cam, const ImageView& img, cudaStream_t stream, bool debug) {
+int launch_tile_scan(const Camera& cam, const ImageView& img, uint32_t r_cap, uint32_t tile_cap, cudaStream_t stream,
+                     bool debug) {
     prof_begin(ST_SCAN, stream);
-    tile_scan_kernel<<<1, 1024, 0, stream>>>(cam.grid_x * cam.grid_y, img.tile_count, img.ranges, img.info);
+    tile_scan_kernel<<<1, 1024, 0, stream>>>(cam.grid_x * cam.grid_y, img.tile_count, img.ranges, img.info, r_cap,
+                                             tile_cap);
     prof_end(ST_SCAN, stream);
     HS_LAUNCH_OK(stream, debug);
     return 0;
@@ -348,7 +360,9 @@ int launch_tile_scan(const Camera& cam, const ImageView& img, cudaStream_t strea
 __global__ void __launch_bounds__(256) scatter_kernel(int P, const float2* __restrict__ points_xy,
                                                       const float* __restrict__ depths,
                                                       uint32_t* __restrict__ cursor, uint64_t* __restrict__ seg,
-                                                      const int* __restrict__ radii, unsigned gx, unsigned gy) {
+                                                      const int* __restrict__ radii, unsigned gx, unsigned gy,
+                                                      const uint32_t* __restrict__ info) {
+    if (info[3] != 0) return;   // capacity mode: the frame does not fit the binning buffer (tile_scan_kernel)
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     uint32_t w = 0, count = 0, dbits = 0;
@@ -498,7 +512,7 @@ int launch_tile_binning(int P, int R, int max_tile, int n_small, const Camera& c
     const int tiles = cam.grid_x * cam.grid_y;
     prof_begin(ST_DUPLICATE, stream);
     scatter_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, g.means2D, g.depths, img.tile_count, b.keys_unsorted, radii,
-                                                       cam.grid_x, cam.grid_y);
+                                                       cam.grid_x, cam.grid_y, img.info);
     prof_end(ST_DUPLICATE, stream);
     HS_LAUNCH_OK(stream, debug);
     prof_begin(ST_SORT, stream);

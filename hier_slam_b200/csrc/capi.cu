@@ -91,6 +91,12 @@ int hs_image_state_layout(int H, int W, size_t off[3]) {
     off[2] = (size_t)v.ranges;
     return 0;
 }
+size_t hs_image_state_info_offset(int H, int W) {
+    ImageView v;
+    const size_t tiles = (size_t)((W + HS_TILE_X - 1) / HS_TILE_X) * ((H + HS_TILE_Y - 1) / HS_TILE_Y);
+    image_view(nullptr, (size_t)H * W, tiles, &v);
+    return (size_t)v.info;
+}
 int hs_binning_state_layout(int R, size_t off[5]) {
     BinningView v;
     if (binning_view(nullptr, (size_t)R, &v)) return 2;
@@ -114,6 +120,7 @@ int hs_forward_geometry(const hs_camera* c, int P, const float* means3D, const f
         set_error("num_rendered / binning_hint is NULL");
         return 1;
     }
+    const int cap_instances = *num_rendered, cap_hint = *binning_hint;   // HS_ASYNC_BINNING: capacities on entry
     *num_rendered = 0;
     *binning_hint = 0;
     if (P <= 0) return 0;
@@ -144,10 +151,14 @@ int hs_forward_geometry(const hs_camera* c, int P, const float* means3D, const f
             return 1;
         }
     }
-    int* host = pinned_int();
-    if (host == nullptr) {
+    int* host = (flags & HS_ASYNC_BINNING) ? nullptr : pinned_int();
+    if (host == nullptr && !(flags & HS_ASYNC_BINNING)) {
         set_error("cudaHostAlloc failed");
         return 2;
+    }
+    if ((flags & HS_SORT_GLOBAL) && (flags & HS_ASYNC_BINNING)) {
+        set_error("HS_ASYNC_BINNING needs the tile-bucket binning (not HS_SORT_GLOBAL)");
+        return 1;
     }
     if (flags & HS_SORT_GLOBAL) {
         // reference-style binning: offsets scan over the Gaussians, the count is the last offset
@@ -180,10 +191,22 @@ int hs_forward_geometry(const hs_camera* c, int P, const float* means3D, const f
     int rc = launch_preprocess(P, means3D, scales, rotations, opacities, cov3D_precomp, cam, radii, g, img.tile_count,
                                stream, debug);
     if (rc) return rc;
-    rc = launch_tile_scan(cam, img, stream, debug);
+    const bool async = (flags & HS_ASYNC_BINNING) != 0;
+    const int tile_cap = cap_hint & HS_HINT_MASK;
+    if (async && (cap_instances <= 0 || cap_hint < 0 || tile_cap <= 0 || tile_cap > HS_TILE_SORT_MAX)) {
+        set_error("HS_ASYNC_BINNING: *num_rendered / *binning_hint must hold the capacities (instances > 0, 0 < longest "
+                  "tile list <= %d)", HS_TILE_SORT_MAX);
+        return 1;
+    }
+    rc = launch_tile_scan(cam, img, async ? (uint32_t)cap_instances : 0u, async ? (uint32_t)tile_cap : 0u, stream, debug);
     if (rc) return rc;
     if (shs != nullptr) rc = launch_sh_forward(P, sh_degree, sh_coeffs, means3D, c->campos, shs, radii, g, stream, debug);
     if (rc) return rc;
+    if (async) {
+        *num_rendered = cap_instances;
+        *binning_hint = tile_cap;   // both sort classes may be needed; nothing is read back, nothing synchronises
+        return 0;
+    }
     HS_CUDA_OK(cudaMemcpyAsync(host, img.info, 3 * sizeof(int), cudaMemcpyDeviceToHost, stream));
     HS_CUDA_OK(cudaStreamSynchronize(stream));
     *num_rendered = host[0];

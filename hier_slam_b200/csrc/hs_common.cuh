@@ -101,7 +101,8 @@ int launch_preprocess(int P, const float* means3D, const float* scales, const fl
                       const float* opacities, const float* cov3D_precomp, const Camera& cam, int* radii,
                       const GeomView& g, uint32_t* tile_count, cudaStream_t stream, bool debug);
 int launch_scan(int P, const GeomView& g, cudaStream_t stream, bool debug);
-int launch_tile_scan(const Camera& cam, const ImageView& img, cudaStream_t stream, bool debug);
+int launch_tile_scan(const Camera& cam, const ImageView& img, uint32_t r_cap, uint32_t tile_cap, cudaStream_t stream,
+                     bool debug);
 int launch_tile_binning(int P, int R, int max_tile, int n_small, const Camera& cam, const int* radii, const GeomView& g,
                         const BinningView& b, const ImageView& img, cudaStream_t stream, bool debug);
 int launch_binning(int P, int R, const Camera& cam, const int* radii, const GeomView& g, const BinningView& b,

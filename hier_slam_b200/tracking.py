@@ -95,3 +95,171 @@ class PoseRasterizer_semantic(nn.Module):
             raise RuntimeError("means3D must have dimensions (num_points, 3)")
         return _RasterizePose.apply(w2c, means3D.contiguous(), means2D, colors_precomp, semantics_precomp, opacities,
                                     scales, rotations, self.raster_settings)
+
+
+# ------------------------------------------------------------------------------------------------------
+# CUDA-graph tracking loop
+# ------------------------------------------------------------------------------------------------------
+def _pose_matrix(cam_rot: torch.Tensor, cam_tran: torch.Tensor) -> torch.Tensor:
+    """rel_w2c of transform_to_frame (utils/slam_helpers.py:278-330): normalised quaternion (r, x, y, z) -> rotation
+    (utils/slam_external.py build_rotation), translation in the last column."""
+    q = torch.nn.functional.normalize(cam_rot, dim=0)
+    r, x, y, z = q[0], q[1], q[2], q[3]
+    one, zero = torch.ones_like(r), torch.zeros_like(r)
+    return torch.stack([
+        torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y - r * z), 2 * (x * z + r * y), cam_tran[0]]),
+        torch.stack([2 * (x * y + r * z), 1 - 2 * (x * x + z * z), 2 * (y * z - r * x), cam_tran[1]]),
+        torch.stack([2 * (x * z - r * y), 2 * (y * z + r * x), 1 - 2 * (x * x + y * y), cam_tran[2]]),
+        torch.stack([zero, zero, zero, one])])
+
+
+class GraphedTracker:
+    """Hier-SLAM's per-frame camera tracking (scripts/hierslam.py:1805-1880; BASELINE.json config 3) with ONE CUDA-graph
+    launch per iteration.
+
+    An iteration is: pose -> rel_w2c -> render (`PoseRasterizer_semantic`, colour + depth + silhouette; the semantic
+    channels are not rendered because no tracking loss reads them) -> mask = (gt_depth > 0) & ~isnan(depth)
+    [& (silhouette > sil_thres)] -> loss = depth_weight * sum|gt_depth - depth|[mask] + im_weight * sum|gt_im - im|[mask]
+    (get_loss_semantic(tracking=True), :765-796) -> best-candidate bookkeeping (:1850-1856) -> backward -> Adam on the
+    unnormalised quaternion and the translation (configs/replica/hierslam_semantic_run.py:85-95).
+
+    The forward runs in capacity mode (`_C.BinningCapacity`: no `num_rendered` read-back), so nothing in the iteration
+    touches the host and the whole of it -- ~45 kernels, autograd included -- replays from one graph.  The overflow flag
+    is read ONCE per frame together with the result; a frame that outgrew the capacity is repeated after re-capturing
+    with a larger one.  The graph is re-captured when the number of Gaussians or the image size changes."""
+
+    def __init__(self, raster_settings, lr_rot: float = 0.0004, lr_trans: float = 0.002, sil_thres: float = 0.99,
+                 use_sil_for_loss: bool = True, depth_weight: float = 1.0, im_weight: float = 0.5, slack: float = 1.3,
+                 extra_instances: int = 65536):
+        self.rs = raster_settings
+        self.lr_rot, self.lr_trans = float(lr_rot), float(lr_trans)
+        self.sil_thres, self.use_sil = float(sil_thres), bool(use_sil_for_loss)
+        self.depth_weight, self.im_weight = float(depth_weight), float(im_weight)
+        self.slack, self.extra_instances = float(slack), int(extra_instances)
+        self.raster = PoseRasterizer_semantic(raster_settings)
+        self.graph = None
+        self.capacity = None
+        self.captures = 0
+        self._P = None
+
+    # -- one iteration on the static buffers (runs eagerly for warm-up, and once under capture)
+    def _iteration(self):
+        from .losses import masked_l1_sum
+        st = self.st
+        rel = _pose_matrix(st["cam_rot"], st["cam_tran"])
+        im, _radii, _sem, depth, _median, sil = self.raster(rel, st["means3D"], st["means2D"], st["opacities"],
+                                                            st["rgb_colors"], st["scales"], st["rotations"], None)
+        mask = (st["gt_depth"] > 0) & ~torch.isnan(depth)
+        if self.use_sil:
+            mask = mask & (sil > self.sil_thres)
+        loss = self.depth_weight * masked_l1_sum(depth, st["gt_depth"], mask) + \
+            self.im_weight * masked_l1_sum(im, st["gt_im"], mask)
+        with torch.no_grad():            # the candidate is the pose that PRODUCED this loss (before the step)
+            better = loss.detach() < st["min_loss"]
+            st["cand_rot"].copy_(torch.where(better, st["cam_rot"].detach(), st["cand_rot"]))
+            st["cand_tran"].copy_(torch.where(better, st["cam_tran"].detach(), st["cand_tran"]))
+            st["min_loss"].copy_(torch.where(better, loss.detach(), st["min_loss"]))
+            st["last_loss"].copy_(loss.detach())
+        loss.backward()
+        self.opt.step()
+
+    def _allocate(self, P: int, dev):
+        H, W = self.rs.image_height, self.rs.image_width
+        f = dict(dtype=torch.float32, device=dev)
+        self.st = dict(means3D=torch.zeros(P, 3, **f), means2D=torch.zeros(P, 3, **f), opacities=torch.zeros(P, 1, **f),
+                       rgb_colors=torch.zeros(P, 3, **f), scales=torch.zeros(P, 3, **f), rotations=torch.zeros(P, 4, **f),
+                       gt_im=torch.zeros(3, H, W, **f), gt_depth=torch.zeros(1, H, W, **f),
+                       cam_rot=torch.zeros(4, **f).requires_grad_(True), cam_tran=torch.zeros(3, **f).requires_grad_(True),
+                       cand_rot=torch.zeros(4, **f), cand_tran=torch.zeros(3, **f), min_loss=torch.zeros((), **f),
+                       last_loss=torch.zeros((), **f))
+        self.opt = torch.optim.Adam([{"params": [self.st["cam_rot"]], "lr": self.lr_rot},
+                                     {"params": [self.st["cam_tran"]], "lr": self.lr_trans}], capturable=True)
+        self._P = P
+        self.graph = None
+
+    def _reset(self, init_rot, init_tran):
+        st = self.st
+        with torch.no_grad():
+            st["cam_rot"].copy_(init_rot.reshape(4))
+            st["cam_tran"].copy_(init_tran.reshape(3))
+            st["cand_rot"].copy_(st["cam_rot"])
+            st["cand_tran"].copy_(st["cam_tran"])
+            st["min_loss"].fill_(float(1e20))
+            for state in self.opt.state.values():       # the reference builds a fresh optimizer for every frame
+                for v in state.values():
+                    if torch.is_tensor(v):
+                        v.zero_()
+
+    def _capture(self, at_least=None):
+        """eager synchronous iterations (warm-up + the counts that size the capacity), then the capture"""
+        dev = self.st["means3D"].device
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                self.opt.zero_grad(set_to_none=True)
+                self._iteration()
+            # counts of the current frame (a plain synchronous forward of the same render)
+            with torch.no_grad():
+                rs, st = self.rs, self.st
+                rel = _pose_matrix(st["cam_rot"], st["cam_tran"])
+                means_cam = torch.addmm(rel[:3, 3], st["means3D"], rel[:3, :3].t())
+                e = torch.empty(0)
+                out = _C.rasterize_gaussians(rs.bg, means_cam, st["rgb_colors"], st["opacities"], st["scales"],
+                                             st["rotations"], rs.scale_modifier, e, rs.viewmatrix, rs.projmatrix,
+                                             rs.tanfovx, rs.tanfovy, rs.image_height, rs.image_width, e, rs.sh_degree,
+                                             rs.campos, rs.prefiltered, rs.debug)
+                info = _C.binning_info(out[-1], rs.image_height, rs.image_width)
+                cap = _C.BinningCapacity.from_info(info, self.slack, self.extra_instances)
+            if at_least is not None:      # what an overflowed frame actually needed, with head-room
+                cap = _C.BinningCapacity(max(cap.instances, at_least.instances),
+                                         max(cap.longest_tile, at_least.longest_tile))
+        torch.cuda.current_stream(dev).wait_stream(side)
+        self.capacity = cap
+        self.opt.zero_grad(set_to_none=True)
+        self.graph = torch.cuda.CUDAGraph()
+        with _C.async_binning(cap):
+            with torch.cuda.graph(self.graph):
+                self._iteration()
+        self.captures += 1
+
+    @torch.no_grad()
+    def _load(self, means3D, rgb_colors, opacities, scales, rotations, gt_im, gt_depth):
+        st = self.st
+        for k, v in (("means3D", means3D), ("rgb_colors", rgb_colors), ("opacities", opacities), ("scales", scales),
+                     ("rotations", rotations), ("gt_im", gt_im), ("gt_depth", gt_depth)):
+            st[k].copy_(v.detach().reshape(st[k].shape))
+
+    def track(self, means3D, rgb_colors, opacities, scales, rotations, gt_im, gt_depth, init_rot, init_tran,
+              num_iters: int = 40, max_retries: int = 3):
+        """Optimise the pose of one frame.  means3D [P,3] are WORLD-frame means; opacities / scales [P,3] / rotations are
+        the render variables of transformed_params2rendervar (activated, normalised); gt_im [3,H,W], gt_depth [1,H,W].
+        Returns dict(rot, tran: the best candidate; loss: its loss; last_rot, last_tran, last_loss; retries)."""
+        if not means3D.is_cuda:
+            raise RuntimeError("GraphedTracker is CUDA-only (no CPU fallback)")
+        P, dev = means3D.shape[0], means3D.device
+        with torch.cuda.device(dev):
+            if self._P != P or self.st["means3D"].device != dev:
+                self._allocate(P, dev)
+            self._load(means3D, rgb_colors, opacities, scales, rotations, gt_im, gt_depth)
+            retries, at_least = 0, None
+            while True:
+                self._reset(init_rot, init_tran)
+                if self.graph is None:
+                    self._capture(at_least)
+                    self._reset(init_rot, init_tran)
+                for _ in range(num_iters):
+                    self.graph.replay()
+                st = self.st
+                flag = self.capacity.infos[0][3:4].to(torch.float32)
+                host = torch.cat((st["cand_rot"], st["cand_tran"], st["min_loss"].reshape(1), st["cam_rot"].detach(),
+                                  st["cam_tran"].detach(), st["last_loss"].reshape(1), flag)).cpu()   # the frame's one sync
+                if host[16] == 0 or retries >= max_retries:
+                    break
+                retries += 1          # the frame outgrew the binning capacity: re-capture larger and repeat it
+                at_least = _C.BinningCapacity.from_info(self.capacity.infos[0], 1.3)
+                self.graph = None
+            if host[16] != 0:
+                raise RuntimeError("tracking frame does not fit the binning capacity after re-captures")
+        return dict(rot=host[0:4].clone(), tran=host[4:7].clone(), loss=float(host[7]), last_rot=host[8:12].clone(),
+                    last_tran=host[12:15].clone(), last_loss=float(host[15]), retries=retries)

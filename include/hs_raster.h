@@ -43,6 +43,14 @@ extern "C" {
 #define HS_SORT_GLOBAL 32    /* hs_forward_geometry: reference-style binning (offsets scan, key duplication, one global
                                 radix sort) instead of the default per-tile bucket sort; sorted keys, tile lists and
                                 ranges are bit-identical either way */
+#define HS_ASYNC_BINNING 64  /* hs_forward_geometry: capacity mode -- no read-back, no stream synchronisation (CUDA-graph
+                                capturable).  On entry *num_rendered / *binning_hint hold the CAPACITIES the caller sized
+                                the binning buffer for (instances, longest tile list <= 16384; typically taken from an
+                                earlier synchronous call on a similar frame plus slack) and are handed on to
+                                hs_forward_render / hs_backward as if they were the counts.  If the frame needs more, the
+                                fourth int32 at hs_image_state_info_offset() inside image_state becomes 1, the frame
+                                renders empty (memory-safely) and the caller must repeat it synchronously; ints 0..2 there
+                                are the actual instance count, longest list and number of short lists. */
 
 /* Mirror of GaussianRasterizationSettings (diff_gaussian_rasterization/__init__.py:161-173). */
 typedef struct hs_camera {
@@ -68,12 +76,14 @@ int hs_supports_semantic_channels(int S);
 size_t hs_geom_state_bytes(int P);
 size_t hs_image_state_bytes(int image_height, int image_width);
 size_t hs_binning_state_bytes(int num_rendered);
+/* byte offset, inside image_state, of four int32: {num_rendered, longest tile list, short lists, capacity overflow} */
+size_t hs_image_state_info_offset(int image_height, int image_width);
 
 /* Stage 1 of the forward: per-Gaussian projection / cull / tile counting.
  * Writes radii[P] (int32, device), fills geom_state and the tile ranges inside image_state, and returns (HOST
  * pointers) the number of (Gaussian, tile) instances in *num_rendered and, in *binning_hint, an opaque value that
  * must be handed to hs_forward_render (it encodes the longest tile list; -1 with HS_SORT_GLOBAL).  Synchronises `stream` once (the only host sync of a forward+backward).
- * scales/rotations may be NULL iff cov3D_precomp is given, and vice versa.  flags: 0 or HS_SORT_GLOBAL.
+ * scales/rotations may be NULL iff cov3D_precomp is given, and vice versa.  flags: 0, HS_SORT_GLOBAL or HS_ASYNC_BINNING.
  * shs (may be NULL): spherical-harmonics coefficients [P, sh_coeffs, 3]; when given, the view-dependent colours of
  * degree sh_degree (0..3, reference forward.cu:20-71) are evaluated into geom_state and hs_forward_render /
  * hs_backward are called with colors == NULL. */

@@ -626,6 +626,67 @@ def test_render_depth_silhouette_is_bit_identical_to_the_semantic_render():
         assert not depth.requires_grad and not sil.requires_grad
 
 
+def _eager_tracking_loop(settings_mod, cfg, scene, gt_im, gt_depth, iters):
+    """the reference's tracking iteration written with the public API and plain torch (scripts/hierslam.py:765-796,
+    1837-1856): transform in torch, boolean-mask L1 sums, torch.optim.Adam, best candidate"""
+    import torch.nn.functional as F
+    from hier_slam_b200.tracking import _pose_matrix
+    import diff_gaussian_rasterization as ours
+    raster = ours.GaussianRasterizer_semantic(pt.make_settings(ours.GaussianRasterizationSettings, cfg, "cuda"))
+    cam_rot = torch.tensor([1.0, 0, 0, 0], device="cuda").requires_grad_(True)
+    cam_tran = torch.zeros(3, device="cuda").requires_grad_(True)
+    opt = torch.optim.Adam([{"params": [cam_rot], "lr": 0.0004}, {"params": [cam_tran], "lr": 0.002}])
+    pts = scene["means3D"]
+    ones = torch.ones(pts.shape[0], 1, device="cuda")
+    best = (float("inf"), None, None)
+    for _ in range(iters):
+        rel = _pose_matrix(cam_rot, cam_tran)
+        tp = (rel @ torch.cat((pts, ones), 1).T).T[:, :3]
+        im, _, _, depth, _, sil = raster(means3D=tp, means2D=torch.zeros_like(pts), opacities=scene["opacities"],
+                                         colors_precomp=scene["colors_precomp"], scales=scene["scales"],
+                                         rotations=scene["rotations"], semantics_precomp=scene["semantics_precomp"])
+        mask = (gt_depth > 0) & ~torch.isnan(depth) & (sil > 0.99)
+        loss = torch.abs(gt_depth - depth)[mask].sum() + 0.5 * torch.abs(gt_im - im)[mask.expand(3, -1, -1)].sum()
+        if float(loss) < best[0]:
+            best = (float(loss), cam_rot.detach().clone().cpu(), cam_tran.detach().clone().cpu())
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+    return best
+
+
+def test_graphed_tracker_matches_the_eager_tracking_loop():
+    """hier_slam_b200.tracking.GraphedTracker (one CUDA-graph launch per iteration, sync-free binning) follows the same pose
+    trajectory as the reference-style eager loop, also when a frame outgrows the binning capacity and is repeated."""
+    from hier_slam_b200.scene import keyframe_poses
+    from hier_slam_b200.tracking import GraphedTracker
+    import diff_gaussian_rasterization as ours
+    cfg = CONFIGS["c1"]
+    scene = make_scene(cfg, 0, device="cuda")
+    settings = pt.make_settings(ours.GaussianRasterizationSettings, cfg, "cuda")
+    raster = ours.GaussianRasterizer_semantic(settings)
+    gt_pose = keyframe_poses(2, seed=2, max_angle_deg=1.0, max_trans=0.02).to("cuda")[1]
+    with torch.no_grad():
+        tp = torch.addmm(gt_pose[:3, 3], scene["means3D"], gt_pose[:3, :3].t())
+        gt_im, _, _, gt_depth, _, _ = raster(means3D=tp, means2D=torch.zeros_like(tp), opacities=scene["opacities"],
+                                             colors_precomp=scene["colors_precomp"], scales=scene["scales"],
+                                             rotations=scene["rotations"], semantics_precomp=scene["semantics_precomp"])
+    iters = 12
+    ref_loss, ref_rot, ref_tran = _eager_tracking_loop(ours, cfg, scene, gt_im, gt_depth, iters)
+    init_rot, init_tran = torch.tensor([1.0, 0, 0, 0]), torch.zeros(3)
+    args = (scene["means3D"], scene["colors_precomp"], scene["opacities"], scene["scales"], scene["rotations"], gt_im,
+            gt_depth, init_rot, init_tran)
+    for tracker, expect_retry in ((GraphedTracker(settings), False),
+                                  (GraphedTracker(settings, slack=0.5, extra_instances=0), True)):
+        out = tracker.track(*args, num_iters=iters)
+        assert (out["retries"] > 0) == expect_retry
+        assert abs(out["loss"] - ref_loss) <= 1e-3 * abs(ref_loss)
+        assert float((out["rot"] - ref_rot).abs().max()) < 1e-5 and float((out["tran"] - ref_tran).abs().max()) < 1e-5
+        again = tracker.track(*args, num_iters=iters)          # second frame: replays the captured graph
+        assert tracker.captures == (2 if expect_retry else 1)
+        assert float((again["tran"] - out["tran"]).abs().max()) < 1e-5 and again["retries"] == 0
+
+
 def test_full_size_properties_c2():
     """BASELINE.json config 2 at full size (1200x680, 300K Gaussians, S=26): properties that need no oracle."""
     C, Settings = new_impl()

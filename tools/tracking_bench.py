@@ -103,6 +103,45 @@ def run(mod, cfg, frames, iters, dev="cuda", fused=False, fused_loss=False):
                 wall_ms_per_iter=wall * 1e3 / (frames * iters), final_loss=float(loss)), torch.stack(traj)
 
 
+def run_graphed(mod, cfg, frames, iters, dev="cuda"):
+    """the same loop through hier_slam_b200.tracking.GraphedTracker: one CUDA-graph launch per iteration, the mask is the
+    reference's per-iteration one ((gt_depth > 0) & (rendered silhouette > 0.99)), one host sync per frame"""
+    from hier_slam_b200.tracking import GraphedTracker
+    sc = make_scene(cfg, 0, device=dev)
+    settings = pt.make_settings(mod.GaussianRasterizationSettings, cfg, dev)
+    raster = mod.GaussianRasterizer_semantic(raster_settings=settings)
+    gt_poses = keyframe_poses(frames, seed=2, max_angle_deg=1.0, max_trans=0.02).to(dev)
+    gts = []
+    with torch.no_grad():
+        for f in range(frames):
+            tp = torch.addmm(gt_poses[f][:3, 3], sc["means3D"], gt_poses[f][:3, :3].t())
+            im, _, _, depth, _, _ = raster(means3D=tp, means2D=torch.zeros_like(tp), opacities=sc["opacities"],
+                                           colors_precomp=sc["colors_precomp"], scales=sc["scales"],
+                                           rotations=sc["rotations"], semantics_precomp=sc["semantics_precomp"])
+            gts.append((im.clone(), depth.clone()))
+    tracker = GraphedTracker(settings)
+    rot, tran = torch.tensor([1.0, 0, 0, 0]), torch.zeros(3)
+    args = (sc["means3D"], sc["colors_precomp"], sc["opacities"], sc["scales"], sc["rotations"])
+    tracker.track(*args, gts[0][0], gts[0][1], rot, tran, num_iters=3)       # capture + warm-up
+    traj, retries = [], 0
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for f in range(frames):
+        out = tracker.track(*args, gts[f][0], gts[f][1], rot, tran, num_iters=iters)
+        rot, tran = out["last_rot"], out["last_tran"]          # the bench's other arms continue from the last pose too
+        retries += out["retries"]
+        traj.append(torch.cat([rot, tran]))
+    e1.record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    ms = e0.elapsed_time(e1)
+    return dict(iters_per_s=frames * iters / (ms * 1e-3), frames_per_s=frames / (ms * 1e-3), ms_per_iter=ms / (frames * iters),
+                wall_ms_per_iter=wall * 1e3 / (frames * iters), final_loss=out["last_loss"], retries=retries,
+                graph_captures=tracker.captures), torch.stack(traj)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--impl", default="both")
@@ -125,6 +164,9 @@ def main():
         res["fused2"] = run(ours, cfg, a.frames, a.iters, fused=True, fused_loss=True)
         print(json.dumps({"impl": "ours-fused-pose+masked-l1", "config": cfg.name, "workload": "c3 tracking", **res["fused2"][0],
                           "pose_trajectory_max_abs_diff_vs_unfused": float((res["fused2"][1] - res["ours"][1]).abs().max())}))
+        res["graphed"] = run_graphed(ours, cfg, a.frames, a.iters)
+        print(json.dumps({"impl": "ours-graphed-tracker", "config": cfg.name, "workload": "c3 tracking", **res["graphed"][0],
+                          "pose_trajectory_max_abs_diff_vs_unfused": float((res["graphed"][1] - res["ours"][1]).abs().max())}))
     if a.impl in ("ref-cuda", "both"):
         from oracle import ref_loader
         ref = ref_loader.load_reference(cfg.num_semantic)
