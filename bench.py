@@ -356,6 +356,134 @@ def run_ours(a, rank, world, local):
     return out, (scene_cpu, grads_cpu, cfg)
 
 
+def timed_loop(fn, n, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+
+def run_extras(a):
+    """Bounded extra legs on the same workload (N = 1, rank 0): the fwd+bwd step replayed from a
+    CUDA graph (capacity-mode binning), the c3 tracking loop through GraphedTracker, and a mapping iteration with Hier-SLAM's
+    complete loss through the fused loss kernels + FlatAdam.  Reported next to the headline value, never instead of it."""
+    from hier_slam_b200 import _C
+    from hier_slam_b200.losses import l1_ssim_loss, masked_l1_sum, tree_semantic_loss
+    from hier_slam_b200.mapping import FlatParams
+    from hier_slam_b200.optim import FlatAdam
+    from hier_slam_b200.rasterizer import GaussianRasterizationSettings, GaussianRasterizer_semantic
+    from hier_slam_b200.scene import keyframe_poses
+    from hier_slam_b200.tracking import GraphedTracker
+    import parity_tools as pt
+    dev = torch.device("cuda", 0)
+    cfg = CONFIGS[a.config]
+    scene_cpu, grads_cpu = build_workload(cfg, 0, 1, dev)
+    settings = pt.make_settings(GaussianRasterizationSettings, cfg, dev)
+    raster = GaussianRasterizer_semantic(raster_settings=settings)
+    params = FlatParams({k: v.to(dev) for k, v in scene_cpu.items()})
+    lv = params.leaves
+    P, H, W = lv["means3D"].shape[0], cfg.height, cfg.width
+    means2D = torch.zeros(P, 3, device=dev)
+    up = {k: v.to(dev) for k, v in grads_cpu.items()}
+    up_tuple = (up["color"], up["semantic"], up["depth"], up["median_depth"], up["final_opacity"])
+    out = {}
+
+    def render():
+        return raster(means3D=lv["means3D"], means2D=means2D, opacities=lv["opacities"], colors_precomp=lv["colors_precomp"],
+                      scales=lv["scales"], rotations=lv["rotations"], semantics_precomp=lv["semantics_precomp"])
+
+    # (1) the headline step without its host sync, replayed from a CUDA graph
+    def step():
+        params.zero_grad()
+        color, radii, sem, depth, median, opac = render()
+        torch.autograd.backward((color, sem, depth, median, opac), up_tuple)
+        return radii
+    side = torch.cuda.Stream(dev)
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            step()
+        with torch.no_grad():
+            info = _C.binning_info(_C.rasterize_gaussians_semantic(
+                settings.bg, lv["means3D"], lv["colors_precomp"], lv["semantics_precomp"], lv["opacities"], lv["scales"],
+                lv["rotations"], 1.0, torch.empty(0), settings.viewmatrix, settings.projmatrix, settings.tanfovx,
+                settings.tanfovy, H, W, torch.empty(0), 0, settings.campos, False, False)[-1], H, W)
+            cap = _C.BinningCapacity.from_info(info)
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with _C.async_binning(cap):
+        with torch.cuda.graph(graph):
+            step()
+    ms = timed_loop(graph.replay, a.steps)
+    out["graphed_step"] = {"value": 1e3 / ms, "unit": UNIT, "ms_per_step": ms, "capacity_overflow": cap.overflowed(),
+                           "what": "the same fwd+bwd step (all five upstream gradients) in capacity mode (HS_ASYNC_BINNING: no "
+                                   "num_rendered read-back), captured once and replayed as one CUDA graph per step"}
+    del graph
+
+    # (2) BASELINE.json config 3: 40 pose-only iterations per frame, one graph launch per iteration
+    gt_poses = keyframe_poses(2, seed=2, max_angle_deg=1.0, max_trans=0.02).to(dev)
+    gts = []
+    with torch.no_grad():
+        for f in range(2):
+            tp = torch.addmm(gt_poses[f][:3, 3], lv["means3D"], gt_poses[f][:3, :3].t())
+            im, _, _, depth, _, _ = raster(means3D=tp, means2D=means2D, opacities=lv["opacities"],
+                                           colors_precomp=lv["colors_precomp"], scales=lv["scales"],
+                                           rotations=lv["rotations"], semantics_precomp=lv["semantics_precomp"])
+            gts.append((im.clone(), depth.clone()))
+    tracker = GraphedTracker(settings)
+    targs = tuple(lv[k].detach() for k in ("means3D", "colors_precomp", "opacities", "scales", "rotations"))
+    rot, tran = torch.tensor([1.0, 0, 0, 0]), torch.zeros(3)
+    tracker.track(*targs, gts[0][0], gts[0][1], rot, tran, num_iters=3)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    retries = 0
+    for f in range(2):
+        r = tracker.track(*targs, gts[f][0], gts[f][1], rot, tran, num_iters=40)
+        rot, tran, retries = r["last_rot"], r["last_tran"], retries + r["retries"]
+    wall = time.perf_counter() - t0          # track() ends with the frame's device->host read: wall clock == device time
+    out["tracking_c3"] = {"iterations_per_s": 80 / wall, "frames_per_s": 2 / wall, "ms_per_iteration": wall * 1e3 / 80,
+                          "iterations_per_frame": 40, "capacity_retries": retries, "graph_captures": tracker.captures,
+                          "what": "GraphedTracker: pose -> render (colour, depth, silhouette) -> masked L1 depth + colour -> "
+                                  "backward -> Adam on the camera quaternion / translation, one CUDA-graph launch per iteration"}
+    del tracker
+
+    # (3) a mapping iteration with the complete loss of get_loss_semantic_mlp and the parameter step
+    sizes = {26: [4, 5, 5, 6, 6], 16: [4, 4, 4, 4], 74: [6, 10, 14, 20, 24]}.get(cfg.num_semantic)
+    if sizes is not None:
+        leaves_n = {26: 102, 16: 41, 74: 550}[cfg.num_semantic]
+        g = torch.Generator().manual_seed(3)
+        gt_im = torch.rand(3, H, W, generator=g).to(dev)
+        gt_depth = (0.5 + 5 * torch.rand(1, H, W, generator=g)).to(dev)
+        labels = torch.stack([torch.randint(0, n, (H, W), generator=g) for n in sizes + [leaves_n]]).to(dev)
+        mask = gt_depth > 0.6
+        n_mask = float(mask.sum())
+        conv = torch.nn.Conv2d(cfg.num_semantic, leaves_n, kernel_size=1).to(dev)
+        opt = FlatAdam(params, {k: 1e-3 for k in params.names}, eps=1e-15)
+        conv_opt = torch.optim.Adam(conv.parameters(), lr=5e-4)
+
+        def map_step():
+            opt.zero_grad()
+            conv_opt.zero_grad(set_to_none=True)
+            im, radii, sem, depth, median, sil = render()
+            loss = (masked_l1_sum(depth, gt_depth, mask) / n_mask + 0.5 * l1_ssim_loss(im, gt_im)
+                    + 0.2 * tree_semantic_loss(sem, labels, sizes, conv.weight, conv.bias, 1.0, 5.0, num_valid=H * W))
+            loss.backward()
+            opt.step()
+            conv_opt.step()
+        ms = timed_loop(map_step, max(5, min(a.steps, 20)))
+        out["mapping_iteration"] = {"value": 1e3 / ms, "unit": "iterations/s", "ms_per_iteration": ms,
+                                    "what": "render + 1.0 depth L1 + 0.5 (0.8 L1 + 0.2 (1 - SSIM)) + 0.2 (level CE + 5 leaf CE "
+                                            f"behind a 1x1 conv to {leaves_n} classes) + backward + Adam on all Gaussian "
+                                            "parameters (FlatAdam) and the conv: the loss structure of scripts/hierslam.py:"
+                                            "905-1016 through hier_slam_b200.losses / optim"}
+    return out
+
+
 def run_ref_cuda(a, steps, warmup):
     """The unmodified reference CUDA extension through its OWN python API on the same inputs (N = 1)."""
     from oracle import ref_loader
@@ -511,6 +639,10 @@ def main():
                     out["speedup_vs_ref_cuda"] = out["value"] / out["ref_cuda"]["value"]
             except Exception as ex:  # the reference build is a reported baseline, never a dependency
                 out["ref_cuda"] = {"unavailable": repr(ex)}
+            try:
+                out.update(run_extras(a))
+            except Exception as ex:  # extra legs never take the headline line down
+                out["extras_error"] = repr(ex)
             out["cpu_baseline"] = run_cpu_reference(a, scene_cpu, grads_cpu, steps=1, warmup=0, budget_s=20.0)
         print(json.dumps(out), flush=True)
     if world > 1:
