@@ -449,7 +449,8 @@ def run_extras(a):
     out["tracking_c3"] = {"iterations_per_s": 80 / wall, "frames_per_s": 2 / wall, "ms_per_iteration": wall * 1e3 / 80,
                           "iterations_per_frame": 40, "capacity_retries": retries, "graph_captures": tracker.captures,
                           "what": "GraphedTracker: pose -> render (colour, depth, silhouette) -> masked L1 depth + colour -> "
-                                  "backward -> Adam on the camera quaternion / translation, one CUDA-graph launch per iteration"}
+                                  "backward (pose gradient reduced in-kernel) -> Adam on the camera quaternion / translation; ~16 kernels, no "
+                                  "autograd, one CUDA-graph launch per iteration"}
     del tracker
 
     # (3) a mapping iteration with the complete loss of get_loss_semantic_mlp and the parameter step

@@ -370,6 +370,37 @@ int hs_hier_cross_entropy(const float* sem, const int* labels, int levels, const
                                      (cudaStream_t)stream_);
 }
 
+int hs_transform_points(const float* w2c, const float* world, int P, float* cam, void* stream_) {
+    if (P > 0 && (w2c == nullptr || world == nullptr || cam == nullptr)) {
+        set_error("hs_transform_points: NULL argument");
+        return 1;
+    }
+    return launch_transform_points(w2c, world, P, cam, (cudaStream_t)stream_);
+}
+
+int hs_tracking_loss(const float* im, const float* depth, const float* silhouette, const float* gt_im,
+                     const float* gt_depth, size_t pixels, float sil_thres, int use_silhouette, float depth_weight,
+                     float im_weight, float* loss, float* grad_im, float* grad_depth, void* stream_) {
+    if (im == nullptr || depth == nullptr || gt_im == nullptr || gt_depth == nullptr || loss == nullptr ||
+        grad_im == nullptr || grad_depth == nullptr || (use_silhouette && silhouette == nullptr)) {
+        set_error("hs_tracking_loss: NULL argument");
+        return 1;
+    }
+    return launch_tracking_loss(im, depth, silhouette, gt_im, gt_depth, pixels, sil_thres, use_silhouette, depth_weight,
+                                im_weight, loss, grad_im, grad_depth, (cudaStream_t)stream_);
+}
+
+int hs_pose_step(float* cam_rot, float* cam_tran, const float* dL_dpose, float* loss, float* state, float* w2c,
+                 float lr_rot, float lr_tran, float beta1, float beta2, float eps, int mode, void* stream_) {
+    if (cam_rot == nullptr || cam_tran == nullptr || w2c == nullptr ||
+        (mode != 0 && (dL_dpose == nullptr || loss == nullptr || state == nullptr))) {
+        set_error("hs_pose_step: NULL argument");
+        return 1;
+    }
+    return launch_pose_step(cam_rot, cam_tran, dL_dpose, loss, state, w2c, lr_rot, lr_tran, beta1, beta2, eps, mode,
+                            (cudaStream_t)stream_);
+}
+
 int hs_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, int segments,
                  const unsigned long long* segment_end, const double* segment_lr, double beta1, double beta2, double eps,
                  int step, void* stream_) {

@@ -136,6 +136,12 @@ int launch_masked_l1(const float* pred, const float* target, const uint8_t* mask
                      float* grad, cudaStream_t stream);
 int launch_hier_cross_entropy(const float* sem, const int* labels, int L, const int* level_begin, const float* level_scale,
                               size_t HW, float* loss, float* grad, cudaStream_t stream);
+int launch_transform_points(const float* w2c, const float* world, int P, float* cam, cudaStream_t stream);
+int launch_tracking_loss(const float* im, const float* depth, const float* sil, const float* gt_im, const float* gt_depth,
+                         size_t HW, float sil_thres, int use_sil, float w_depth, float w_im, float* loss, float* grad_im,
+                         float* grad_depth, cudaStream_t stream);
+int launch_pose_step(float* cam_rot, float* cam_tran, const float* dL_dpose, float* loss, float* state, float* w2c,
+                     float lr_rot, float lr_tran, float beta1, float beta2, float eps, int mode, cudaStream_t stream);
 int launch_adam_flat(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, int n_seg,
                      const unsigned long long* seg_end, const double* seg_lr, double beta1, double beta2, double eps, int step,
                      cudaStream_t stream);

@@ -117,78 +117,94 @@ class GraphedTracker:
     """Hier-SLAM's per-frame camera tracking (scripts/hierslam.py:1805-1880; BASELINE.json config 3) with ONE CUDA-graph
     launch per iteration.
 
-    An iteration is: pose -> rel_w2c -> render (`PoseRasterizer_semantic`, colour + depth + silhouette; the semantic
-    channels are not rendered because no tracking loss reads them) -> mask = (gt_depth > 0) & ~isnan(depth)
+    An iteration is: pose -> rel_w2c -> camera-frame means -> render (S = 0 pipeline: colour + depth + silhouette; the
+    semantic channels are not rendered because no tracking loss reads them) -> mask = (gt_depth > 0) & ~isnan(depth)
     [& (silhouette > sil_thres)] -> loss = depth_weight * sum|gt_depth - depth|[mask] + im_weight * sum|gt_im - im|[mask]
-    (get_loss_semantic(tracking=True), :765-796) -> best-candidate bookkeeping (:1850-1856) -> backward -> Adam on the
-    unnormalised quaternion and the translation (configs/replica/hierslam_semantic_run.py:85-95).
+    (get_loss_semantic(tracking=True), :765-796) -> best-candidate bookkeeping (:1850-1856) -> backward with the pose
+    gradient reduced in the per-Gaussian kernel -> Adam on the unnormalised quaternion and the translation
+    (configs/replica/hierslam_semantic_run.py:85-95).
 
-    The forward runs in capacity mode (`_C.BinningCapacity`: no `num_rendered` read-back), so nothing in the iteration
-    touches the host and the whole of it -- ~45 kernels, autograd included -- replays from one graph.  The overflow flag
-    is read ONCE per frame together with the result; a frame that outgrew the capacity is repeated after re-capturing
-    with a larger one.  The graph is re-captured when the number of Gaussians or the image size changes."""
+    Nothing in it needs autograd or the host: the steps between the rasterizer calls are three kernels of the library
+    (hs_transform_points, hs_tracking_loss, hs_pose_step; in torch they are ~200 tiny launches per iteration) and the
+    forward runs in capacity mode (`_C.BinningCapacity`: no `num_rendered` read-back), so an iteration is ~16 launches
+    replayed from one graph.  The overflow flag is read ONCE per frame together with the result; a frame that outgrew
+    the capacity is repeated after re-capturing with a larger one.  The graph is re-captured when the number of
+    Gaussians changes."""
 
     def __init__(self, raster_settings, lr_rot: float = 0.0004, lr_trans: float = 0.002, sil_thres: float = 0.99,
                  use_sil_for_loss: bool = True, depth_weight: float = 1.0, im_weight: float = 0.5, slack: float = 1.3,
-                 extra_instances: int = 65536):
+                 extra_instances: int = 65536, betas=(0.9, 0.999), eps: float = 1e-8):
         self.rs = raster_settings
         self.lr_rot, self.lr_trans = float(lr_rot), float(lr_trans)
         self.sil_thres, self.use_sil = float(sil_thres), bool(use_sil_for_loss)
         self.depth_weight, self.im_weight = float(depth_weight), float(im_weight)
         self.slack, self.extra_instances = float(slack), int(extra_instances)
-        self.raster = PoseRasterizer_semantic(raster_settings)
+        self.betas, self.eps = (float(betas[0]), float(betas[1])), float(eps)
         self.graph = None
         self.capacity = None
         self.captures = 0
         self._P = None
 
-    # -- one iteration on the static buffers (runs eagerly for warm-up, and once under capture)
-    def _iteration(self):
-        from .losses import masked_l1_sum
+    def _pose_step(self, mode: int, d_pose=None):
+        import ctypes
+        from . import _lib
         st = self.st
-        rel = _pose_matrix(st["cam_rot"], st["cam_tran"])
-        im, _radii, _sem, depth, _median, sil = self.raster(rel, st["means3D"], st["means2D"], st["opacities"],
-                                                            st["rgb_colors"], st["scales"], st["rotations"], None)
-        mask = (st["gt_depth"] > 0) & ~torch.isnan(depth)
-        if self.use_sil:
-            mask = mask & (sil > self.sil_thres)
-        loss = self.depth_weight * masked_l1_sum(depth, st["gt_depth"], mask) + \
-            self.im_weight * masked_l1_sum(im, st["gt_im"], mask)
-        with torch.no_grad():            # the candidate is the pose that PRODUCED this loss (before the step)
-            better = loss.detach() < st["min_loss"]
-            st["cand_rot"].copy_(torch.where(better, st["cam_rot"].detach(), st["cand_rot"]))
-            st["cand_tran"].copy_(torch.where(better, st["cam_tran"].detach(), st["cand_tran"]))
-            st["min_loss"].copy_(torch.where(better, loss.detach(), st["min_loss"]))
-            st["last_loss"].copy_(loss.detach())
-        loss.backward()
-        self.opt.step()
+        vp = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
+        dev = st["cam_rot"].device
+        _lib.check(_lib.load().hs_pose_step(vp(st["cam_rot"]), vp(st["cam_tran"]), vp(d_pose), vp(st["loss"]),
+                                            vp(st["state"]), vp(st["w2c"]), self.lr_rot, self.lr_trans, self.betas[0],
+                                            self.betas[1], self.eps, mode,
+                                            ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "hs_pose_step")
+
+    # -- one iteration on the static buffers (runs eagerly for warm-up, and once under capture); returns the image buffer
+    @torch.no_grad()
+    def _iteration(self):
+        import ctypes
+        from . import _lib
+        lib, st, rs = _lib.load(), self.st, self.rs
+        dev = st["means3D"].device
+        vp = lambda t: ctypes.c_void_p(t.data_ptr())
+        stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        H, W, P = rs.image_height, rs.image_width, st["means3D"].shape[0]
+        e = torch.empty(0)
+        _lib.check(lib.hs_transform_points(vp(st["w2c"]), vp(st["means3D"]), P, vp(st["means_cam"]), stream),
+                   "hs_transform_points")
+        (n, im, depth, _median, sil, _mask, radii, gb, bb, ib) = _C.rasterize_gaussians(
+            rs.bg, st["means_cam"], st["rgb_colors"], st["opacities"], st["scales"], st["rotations"], rs.scale_modifier, e,
+            rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, H, W, e, rs.sh_degree, rs.campos, rs.prefiltered, rs.debug)
+        g_im, g_depth = torch.empty_like(im), torch.empty_like(depth)
+        _lib.check(lib.hs_tracking_loss(vp(im), vp(depth), vp(sil), vp(st["gt_im"]), vp(st["gt_depth"]), H * W,
+                                        self.sil_thres, int(self.use_sil), self.depth_weight, self.im_weight,
+                                        vp(st["loss"]), vp(g_im), vp(g_depth), stream), "hs_tracking_loss")
+        grads = _C.rasterize_gaussians_backward(
+            rs.bg, st["means_cam"], radii, st["rgb_colors"], st["scales"], st["rotations"], rs.scale_modifier, e,
+            rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, g_im, g_depth, None, None, e, rs.sh_degree, rs.campos,
+            gb, n, bb, ib, rs.debug, H, W, pose_points=st["means3D"])
+        self._pose_step(1, grads[-1])
+        return ib
 
     def _allocate(self, P: int, dev):
         H, W = self.rs.image_height, self.rs.image_width
         f = dict(dtype=torch.float32, device=dev)
-        self.st = dict(means3D=torch.zeros(P, 3, **f), means2D=torch.zeros(P, 3, **f), opacities=torch.zeros(P, 1, **f),
+        self.st = dict(means3D=torch.zeros(P, 3, **f), means_cam=torch.zeros(P, 3, **f), opacities=torch.zeros(P, 1, **f),
                        rgb_colors=torch.zeros(P, 3, **f), scales=torch.zeros(P, 3, **f), rotations=torch.zeros(P, 4, **f),
-                       gt_im=torch.zeros(3, H, W, **f), gt_depth=torch.zeros(1, H, W, **f),
-                       cam_rot=torch.zeros(4, **f).requires_grad_(True), cam_tran=torch.zeros(3, **f).requires_grad_(True),
-                       cand_rot=torch.zeros(4, **f), cand_tran=torch.zeros(3, **f), min_loss=torch.zeros((), **f),
-                       last_loss=torch.zeros((), **f))
-        self.opt = torch.optim.Adam([{"params": [self.st["cam_rot"]], "lr": self.lr_rot},
-                                     {"params": [self.st["cam_tran"]], "lr": self.lr_trans}], capturable=True)
+                       gt_im=torch.zeros(3, H, W, **f), gt_depth=torch.zeros(1, H, W, **f), cam_rot=torch.zeros(4, **f),
+                       cam_tran=torch.zeros(3, **f), w2c=torch.zeros(16, **f), loss=torch.zeros(1, **f),
+                       state=torch.zeros(24, **f))
         self._P = P
         self.graph = None
 
+    @torch.no_grad()
     def _reset(self, init_rot, init_tran):
         st = self.st
-        with torch.no_grad():
-            st["cam_rot"].copy_(init_rot.reshape(4))
-            st["cam_tran"].copy_(init_tran.reshape(3))
-            st["cand_rot"].copy_(st["cam_rot"])
-            st["cand_tran"].copy_(st["cam_tran"])
-            st["min_loss"].fill_(float(1e20))
-            for state in self.opt.state.values():       # the reference builds a fresh optimizer for every frame
-                for v in state.values():
-                    if torch.is_tensor(v):
-                        v.zero_()
+        st["cam_rot"].copy_(init_rot.reshape(4))
+        st["cam_tran"].copy_(init_tran.reshape(3))
+        st["state"].zero_()                    # the reference builds a fresh optimizer for every frame
+        st["state"][15] = 1e20                 # min_loss
+        st["state"][16:20].copy_(st["cam_rot"])
+        st["state"][20:23].copy_(st["cam_tran"])
+        st["loss"].zero_()
+        self._pose_step(0)
 
     def _capture(self, at_least=None):
         """eager synchronous iterations (warm-up + the counts that size the capacity), then the capture"""
@@ -196,27 +212,15 @@ class GraphedTracker:
         side = torch.cuda.Stream(dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
-            for _ in range(3):
-                self.opt.zero_grad(set_to_none=True)
-                self._iteration()
-            # counts of the current frame (a plain synchronous forward of the same render)
-            with torch.no_grad():
-                rs, st = self.rs, self.st
-                rel = _pose_matrix(st["cam_rot"], st["cam_tran"])
-                means_cam = torch.addmm(rel[:3, 3], st["means3D"], rel[:3, :3].t())
-                e = torch.empty(0)
-                out = _C.rasterize_gaussians(rs.bg, means_cam, st["rgb_colors"], st["opacities"], st["scales"],
-                                             st["rotations"], rs.scale_modifier, e, rs.viewmatrix, rs.projmatrix,
-                                             rs.tanfovx, rs.tanfovy, rs.image_height, rs.image_width, e, rs.sh_degree,
-                                             rs.campos, rs.prefiltered, rs.debug)
-                info = _C.binning_info(out[-1], rs.image_height, rs.image_width)
-                cap = _C.BinningCapacity.from_info(info, self.slack, self.extra_instances)
+            for _ in range(2):
+                ib = self._iteration()
+            info = _C.binning_info(ib, self.rs.image_height, self.rs.image_width)
+            cap = _C.BinningCapacity.from_info(info, self.slack, self.extra_instances)
             if at_least is not None:      # what an overflowed frame actually needed, with head-room
                 cap = _C.BinningCapacity(max(cap.instances, at_least.instances),
                                          max(cap.longest_tile, at_least.longest_tile))
         torch.cuda.current_stream(dev).wait_stream(side)
         self.capacity = cap
-        self.opt.zero_grad(set_to_none=True)
         self.graph = torch.cuda.CUDAGraph()
         with _C.async_binning(cap):
             with torch.cuda.graph(self.graph):
@@ -252,14 +256,13 @@ class GraphedTracker:
                     self.graph.replay()
                 st = self.st
                 flag = self.capacity.infos[0][3:4].to(torch.float32)
-                host = torch.cat((st["cand_rot"], st["cand_tran"], st["min_loss"].reshape(1), st["cam_rot"].detach(),
-                                  st["cam_tran"].detach(), st["last_loss"].reshape(1), flag)).cpu()   # the frame's one sync
-                if host[16] == 0 or retries >= max_retries:
+                host = torch.cat((st["state"], st["cam_rot"], st["cam_tran"], flag)).cpu()     # the frame's one sync
+                if host[31] == 0 or retries >= max_retries:
                     break
                 retries += 1          # the frame outgrew the binning capacity: re-capture larger and repeat it
                 at_least = _C.BinningCapacity.from_info(self.capacity.infos[0], 1.3)
                 self.graph = None
-            if host[16] != 0:
+            if host[31] != 0:
                 raise RuntimeError("tracking frame does not fit the binning capacity after re-captures")
-        return dict(rot=host[0:4].clone(), tran=host[4:7].clone(), loss=float(host[7]), last_rot=host[8:12].clone(),
-                    last_tran=host[12:15].clone(), last_loss=float(host[15]), retries=retries)
+        return dict(rot=host[16:20].clone(), tran=host[20:23].clone(), loss=float(host[15]), last_rot=host[24:28].clone(),
+                    last_tran=host[28:31].clone(), last_loss=float(host[23]), retries=retries)

@@ -138,6 +138,26 @@ int hs_masked_l1(const float* pred, const float* target, const unsigned char* ma
 int hs_hier_cross_entropy(const float* sem, const int* labels, int levels, const int* level_begin,
                           const float* level_scale, size_t pixels, float* loss, float* grad, void* stream);
 
+/* Extension: the steps of a tracking iteration between the rasterizer calls
+ * (scripts/hierslam.py:1837-1856, get_loss_semantic(tracking=True) :765-796, transform_to_frame utils/slam_helpers.py:278-330),
+ * each as one kernel so that a whole iteration is ~14 launches and stream-capturable.
+ * hs_transform_points: cam[P,3] = R world + t for the row-major 4x4 w2c (device).
+ * hs_tracking_loss: mask = gt_depth > 0 && !isnan(depth) [&& silhouette > sil_thres]; loss[0] (device, accumulated) +=
+ *   depth_weight * sum_mask |gt_depth - depth| + im_weight * sum_mask sum_c |gt_im - im|; grad_im[3,pixels], grad_depth[pixels]
+ *   = d loss / d im, d loss / d depth.
+ * hs_pose_step (mode 1): best-candidate bookkeeping with loss[0], which is then reset to 0; dL_dpose[3,4] (hs_backward) ->
+ *   gradient of the unnormalised quaternion cam_rot[4] (r,x,y,z) and translation cam_tran[3]; torch.optim.Adam's update with
+ *   per-tensor learning rates; w2c[16] of the updated pose.  state: HS_POSE_STATE_FLOATS floats (device) = exp_avg[7] |
+ *   exp_avg_sq[7] | step | min_loss | candidate rot[4] | candidate tran[3] | last loss; the caller zeroes it and sets
+ *   min_loss large at frame start.  mode 0: only write w2c for the current pose. */
+#define HS_POSE_STATE_FLOATS 24
+int hs_transform_points(const float* w2c, const float* world, int P, float* cam, void* stream);
+int hs_tracking_loss(const float* im, const float* depth, const float* silhouette, const float* gt_im,
+                     const float* gt_depth, size_t pixels, float sil_thres, int use_silhouette, float depth_weight,
+                     float im_weight, float* loss, float* grad_im, float* grad_depth, void* stream);
+int hs_pose_step(float* cam_rot, float* cam_tran, const float* dL_dpose, float* loss, float* state, float* w2c,
+                 float lr_rot, float lr_tran, float beta1, float beta2, float eps, int mode, void* stream);
+
 /* Extension (parameter maintenance): torch.optim.Adam's update (scripts/hierslam.py:411-417;
  * torch/optim/adam.py::_multi_tensor_adam, no weight decay / amsgrad) for every parameter tensor in ONE pass over flat
  * buffers.  param / grad / exp_avg / exp_avg_sq: n floats each (device, n a multiple of 4); segment s covers the floats
