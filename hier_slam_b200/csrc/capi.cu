@@ -401,6 +401,16 @@ int hs_pose_step(float* cam_rot, float* cam_tran, const float* dL_dpose, float* 
                             (cudaStream_t)stream_);
 }
 
+int hs_keyframe_overlap(const float* points, int num_points, const float* w2c, int keyframes, float fx, float fy, float cx,
+                        float cy, int width, int height, int edge, int* counts, void* stream_) {
+    if (keyframes > 0 && (w2c == nullptr || counts == nullptr || (num_points > 0 && points == nullptr))) {
+        set_error("hs_keyframe_overlap: NULL argument");
+        return 1;
+    }
+    return launch_keyframe_overlap(points, num_points, w2c, keyframes, fx, fy, cx, cy, width, height, edge, counts,
+                                   (cudaStream_t)stream_);
+}
+
 int hs_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, int segments,
                  const unsigned long long* segment_end, const double* segment_lr, double beta1, double beta2, double eps,
                  int step, void* stream_) {

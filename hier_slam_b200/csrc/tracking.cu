@@ -164,4 +164,47 @@ int launch_pose_step(float* cam_rot, float* cam_tran, const float* dL_dpose, flo
     return 0;
 }
 
+
+// Keyframe selection (utils/keyframe_selection.py:40-96): for every keyframe, how many of the sampled world points project
+// inside its image (minus an edge margin) with positive depth.  The reference loops over the keyframes in Python (~10 torch
+// kernels and one host sync each); here one CTA per keyframe counts all points.
+__global__ void __launch_bounds__(256) keyframe_overlap_kernel(const float* __restrict__ pts, int N,
+                                                               const float* __restrict__ w2c, float fx, float fy, float cx,
+                                                               float cy, float width, float height, float edge,
+                                                               int* __restrict__ counts) {
+    __shared__ float m[12];
+    __shared__ int s_part[8];
+    if (threadIdx.x < 12) m[threadIdx.x] = w2c[(size_t)blockIdx.x * 16 + threadIdx.x];
+    __syncthreads();
+    int c = 0;
+    for (int i = threadIdx.x; i < N; i += 256) {
+        const float x = pts[3 * i], y = pts[3 * i + 1], z = pts[3 * i + 2];
+        const float X = fmaf(z, m[2], fmaf(y, m[1], fmaf(x, m[0], m[3])));
+        const float Y = fmaf(z, m[6], fmaf(y, m[5], fmaf(x, m[4], m[7])));
+        const float Z = fmaf(z, m[10], fmaf(y, m[9], fmaf(x, m[8], m[11])));
+        const float pz = Z + 1e-5f;                                  // points_z = points_2d[:, 2:] + 1e-5
+        const float u = fmaf(cx, Z, fx * X) / pz, v = fmaf(cy, Z, fy * Y) / pz;
+        c += (u < width - edge && u > edge && v < height - edge && v > edge && pz > 0.f) ? 1 : 0;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) t += s_part[w];
+        counts[blockIdx.x] = t;
+    }
+}
+
+int launch_keyframe_overlap(const float* pts, int N, const float* w2c, int K, float fx, float fy, float cx, float cy, int width,
+                            int height, int edge, int* counts, cudaStream_t stream) {
+    if (K <= 0) return 0;
+    keyframe_overlap_kernel<<<K, 256, 0, stream>>>(pts, N, w2c, fx, fy, cx, cy, (float)width, (float)height, (float)edge,
+                                                   counts);
+    HS_LAUNCH_OK(stream, false);
+    return 0;
+}
+
 }  // namespace hs

@@ -158,6 +158,12 @@ int hs_tracking_loss(const float* im, const float* depth, const float* silhouett
 int hs_pose_step(float* cam_rot, float* cam_tran, const float* dL_dpose, float* loss, float* state, float* w2c,
                  float lr_rot, float lr_tran, float beta1, float beta2, float eps, int mode, void* stream);
 
+/* Extension: keyframe selection by re-projection (utils/keyframe_selection.py:40-96).
+ * counts[k] (int32, device) = number of the num_points world points[.,3] that project into keyframe k's image
+ * (w2c[k] row-major 4x4, pinhole fx fy cx cy) with edge < u < width - edge, edge < v < height - edge and depth + 1e-5 > 0. */
+int hs_keyframe_overlap(const float* points, int num_points, const float* w2c, int keyframes, float fx, float fy, float cx,
+                        float cy, int width, int height, int edge, int* counts, void* stream);
+
 /* Extension (parameter maintenance): torch.optim.Adam's update (scripts/hierslam.py:411-417;
  * torch/optim/adam.py::_multi_tensor_adam, no weight decay / amsgrad) for every parameter tensor in ONE pass over flat
  * buffers.  param / grad / exp_avg / exp_avg_sq: n floats each (device, n a multiple of 4); segment s covers the floats

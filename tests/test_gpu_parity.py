@@ -687,6 +687,34 @@ def test_graphed_tracker_matches_the_eager_tracking_loop():
         assert float((again["tran"] - out["tran"]).abs().max()) < 1e-5 and again["retries"] == 0
 
 
+def test_keyframe_overlap_counts_match_the_reference_loop():
+    """hier_slam_b200.keyframes.keyframe_overlap_counts == the per-keyframe torch code of
+    utils/keyframe_selection.py:70-88 (transform, project, edge test, count), for 37 keyframes at once."""
+    from hier_slam_b200.keyframes import keyframe_overlap_counts
+    from hier_slam_b200.scene import keyframe_poses
+    g = torch.Generator().manual_seed(71)
+    W, H = 1200, 680
+    K = torch.tensor([[600.0, 0, 599.5], [0, 600.0, 339.5], [0, 0, 1]]).cuda()
+    z = 0.5 + 5 * torch.rand(1600, generator=g)
+    pts = torch.stack(((torch.rand(1600, generator=g) * W - 599.5) * z / 600, (torch.rand(1600, generator=g) * H - 339.5) * z / 600,
+                       z), 1).cuda()
+    poses = keyframe_poses(37, seed=5, max_angle_deg=40.0, max_trans=1.5).cuda()
+    poses[3] = torch.diag(torch.tensor([-1.0, 1, -1, 1])).cuda()        # looking backwards: nothing visible
+    got = keyframe_overlap_counts(pts, poses, K, W, H).cpu()
+    want = []
+    for est_w2c in poses:
+        pts4 = torch.cat([pts, torch.ones_like(pts[:, :1])], dim=1)
+        t = (est_w2c @ pts4.T).T[:, :3]
+        p2 = torch.matmul(K, t.transpose(0, 1)).transpose(0, 1)
+        pz = p2[:, 2:] + 1e-5
+        p2 = (p2 / pz)[:, :2]
+        m = (p2[:, 0] < W - 20) * (p2[:, 0] > 20) * (p2[:, 1] < H - 20) * (p2[:, 1] > 20)
+        want.append(int((m & (pz[:, 0] > 0)).sum()))
+    want = torch.tensor(want, dtype=torch.int32)
+    assert int((got - want).abs().max()) <= 1, (got, want)      # a point within float rounding of the margin may flip
+    assert int(got[3]) == 0 and int(got.max()) > 1000
+
+
 def test_full_size_properties_c2():
     """BASELINE.json config 2 at full size (1200x680, 300K Gaussians, S=26): properties that need no oracle."""
     C, Settings = new_impl()
