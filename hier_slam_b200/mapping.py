@@ -60,6 +60,28 @@ class FlatParams:
                 from . import _C
                 _C.register_grad_sink(leaf, leaf.grad)
 
+    @torch.no_grad()
+    def appended(self, new_rows: Dict[str, torch.Tensor]) -> "FlatParams":
+        """A new parameter set with `new_rows[name]` ([n, ...] each, same n) appended to every tensor -- what
+        add_new_gaussians (scripts/hierslam.py:1307-1352: torch.cat per parameter) and cat_params_to_optimizer
+        (utils/slam_external.py:124-139) do -- laid out in fresh flat buffers.  This set is left untouched; call
+        release() on it when it is dropped."""
+        n = {int(v.shape[0]) for v in new_rows.values()}
+        if set(new_rows) != set(self.names) or len(n) != 1:
+            raise RuntimeError("appended(): one [n, ...] tensor per parameter name, all with the same n")
+        n = n.pop()
+        shapes = {k: (self.shapes[k][0] + n,) + tuple(self.shapes[k][1:]) for k in self.names}
+        new = FlatParams.empty(shapes, self.flat.device, self.direct_grads)
+        for k in self.names:
+            if tuple(new_rows[k].shape[1:]) != tuple(self.shapes[k][1:]):
+                raise RuntimeError(f"appended(): {k} rows have shape {tuple(new_rows[k].shape[1:])}, expected {self.shapes[k][1:]}")
+            old_n = int(torch.Size(self.shapes[k]).numel())
+            add_n = int(new_rows[k].numel())
+            o = new.offsets[k]
+            new.flat[o:o + old_n].copy_(self.flat[self.offsets[k]:self.offsets[k] + old_n])
+            new.flat[o + old_n:o + old_n + add_n].copy_(new_rows[k].detach().reshape(-1).float())
+        return new
+
     def release(self) -> None:
         """Drop the gradient-sink registrations of the leaves (a replaced parameter set must not keep its buffers alive)."""
         if self.direct_grads:

@@ -62,6 +62,21 @@ class FlatAdam:
                                         _stream(p.flat.device)), "hs_adam_step")
 
     @torch.no_grad()
+    def append(self, new_rows: Dict[str, torch.Tensor]) -> FlatParams:
+        """cat_params_to_optimizer (utils/slam_external.py:124-139): new Gaussians join every parameter tensor, their Adam
+        moments start at zero, the moments of the existing rows are kept.  Returns (and installs) the new FlatParams."""
+        old = self.params
+        new = old.appended(new_rows)
+        new_m, new_v = torch.zeros_like(new.flat), torch.zeros_like(new.flat)
+        for k in old.names:
+            n = int(torch.Size(old.shapes[k]).numel())
+            for src, dst in ((self.exp_avg, new_m), (self.exp_avg_sq, new_v)):
+                dst[new.offsets[k]:new.offsets[k] + n].copy_(src[old.offsets[k]:old.offsets[k] + n])
+        old.release()
+        self.params, self.exp_avg, self.exp_avg_sq = new, new_m, new_v
+        return new
+
+    @torch.no_grad()
     def prune(self, keep: torch.Tensor) -> FlatParams:
         """Keep the rows (Gaussians) where `keep` is true in every parameter tensor and in both Adam moments, in their
         original order; returns (and installs) the new FlatParams.  One host sync (the number of kept rows)."""

@@ -606,6 +606,15 @@ def test_flat_adam_prune_matches_boolean_indexing():
                 assert torch.equal(new.leaves[k].detach(), before[k][0][keep])
                 assert torch.equal(m, before[k][1][keep]) and torch.equal(v, before[k][2][keep])
                 assert new.leaves[k].grad is not None and new.leaves[k].grad.shape == new.leaves[k].shape
+    # cat_params_to_optimizer: appended rows start with zero moments, existing rows keep theirs
+    extra = {k: torch.randn(11, *shapes[k][1:], generator=g).cuda() for k in shapes}
+    kept = {k: (opt.params.leaves[k].detach().clone(),) + tuple(t.clone() for t in opt.state(k)) for k in shapes}
+    new = opt.append(extra)
+    for k in shapes:
+        m, v = opt.state(k)
+        assert torch.equal(new.leaves[k].detach(), torch.cat((kept[k][0], extra[k])))
+        assert torch.equal(m[:-11], kept[k][1]) and torch.equal(v[:-11], kept[k][2])
+        assert float(m[-11:].abs().max()) == 0.0 and float(v[-11:].abs().max()) == 0.0
 
 
 def test_render_depth_silhouette_is_bit_identical_to_the_semantic_render():
@@ -713,6 +722,49 @@ def test_keyframe_overlap_counts_match_the_reference_loop():
     want = torch.tensor(want, dtype=torch.int32)
     assert int((got - want).abs().max()) <= 1, (got, want)      # a point within float rounding of the margin may flip
     assert int(got[3]) == 0 and int(got.max()) > 1000
+
+
+def test_capacity_mode_matches_the_synchronous_forward():
+    """HS_ASYNC_BINNING (`_C.async_binning`): with a sufficient capacity the public API returns bit-identical images and
+    the same gradients as the synchronous path without reading num_rendered back; with an insufficient one the overflow
+    flag is raised, the frame renders empty and nothing is written out of bounds."""
+    import diff_gaussian_rasterization as ours
+    C, Settings = new_impl()
+    cfg = CONFIGS["small"]
+    scene = make_scene(cfg, 3, device="cuda")
+    settings = pt.make_settings(Settings, cfg)
+    raster = ours.GaussianRasterizer_semantic(settings)
+    ug = {k: v.cuda() for k, v in upstream_grads(cfg, 1).items()}
+
+    def run():
+        leaves = {k: v.clone().requires_grad_(True) for k, v in scene.items()}
+        out = raster(means3D=leaves["means3D"], means2D=torch.zeros_like(leaves["means3D"]), opacities=leaves["opacities"],
+                     colors_precomp=leaves["colors_precomp"], scales=leaves["scales"], rotations=leaves["rotations"],
+                     semantics_precomp=leaves["semantics_precomp"])
+        color, radii, sem, depth, median, opac = out
+        torch.autograd.backward((color, sem, depth, median, opac),
+                                (ug["color"], ug["semantic"], ug["depth"], ug["median_depth"], ug["final_opacity"]))
+        return out, {k: v.grad for k, v in leaves.items()}
+    ref_out, ref_grads = run()
+    f = pt.run_forward(C, settings, scene)
+    info = C.binning_info(f["imgBuffer"], cfg.height, cfg.width)
+    assert int(info[0]) == f["R"] and int(info[3]) == 0
+    cap = C.BinningCapacity.from_info(info, 1.1, extra_instances=1000, extra_tile=16)
+    with C.async_binning(cap):
+        out, grads = run()
+    assert not cap.overflowed() and len(cap.infos) == 1 and int(cap.infos[0][0]) == f["R"]
+    for a, b in zip(out, ref_out):
+        assert torch.equal(a, b)
+    for k in grads:
+        assert_grads_close(grads[k], ref_grads[k], k, tol=1e-5)
+    for small in (C.BinningCapacity(f["R"] - 1, 16384), C.BinningCapacity(2 * f["R"], max(int(info[1]) - 1, 1))):
+        with C.async_binning(small):
+            out, grads = run()
+        assert small.overflowed()
+        assert float(out[0].abs().max()) == 0.0 and float(out[5].abs().max()) == 0.0     # empty render
+        assert all(bool(torch.isfinite(g).all()) for g in grads.values())
+    out, _ = run()                                            # the synchronous path is unaffected afterwards
+    assert torch.equal(out[0], ref_out[0])
 
 
 def test_full_size_properties_c2():

@@ -122,3 +122,22 @@ def test_flat_adam_is_cuda_only():
     from hier_slam_b200.optim import FlatAdam
     with pytest.raises(RuntimeError, match="CUDA-only"):
         FlatAdam(FlatParams({"x": torch.ones(5, 3)}), {"x": 1e-3})
+
+
+def test_flat_params_appended_matches_torch_cat():
+    """FlatParams.appended == torch.cat((param, new_rows)) per parameter (add_new_gaussians / cat_params_to_optimizer),
+    in fresh 64-float-aligned buffers; the source set is untouched."""
+    import torch
+    from hier_slam_b200.mapping import FlatParams
+    g = torch.Generator().manual_seed(5)
+    a = {"means3D": torch.randn(37, 3, generator=g), "logit_opacities": torch.randn(37, 1, generator=g),
+         "semantic": torch.randn(37, 26, generator=g)}
+    extra = {"means3D": torch.randn(9, 3, generator=g), "logit_opacities": torch.randn(9, 1, generator=g),
+             "semantic": torch.randn(9, 26, generator=g)}
+    p = FlatParams({k: v.clone() for k, v in a.items()})
+    q = p.appended(extra)
+    for k in a:
+        assert torch.equal(q.leaves[k].detach(), torch.cat((a[k], extra[k]))) and torch.equal(p.leaves[k].detach(), a[k])
+        assert q.leaves[k].grad.shape == q.leaves[k].shape and q.offsets[k] % 64 == 0
+    with pytest.raises(RuntimeError, match="same n"):
+        p.appended({"means3D": extra["means3D"]})
