@@ -50,9 +50,9 @@ __device__ __forceinline__ void mma_p(float (&d)[4], float (&dc)[4], const float
 
 constexpr int NWARP = 8;
 
-template <int NJ> struct Cfg {
+template <int NJ, int MTV = (NJ <= 4 ? 2 : 1)> struct Cfg {
     static constexpr int SP = 8 * NJ;                 // padded channel count: S + 1 ("ones" channel = bias) rounded to 8
-    static constexpr int MT = NJ <= 4 ? 2 : 1;        // 16-pixel row tiles per warp
+    static constexpr int MT = MTV;                    // 16-pixel row tiles per warp
     static constexpr int BPX = NWARP * 16 * MT;       // pixels per block iteration
     static constexpr int XS = BPX + 8;                // row stride of Xs: == 8 (mod 32) -> conflict-free A-fragment loads
     static constexpr int WS = SP + 4;                 // row stride of Ws: == 4, 20 or 28 (mod 32) -> conflict-free B loads
@@ -64,10 +64,10 @@ template <int NJ> struct Cfg {
 
 // Xs[s][p] = sem[s][px0 + p] for s < S, 1 for s == S (bias channel), 0 above; pixels beyond the image are 0.  Full
 // 4-pixel groups of real channels travel with 16-byte cp.async (the caller commits / waits), the rest is stored directly.
-template <int NJ>
+template <int NJ, int MTV = (NJ <= 4 ? 2 : 1)>
 __device__ __forceinline__ void stage_pixels(float* Xs, const float* __restrict__ sem, int S, size_t HW, size_t px0,
                                              bool vec_ok) {
-    using C = Cfg<NJ>;
+    using C = Cfg<NJ, MTV>;
     for (int idx = threadIdx.x; idx < C::SP * (C::BPX / 4); idx += 32 * NWARP) {
         const int s = idx / (C::BPX / 4), p = (idx % (C::BPX / 4)) * 4;
         const size_t px = px0 + p;
@@ -98,10 +98,10 @@ __device__ __forceinline__ void stage_weights(float* Ws, const float* __restrict
 // z[mt][n][16 px x 8 classes] = X W^T for the MT row tiles of a warp (first pixel pxl) and the two class tiles
 // 2 np, 2 np + 1 of the staged weights.  A fragments are shared by the two class tiles, B fragments by the row tiles;
 // 4 MT (8 MT with the split correction accumulators) independent mma chains are in flight.
-template <int NJ, bool P3, bool SPLIT>
-__device__ __forceinline__ void logits_pair(float (&z)[Cfg<NJ>::MT][2][4], const float* Xs, const float* Ws, int pxl,
+template <int NJ, bool P3, bool SPLIT, int MTV = (NJ <= 4 ? 2 : 1)>
+__device__ __forceinline__ void logits_pair(float (&z)[MTV][2][4], const float* Xs, const float* Ws, int pxl,
                                             int np, int g, int t) {
-    using C = Cfg<NJ>;
+    using C = Cfg<NJ, MTV>;
     float zc[SPLIT ? C::MT : 1][2][4];            // SPLIT: the two correction products run as a second accumulator chain
 #pragma unroll
     for (int mt = 0; mt < C::MT; mt++)
@@ -310,6 +310,148 @@ __global__ void __launch_bounds__(32 * NWARP, Cfg<NJ>::OCC) leaf_ce_pixel_kernel
     }
 }
 
+// One-pass variant for class counts whose logits fit a warp's registers (L <= 16 LT, e.g. Replica's 102 leaves): a warp
+// owns ONE 16-pixel row tile, keeps all its logits (4 LT floats... 8 LT per thread) after the first contraction, and the
+// softmax / gradient pass reuses them instead of recomputing Z: 24 instead of 36 MMAs per (row tile, 16 classes).
+template <int NJ, bool P3, int LT>
+__global__ void __launch_bounds__(32 * NWARP, 2) leaf_ce_pixel_onepass_kernel(
+    const float* __restrict__ sem, const int* __restrict__ labels, const float* __restrict__ weight,
+    const float* __restrict__ bias, int S, int L, size_t HW, float scale, float* __restrict__ loss,
+    float* __restrict__ lse_out, float* __restrict__ grad_sem, int accumulate) {
+    using C = Cfg<NJ, 1>;
+    extern __shared__ float smem[];
+    float* Xbuf = smem;                           // [2][SP][XS]
+    float* Ws = smem + 2 * C::SP * C::XS;         // [16 LT][WS], resident
+    __shared__ float s_part[NWARP];
+    const bool vec_ok = (HW & 3) == 0 && (reinterpret_cast<size_t>(sem) & 15) == 0;
+    stage_weights<NJ>(Ws, weight, bias, S, L, 0, 16 * LT);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int pxl = warp * 16;
+    const int npairs = (L + 15) >> 4;
+    const size_t n_blocks = (HW + C::BPX - 1) / C::BPX;
+    float loss_acc = 0.f;
+    int buf = 0;
+    if (blockIdx.x < n_blocks) stage_pixels<NJ, 1>(Xbuf, sem, S, HW, (size_t)blockIdx.x * C::BPX, vec_ok);
+    __pipeline_commit();
+    for (size_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x, buf ^= 1) {
+        const size_t px0 = blk * C::BPX;
+        const float* Xs = Xbuf + buf * C::SP * C::XS;
+        __pipeline_wait_prior(0);
+        __syncthreads();
+        if (blk + gridDim.x < n_blocks)
+            stage_pixels<NJ, 1>(Xbuf + (buf ^ 1) * C::SP * C::XS, sem, S, HW, (blk + gridDim.x) * C::BPX, vec_ok);
+        __pipeline_commit();
+        int y[2];
+        float sc[2], m[2] = {-1.0e30f, -1.0e30f}, zy[2] = {0.f, 0.f};
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            const size_t px = px0 + pxl + g + 8 * r;
+            const int lab = px < HW ? labels[px] : -1;
+            const bool use = lab >= 0 && lab < L;
+            y[r] = use ? lab : -1;
+            sc[r] = use ? scale : 0.f;
+        }
+        float z[LT][1][2][4];
+#pragma unroll
+        for (int np = 0; np < LT; np++) {
+            if (np >= npairs) continue;                         // warp-uniform
+            logits_pair<NJ, P3, true, 1>(z[np], Xs, Ws, pxl, np, g, t);
+#pragma unroll
+            for (int n = 0; n < 2; n++) {
+                const int l0 = 16 * np + 8 * n + 2 * t;
+#pragma unroll
+                for (int r = 0; r < 2; r++) {
+                    if (l0 >= L) z[np][0][n][2 * r] = -3.0e38f;
+                    if (l0 + 1 >= L) z[np][0][n][2 * r + 1] = -3.0e38f;
+                    m[r] = fmaxf(m[r], fmaxf(z[np][0][n][2 * r], z[np][0][n][2 * r + 1]));
+                    if (l0 == y[r]) zy[r] = z[np][0][n][2 * r];
+                    if (l0 + 1 == y[r]) zy[r] = z[np][0][n][2 * r + 1];
+                }
+            }
+        }
+        float lse[2];
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            m[r] = fmaxf(m[r], __shfl_xor_sync(0xffffffffu, m[r], 1));
+            m[r] = fmaxf(m[r], __shfl_xor_sync(0xffffffffu, m[r], 2));
+            zy[r] += __shfl_xor_sync(0xffffffffu, zy[r], 1);
+            zy[r] += __shfl_xor_sync(0xffffffffu, zy[r], 2);
+        }
+        float sum[2] = {0.f, 0.f};
+#pragma unroll
+        for (int np = 0; np < LT; np++) {
+            if (np >= npairs) continue;
+#pragma unroll
+            for (int n = 0; n < 2; n++)
+#pragma unroll
+                for (int q = 0; q < 4; q++) {                   // z becomes exp(z - max); masked classes give 0
+                    z[np][0][n][q] = __expf(z[np][0][n][q] - m[q >> 1]);
+                    sum[q >> 1] += z[np][0][n][q];
+                }
+        }
+        float inv[2];
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], 1);
+            sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], 2);
+            lse[r] = m[r] + __logf(sum[r]);
+            inv[r] = sc[r] / sum[r];
+            const size_t px = px0 + pxl + g + 8 * r;
+            if (t == 0 && px < HW) {
+                lse_out[px] = lse[r];
+                loss_acc += sc[r] * (lse[r] - zy[r]);
+            }
+        }
+        float dx[NJ][4];
+#pragma unroll
+        for (int j = 0; j < NJ; j++) dx[j][0] = dx[j][1] = dx[j][2] = dx[j][3] = 0.f;
+#pragma unroll
+        for (int np = 0; np < LT; np++) {
+            if (np >= npairs) continue;
+#pragma unroll
+            for (int n = 0; n < 2; n++) {
+                const int l0 = 16 * np + 8 * n + 2 * t;
+                float ga[4], gl[4];
+#pragma unroll
+                for (int r = 0; r < 2; r++) {                   // a0 = G(g, 2t), a1 = G(g+8, 2t), a2 = G(g, 2t+1), a3 = G(g+8, 2t+1)
+                    ga[r] = z[np][0][n][2 * r] * inv[r] - (l0 == y[r] ? sc[r] : 0.f);
+                    ga[2 + r] = z[np][0][n][2 * r + 1] * inv[r] - (l0 + 1 == y[r] ? sc[r] : 0.f);
+                }
+                if (P3) lo_parts(gl, ga);
+                const float* w0 = Ws + (16 * np + 8 * n + 2 * t) * C::WS + g;
+#pragma unroll
+                for (int j = 0; j < NJ; j++) {
+                    const float b[2] = {w0[8 * j], w0[C::WS + 8 * j]};
+                    float bl[2];
+                    if (P3) lo_parts(bl, b);
+                    mma_p<P3>(dx[j], dx[j], ga, gl, b, bl);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < NJ; j++)
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int s = 8 * j + 2 * t + (q & 1);
+                const size_t px = px0 + pxl + g + 8 * (q >> 1);
+                if (s < S && px < HW) {
+                    float* dst = grad_sem + (size_t)s * HW + px;
+                    *dst = accumulate ? *dst + dx[j][q] : dx[j][q];
+                }
+            }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) loss_acc += __shfl_xor_sync(0xffffffffu, loss_acc, o);
+    if (lane == 0) s_part[warp] = loss_acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float tot = 0.f;
+#pragma unroll
+        for (int w = 0; w < NWARP; w++) tot += s_part[w];
+        atomicAdd(loss, tot);
+    }
+}
+
 template <int NJ, bool P3>
 __global__ void __launch_bounds__(32 * NWARP, 2) leaf_ce_weight_kernel(
     const float* __restrict__ sem, const int* __restrict__ labels, const float* __restrict__ weight,
@@ -426,7 +568,16 @@ static int launch_t(const float* sem, const int* labels, const float* weight, co
                     float* grad_bias, cudaStream_t stream) {
     using C = Cfg<NJ>;
     const size_t n_blocks = (HW + C::BPX - 1) / C::BPX;
-    {
+    constexpr int LT = 7;                     // one-pass variant: up to 112 classes
+    if (NJ <= 4 && L <= 16 * LT) {
+        using C1 = Cfg<NJ, 1>;
+        auto k = leaf_ce_pixel_onepass_kernel<NJ, P3, (NJ <= 4 ? LT : 1)>;
+        const size_t sh = (size_t)(2 * C1::SP * C1::XS + 16 * LT * C1::WS) * sizeof(float);
+        HS_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+        const int grid = (int)min((size_t)148 * 2, (HW + C1::BPX - 1) / C1::BPX);
+        k<<<grid, 32 * NWARP, sh, stream>>>(sem, labels, weight, bias, S, L, HW, scale, loss, lse, grad_sem, accumulate);
+        HS_LAUNCH_OK(stream, false);
+    } else {
         auto k = leaf_ce_pixel_kernel<NJ, P3>;
         const size_t sh = (size_t)(2 * C::SP * C::XS + C::LC * C::WS) * sizeof(float);
         HS_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));

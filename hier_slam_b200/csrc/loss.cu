@@ -51,8 +51,8 @@ int launch_masked_l1(const float* pred, const float* target, const uint8_t* mask
 // :91-111): the S rendered channels are the concatenation of L levels; level l owns channels [begin[l], begin[l+1]) and
 // contributes weight * mean_pixels CE(softmax(slice), label_l).  The reference evaluates every level with a permute +
 // view (a transposing copy of the slice), a CrossEntropyLoss forward and its backward; this kernel reads each channel
-// plane once more than strictly needed (max/sum pass, gradient pass) and writes d loss / d sem directly in the planar
-// [S,H,W] layout the rasterizer's backward consumes.  One thread per pixel, coalesced across the plane.
+// plane exactly once (a level's channels live in registers) and writes d loss / d sem directly in the planar [S,H,W]
+// layout the rasterizer's backward consumes.  One thread per pixel, coalesced across the plane.
 namespace hs {
 
 struct HierLevels {
@@ -61,6 +61,32 @@ struct HierLevels {
     float scale[HS_MAX_LEVELS];   // weight_l / (number of pixels whose label is not ignored)
 };
 
+// One level of one pixel with the level's channels held in registers: every channel plane is read ONCE (all loads of a
+// level are independent and in flight together), one exp per channel.  N = register capacity (channels of the level <= N).
+template <int N>
+__device__ __forceinline__ float level_ce(const float* __restrict__ sem, float* __restrict__ grad, size_t HW, size_t p, int b,
+                                          int n, int y, float scale) {
+    float x[N];
+#pragma unroll
+    for (int c = 0; c < N; c++) x[c] = c < n ? sem[(size_t)(b + c) * HW + p] : -3.0e38f;
+    float m = x[0];
+#pragma unroll
+    for (int c = 1; c < N; c++) m = fmaxf(m, x[c]);
+    float z = 0.f, xy = 0.f;
+#pragma unroll
+    for (int c = 0; c < N; c++) {
+        if (c == y) xy = x[c];
+        x[c] = c < n ? __expf(x[c] - m) : 0.f;
+        z += x[c];
+    }
+    const bool use = y >= 0 && y < n;                   // torch's ignore_index (-100) and out-of-range labels
+    const float sc = use ? scale : 0.f, inv = sc / z;
+#pragma unroll
+    for (int c = 0; c < N; c++)
+        if (c < n) grad[(size_t)(b + c) * HW + p] = x[c] * inv - (c == y ? sc : 0.f);
+    return use ? sc * (m + __logf(z) - xy) : 0.f;
+}
+
 __global__ void __launch_bounds__(256) hier_ce_kernel(const float* __restrict__ sem, const int* __restrict__ labels,
                                                       HierLevels lv, size_t HW, float* __restrict__ loss,
                                                       float* __restrict__ grad) {
@@ -68,20 +94,11 @@ __global__ void __launch_bounds__(256) hier_ce_kernel(const float* __restrict__ 
     float acc = 0.f;
     for (size_t p = (size_t)blockIdx.x * 256 + threadIdx.x; p < HW; p += (size_t)gridDim.x * 256) {
         for (int l = 0; l < lv.L; l++) {
-            const int b = lv.begin[l], e = lv.begin[l + 1];
+            const int b = lv.begin[l], n = lv.begin[l + 1] - b;
             const int y = labels[(size_t)l * HW + p];
-            const bool use = y >= 0 && y < e - b;           // torch's ignore_index (-100) and out-of-range labels
-            float m = -3.0e38f;
-            for (int c = b; c < e; c++) m = fmaxf(m, sem[(size_t)c * HW + p]);
-            float z = 0.f;
-            for (int c = b; c < e; c++) z += __expf(sem[(size_t)c * HW + p] - m);
-            const float inv = 1.f / z, sc = use ? lv.scale[l] : 0.f;
-            for (int c = b; c < e; c++) {
-                const float x = sem[(size_t)c * HW + p];
-                const float sm = __expf(x - m) * inv;
-                grad[(size_t)c * HW + p] = sc * (sm - ((c - b) == y ? 1.f : 0.f));
-                if (use && (c - b) == y) acc += sc * (m + __logf(z) - x);
-            }
+            if (n <= 8) acc += level_ce<8>(sem, grad, HW, p, b, n, y, lv.scale[l]);
+            else if (n <= 16) acc += level_ce<16>(sem, grad, HW, p, b, n, y, lv.scale[l]);
+            else acc += level_ce<32>(sem, grad, HW, p, b, n, y, lv.scale[l]);
         }
     }
 #pragma unroll
@@ -103,6 +120,12 @@ int launch_hier_cross_entropy(const float* sem, const int* labels, int L, const 
         set_error("hierarchical cross-entropy: at most %d levels", HS_MAX_LEVELS);
         return 1;
     }
+    for (int l = 0; l < L; l++)
+        if (level_begin[l + 1] - level_begin[l] < 1 || level_begin[l + 1] - level_begin[l] > 32) {
+            set_error("hierarchical cross-entropy: 1..32 channels per level supported (level %d has %d)", l,
+                      level_begin[l + 1] - level_begin[l]);
+            return 1;
+        }
     HierLevels lv;
     lv.L = L;
     for (int l = 0; l <= L; l++) lv.begin[l] = level_begin[l];
