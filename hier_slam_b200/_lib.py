@@ -111,7 +111,7 @@ def load() -> ctypes.CDLL:
     lib.hs_profile_read.argtypes = [POINTER(c_float), POINTER(c_int)]
     lib.hs_kernel_launch_count.restype = ctypes.c_longlong
     lib.hs_library_call_count.restype = ctypes.c_longlong
-    if lib.hs_abi_version() != 2:
+    if lib.hs_abi_version() != 3:
         raise ImportError("libhsraster.so ABI version mismatch; rebuild with `python -m hier_slam_b200.build --force`")
     _lib = lib
     return lib

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define HS_RASTER_ABI_VERSION 2
+#define HS_RASTER_ABI_VERSION 3
 
 /* flags (bit-or) */
 #define HS_SEM_ALPHA_EXACT 1 /* backward: semantic channels contribute to dL/dalpha (the mathematically intended
