@@ -77,6 +77,24 @@ class async_binning:
         return False
 
 
+_recorder: Optional[list] = None
+
+
+class record_binning:
+    """with record_binning() as infos: the int32[4] binning counts of every forward inside are appended to `infos`
+    (used to size a BinningCapacity from synchronous renders)."""
+
+    def __enter__(self):
+        global _recorder
+        self.prev, _recorder = _recorder, []
+        return _recorder
+
+    def __exit__(self, *exc):
+        global _recorder
+        _recorder = self.prev
+        return False
+
+
 def binning_info(imgBuffer: torch.Tensor, H: int, W: int) -> torch.Tensor:
     """int32[4] view {num_rendered, longest tile list, short lists, capacity overflow} into a forward's image buffer"""
     off = _lib.load().hs_image_state_info_offset(int(H), int(W))
@@ -245,6 +263,8 @@ def _forward(background, means3D, colors, semantics, opacity, scales, rotations,
         num_rendered = int(R.value)          # capacity mode: the capacity (the counts stay on the device)
         if cap is not None:
             cap.infos.append(binning_info(imgBuffer, H, W))
+        if _recorder is not None and not SORT_GLOBAL:
+            _recorder.append(binning_info(imgBuffer, H, W))
         bin_bytes = lib.hs_binning_state_bytes(num_rendered)
         binningBuffer = torch.empty(bin_bytes, **byte)
         out_color = torch.empty(3, H, W, **fopt)

@@ -927,8 +927,17 @@ def test_keyframe_parallel_mapping_gradient_sum():
         acc += p1.flat_grad
     assert_grads_close(total, acc, "sum of keyframe gradients", tol=1e-5)
     assert float(total.abs().max()) > 0
-    # gradient sinks (dL/dcolors, dL/dsemantics accumulated straight into the flat buffer) == plain autograd
+    # capacity mode (sync-free forwards, one overflow check per iteration): same gradient; an undersized capacity is
+    # detected and the iteration is repeated synchronously
     from hier_slam_b200 import _C
+    from hier_slam_b200.mapping import capacity_for
+    cap = capacity_for(losses, params)
+    for c, overflow in ((cap, False), (_C.BinningCapacity(max(cap.instances // 50, 1), cap.longest_tile), True)):
+        pc = FlatParams(sc)
+        mapping_iteration(pc, losses, 0, 1, capacity=c)
+        assert c.overflowed() == overflow and len(c.infos) == 3
+        assert_grads_close(pc.flat_grad, total, "capacity-mode mapping iteration", tol=1e-5)
+    # gradient sinks (dL/dcolors, dL/dsemantics accumulated straight into the flat buffer) == plain autograd
     _C.clear_grad_sinks()
     plain = FlatParams(sc, direct_grads=False)
     mapping_iteration(plain, losses, 0, 1)

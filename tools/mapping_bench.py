@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import parity_tools as pt
 import diff_gaussian_rasterization as dgr
-from hier_slam_b200.mapping import FlatParams, mapping_iteration
+from hier_slam_b200.mapping import FlatParams, capacity_for, keyframes_of_rank, mapping_iteration
 from hier_slam_b200.scene import CONFIGS, keyframe_poses, make_scene, upstream_grads
 
 ap = argparse.ArgumentParser()
@@ -22,6 +22,7 @@ ap.add_argument("--config", default="c4")
 ap.add_argument("--keyframes", type=int, default=8)
 ap.add_argument("--iters", type=int, default=10)
 ap.add_argument("--warmup", type=int, default=3)
+ap.add_argument("--capacity", action="store_true", help="sync-free forwards (capacity-mode binning)")
 a = ap.parse_args()
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
@@ -53,15 +54,16 @@ def make_loss(k):
 
 losses = [make_loss(k) for k in range(a.keyframes)]
 params = FlatParams(sc)
+cap = capacity_for([losses[k] for k in keyframes_of_rank(a.keyframes, rank, world)], params) if a.capacity else None
 for _ in range(a.warmup):
-    mapping_iteration(params, losses, rank, world)
+    mapping_iteration(params, losses, rank, world, capacity=cap)
 if world > 1:
     dist.barrier()
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for _ in range(a.iters):
-    mapping_iteration(params, losses, rank, world)
+    mapping_iteration(params, losses, rank, world, capacity=cap)
 e1.record()
 if world > 1:
     dist.barrier()
@@ -73,6 +75,7 @@ if rank == 0:
     t = float(ms) / a.iters
     print(json.dumps(dict(workload=cfg.name, keyframes_per_iteration=a.keyframes, n_gpus=world, scaling="strong",
                           ms_per_iteration=round(t, 3), keyframes_per_s=round(a.keyframes / (t * 1e-3), 1),
-                          allreduce_bytes=params.grad_bytes(), gaussians=P, semantic_channels=cfg.num_semantic)))
+                          allreduce_bytes=params.grad_bytes(), gaussians=P, semantic_channels=cfg.num_semantic,
+                          capacity_mode=bool(a.capacity))))
 if world > 1:
     dist.destroy_process_group()
