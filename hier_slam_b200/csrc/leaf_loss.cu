@@ -56,10 +56,10 @@ template <int NJ, int MTV = (NJ <= 4 ? 2 : 1)> struct Cfg {
     static constexpr int BPX = NWARP * 16 * MT;       // pixels per block iteration
     static constexpr int XS = BPX + 8;                // row stride of Xs: == 8 (mod 32) -> conflict-free A-fragment loads
     static constexpr int WS = SP + 4;                 // row stride of Ws: == 4, 20 or 28 (mod 32) -> conflict-free B loads
-    static constexpr int LC = 128;                    // classes per staged weight chunk of the pixel kernel
+    static constexpr int LC = NJ <= 4 ? 128 : 64;     // classes per staged weight chunk of the pixel kernel (2 CTAs / SM)
     static constexpr int LG = NJ <= 4 ? 64 : 32;      // classes per CTA of the weight-gradient kernel
     static constexpr int GS = 20;                     // row stride of the warp-private G tiles (conflict-free)
-    static constexpr int OCC = NJ <= 4 ? 2 : 1;       // CTAs per SM of the pixel kernel (registers: dX is 4 NJ MT floats)
+    static constexpr int OCC = 2;                     // CTAs per SM of the pixel kernel
 };
 
 // Xs[s][p] = sem[s][px0 + p] for s < S, 1 for s == S (bias channel), 0 above; pixels beyond the image are 0.  Full
