@@ -460,7 +460,7 @@ def run_extras(a):
         g = torch.Generator().manual_seed(3)
         gt_im = torch.rand(3, H, W, generator=g).to(dev)
         gt_depth = (0.5 + 5 * torch.rand(1, H, W, generator=g)).to(dev)
-        labels = torch.stack([torch.randint(0, n, (H, W), generator=g) for n in sizes + [leaves_n]]).to(dev)
+        labels = torch.stack([torch.randint(0, n, (H, W), generator=g) for n in sizes + [leaves_n]]).int().to(dev)
         mask = gt_depth > 0.6
         n_mask = float(mask.sum())
         conv = torch.nn.Conv2d(cfg.num_semantic, leaves_n, kernel_size=1).to(dev)
@@ -472,7 +472,8 @@ def run_extras(a):
             conv_opt.zero_grad(set_to_none=True)
             im, radii, sem, depth, median, sil = render()
             loss = (masked_l1_sum(depth, gt_depth, mask) / n_mask + 0.5 * l1_ssim_loss(im, gt_im)
-                    + 0.2 * tree_semantic_loss(sem, labels, sizes, conv.weight, conv.bias, 1.0, 5.0, num_valid=H * W))
+                    + 0.2 * tree_semantic_loss(sem, labels, sizes, conv.weight, conv.bias, 1.0, 5.0, num_valid=H * W,
+                                             level_valid=H * W))
             loss.backward()
             opt.step()
             conv_opt.step()

@@ -6,7 +6,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_size_t, c_void_p
+from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_size_t, c_ulonglong, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("HS_LIB", os.path.join(HERE, "libhsraster.so"))
@@ -80,7 +80,6 @@ def load() -> ctypes.CDLL:
     lib.hs_leaf_cross_entropy.restype = c_int
     lib.hs_l1_ssim.argtypes = [vp, vp, c_int, c_int, c_int, POINTER(c_float), c_float, c_float, vp, vp, vp, vp]
     lib.hs_l1_ssim.restype = c_int
-    from ctypes import c_double, c_ulonglong
     lib.hs_adam_step.argtypes = [vp, vp, vp, vp, c_size_t, c_int, POINTER(c_ulonglong), POINTER(c_double), c_double, c_double,
                                  c_double, c_int, vp]
     lib.hs_adam_step.restype = c_int

@@ -55,7 +55,7 @@ def masked_l1_sum(pred: torch.Tensor, target: torch.Tensor, mask: torch.Tensor |
 
 class _HierCE(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, sem, labels, level_sizes, weights):
+    def forward(ctx, sem, labels, level_sizes, weights, level_valid):
         lib = _lib.load()
         if not sem.is_cuda or sem.dtype != torch.float32 or sem.dim() != 3:
             raise RuntimeError("sem must be a float32 CUDA tensor [S,H,W] (no CPU fallback)")
@@ -64,36 +64,31 @@ class _HierCE(torch.autograd.Function):
             raise RuntimeError("labels must be [levels,H,W] with at least len(level_sizes) levels")
         if sum(level_sizes) > sem.shape[0] or L > 8:
             raise RuntimeError("level_sizes must sum to at most S and have at most 8 levels")
-        s = sem.contiguous()
-        lab = labels[:L].to(torch.int32).contiguous()
-        HW = s[0].numel()
-        counts = (lab >= 0).reshape(L, -1).sum(1).clamp_min(1).tolist()     # torch's mean over the non-ignored pixels
-        begin = (ctypes.c_int * (L + 1))(*([0] + [sum(level_sizes[:i + 1]) for i in range(L)]))
-        scale = (ctypes.c_float * L)(*[float(weights[i]) / counts[i] for i in range(L)])
+        s = sem.detach().contiguous()
+        lab = labels[:L].to(torch.int32).contiguous()           # a no-op for int32 labels (convert once per keyframe)
         loss = torch.zeros((), dtype=torch.float32, device=s.device)
         grad = torch.zeros_like(s) if sum(level_sizes) < s.shape[0] else torch.empty_like(s)
         with torch.cuda.device(s.device):
-            stream = ctypes.c_void_p(torch.cuda.current_stream(s.device).cuda_stream)
-            _lib.check(lib.hs_hier_cross_entropy(ctypes.c_void_p(s.data_ptr()), ctypes.c_void_p(lab.data_ptr()), L, begin,
-                                                 scale, HW, ctypes.c_void_p(loss.data_ptr()),
-                                                 ctypes.c_void_p(grad.data_ptr()), stream), "hs_hier_cross_entropy")
+            _run_hier(lib, s, lab, level_sizes, weights, loss, grad, level_valid)
         ctx.save_for_backward(grad)
         return loss
 
     @staticmethod
     def backward(ctx, g):
         (grad,) = ctx.saved_tensors
-        return grad * g, None, None, None
+        return grad * g, None, None, None, None
 
 
-def hierarchical_cross_entropy(sem: torch.Tensor, labels: torch.Tensor, level_sizes, weights=None) -> torch.Tensor:
+def hierarchical_cross_entropy(sem: torch.Tensor, labels: torch.Tensor, level_sizes, weights=None,
+                               level_valid=None) -> torch.Tensor:
     """sum_l weights[l] * CrossEntropyLoss()(sem[begin_l:end_l].permute(1,2,0).view(-1, n_l), labels[l].view(-1))
     -- the inter-level loss of scripts/hierslam.py:955-1000 -- for the planar semantic map [S,H,W] the rasterizer
     returns, in one kernel, with the gradient written in the same planar layout.  labels: [levels,H,W] integer
-    (negative = ignored, like torch's ignore_index)."""
+    (negative = ignored, like torch's ignore_index; int32 labels are used as they are).  level_valid: the number of
+    non-ignored pixels per level if the caller knows it (H*W without ignored labels) -- saves a host sync."""
     level_sizes = [int(v) for v in level_sizes]
     weights = [1.0] * len(level_sizes) if weights is None else [float(w) for w in weights]
-    return _HierCE.apply(sem, labels, level_sizes, weights)
+    return _HierCE.apply(sem, labels, level_sizes, weights, level_valid)
 
 
 # HS_LEAF_TF32=1: one TF32 product per contraction in the leaf loss (torch's default convolution precision) instead of the
@@ -105,10 +100,13 @@ def _stream(dev):
     return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
 
-def _run_hier(lib, s, lab, level_sizes, weights, loss, grad):
+def _run_hier(lib, s, lab, level_sizes, weights, loss, grad, level_valid=None):
     """hs_hier_cross_entropy on contiguous sem [S,H,W] / int32 labels [L,H,W]; writes grad[: sum(level_sizes)]."""
     L = len(level_sizes)
-    counts = (lab >= 0).reshape(L, -1).sum(1).clamp_min(1).tolist()     # torch's mean over the non-ignored pixels
+    if level_valid is None:
+        counts = (lab >= 0).reshape(L, -1).sum(1).clamp_min(1).tolist()  # torch's mean over the non-ignored pixels (host sync)
+    else:
+        counts = [max(int(v), 1) for v in ([level_valid] * L if isinstance(level_valid, int) else level_valid)]
     begin = (ctypes.c_int * (L + 1))(*([0] + [sum(level_sizes[:i + 1]) for i in range(L)]))
     scale = (ctypes.c_float * L)(*[float(weights[i]) / counts[i] for i in range(L)])
     _lib.check(lib.hs_hier_cross_entropy(ctypes.c_void_p(s.data_ptr()), ctypes.c_void_p(lab.data_ptr()), L, begin, scale,
@@ -184,7 +182,7 @@ def leaf_cross_entropy(sem: torch.Tensor, labels: torch.Tensor, weight: torch.Te
 
 class _TreeLoss(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, sem, labels, weight, bias, level_sizes, level_weight, leaf_weight, num_valid):
+    def forward(ctx, sem, labels, weight, bias, level_sizes, level_weight, leaf_weight, num_valid, level_valid):
         lib = _lib.load()
         s, w2, b = _leaf_args(sem, weight, bias)
         nl = len(level_sizes)
@@ -196,7 +194,7 @@ class _TreeLoss(torch.autograd.Function):
         loss = torch.zeros((), dtype=torch.float32, device=s.device)
         grad = torch.zeros_like(s) if sum(level_sizes) < s.shape[0] else torch.empty_like(s)
         with torch.cuda.device(s.device):
-            _run_hier(lib, s, lab[:nl], level_sizes, [level_weight] * nl, loss, grad)
+            _run_hier(lib, s, lab[:nl], level_sizes, [level_weight] * nl, loss, grad, level_valid)
             gw, gb = _run_leaf(lib, s, lab[nl], w2, b, leaf_weight, num_valid, loss, grad, True,
                                ctx.needs_input_grad[2] or (bias is not None and ctx.needs_input_grad[3]))
         ctx.wshape = weight.shape
@@ -207,18 +205,19 @@ class _TreeLoss(torch.autograd.Function):
     def backward(ctx, g):
         grad, gw, gb = ctx.saved_tensors
         return (grad * g, None, None if gw is None else (gw * g).view(ctx.wshape), None if gb is None else gb * g,
-                None, None, None, None)
+                None, None, None, None, None)
 
 
 def tree_semantic_loss(sem: torch.Tensor, labels: torch.Tensor, level_sizes, weight: torch.Tensor,
                        bias: torch.Tensor | None = None, level_weight: float = 1.0, leaf_weight: float = 5.0,
-                       num_valid: int | None = None) -> torch.Tensor:
+                       num_valid: int | None = None, level_valid=None) -> torch.Tensor:
     """Hier-SLAM's whole semantic mapping loss (scripts/hierslam.py:955-984): level_weight * sum over the tree levels of
     the per-level cross-entropy + leaf_weight * the leaf cross-entropy behind the 1x1 convolution (weight_sem = [1, 5]).
     labels: [levels + 1, H, W] like curr_data['semantic_label_gt'] (last map = leaf labels).  One gradient image is
-    produced: the leaf kernels accumulate onto what the level kernel wrote."""
+    produced: the leaf kernels accumulate onto what the level kernel wrote.  num_valid / level_valid: the numbers of
+    non-ignored leaf / per-level pixels when known (no host sync then); int32 labels are used without conversion."""
     return _TreeLoss.apply(sem, labels, weight, bias, [int(v) for v in level_sizes], float(level_weight),
-                           float(leaf_weight), num_valid)
+                           float(leaf_weight), num_valid, level_valid)
 
 
 _WINDOW11 = None

@@ -141,3 +141,34 @@ def test_flat_params_appended_matches_torch_cat():
         assert q.leaves[k].grad.shape == q.leaves[k].shape and q.offsets[k] % 64 == 0
     with pytest.raises(RuntimeError, match="same n"):
         p.appended({"means3D": extra["means3D"]})
+
+
+def test_python_host_has_no_undefined_names():
+    """The CUDA-only code paths of the Python host cannot run in the CPU suite; at least every name they load must be
+    defined somewhere in its module (catches a helper or constant lost in a refactor)."""
+    import ast
+    import builtins
+    import glob
+    import os
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "hier_slam_b200")
+    for path in sorted(glob.glob(os.path.join(root, "*.py"))):
+        tree = ast.parse(open(path).read())
+        defined = set(dir(builtins)) | {"__file__", "__name__"}
+        for n in ast.walk(tree):
+            if isinstance(n, (ast.FunctionDef, ast.ClassDef)):
+                defined.add(n.name)
+            elif isinstance(n, ast.Import):
+                defined.update(a.asname or a.name.split(".")[0] for a in n.names)
+            elif isinstance(n, ast.ImportFrom):
+                defined.update(a.asname or a.name for a in n.names)
+            elif isinstance(n, ast.arg):
+                defined.add(n.arg)
+            elif isinstance(n, ast.Name) and isinstance(n.ctx, ast.Store):
+                defined.add(n.id)
+            elif isinstance(n, (ast.Global, ast.Nonlocal)):
+                defined.update(n.names)
+            elif isinstance(n, ast.ExceptHandler) and n.name:
+                defined.add(n.name)
+        missing = {n.id for n in ast.walk(tree) if isinstance(n, ast.Name) and isinstance(n.ctx, ast.Load)
+                   and n.id not in defined}
+        assert not missing, f"{os.path.basename(path)}: undefined names {sorted(missing)}"

@@ -57,7 +57,7 @@ def torch_ssim(a, b):     # utils/slam_external.py:77-97
 LEAVES = 102
 conv = torch.nn.Conv2d(sum(sizes), LEAVES, kernel_size=1).cuda()
 leaf_labels = torch.randint(0, LEAVES, (H, W), generator=g).cuda()
-all_labels = torch.cat((labels, leaf_labels[None]))
+all_labels = torch.cat((labels, leaf_labels[None])).int()     # converted once per keyframe, as a caller would
 
 
 def torch_losses_full(im, depth, sem):
@@ -72,7 +72,8 @@ def torch_losses_full(im, depth, sem):
 
 def fused_losses_full(im, depth, sem):
     return (masked_l1_sum(depth, gt_depth, mask) / n_mask + 0.5 * l1_ssim_loss(im, gt_im)
-            + 0.2 * tree_semantic_loss(sem, all_labels, sizes, conv.weight, conv.bias, 1.0, 5.0, num_valid=H * W))
+            + 0.2 * tree_semantic_loss(sem, all_labels, sizes, conv.weight, conv.bias, 1.0, 5.0, num_valid=H * W,
+                                       level_valid=H * W))
 
 
 def run(mod, loss_fn, iters=20):
