@@ -767,6 +767,87 @@ def test_capacity_mode_matches_the_synchronous_forward():
     assert torch.equal(out[0], ref_out[0])
 
 
+def test_prune_and_densify_match_a_plain_tensor_restatement():
+    """hier_slam_b200.densify.prune_gaussians / densify on the flat parameter set == the same decisions taken on plain
+    per-name tensors with `tensor[mask]` / `torch.cat` (the reference's utils/slam_external.py:142-243), with the same
+    torch seed for the split offsets: parameters, Adam moments and bookkeeping arrays."""
+    from hier_slam_b200.densify import _rotation_matrices, densify, prune_gaussians
+    from hier_slam_b200.mapping import FlatParams
+    from hier_slam_b200.optim import FlatAdam
+    g = torch.Generator().manual_seed(73)
+    P = 3000
+    init = {"means3D": torch.randn(P, 3, generator=g), "rgb_colors": torch.rand(P, 3, generator=g),
+            "unnorm_rotations": torch.randn(P, 4, generator=g), "logit_opacities": 3 * torch.randn(P, 1, generator=g),
+            "log_scales": torch.log(0.002 + 0.03 * torch.rand(P, 1, generator=g)), "semantic": torch.rand(P, 26, generator=g)}
+    init = {k: v.cuda() for k, v in init.items()}
+    opt = FlatAdam(FlatParams({k: v.clone() for k, v in init.items()}), {k: 1e-3 for k in init})
+    for k in init:
+        opt.params.leaves[k].grad.copy_(torch.randn(init[k].shape, generator=g).cuda())
+    opt.step()
+    ref = {k: opt.params.leaves[k].detach().clone() for k in init}
+    mom = {k: tuple(t.clone() for t in opt.state(k)) for k in init}
+    seen = (torch.rand(P, generator=g) < 0.8).cuda()
+    m2d_grad = (3e-4 * torch.randn(P, 3, generator=g)).cuda()
+    variables = dict(means2D_gradient_accum=torch.zeros(P).cuda(), denom=torch.zeros(P).cuda(),
+                     max_2D_radius=torch.zeros(P).cuda(), seen=seen, scene_radius=1.0)
+    cfg = dict(start_after=0, remove_big_after=0, stop_after=100, densify_every=1, grad_thresh=0.0002, num_to_split_into=2,
+               removal_opacity_threshold=0.005, final_removal_opacity_threshold=0.005, reset_opacities_every=3000)
+    torch.manual_seed(5)
+    densify(opt, variables, 1, cfg, m2d_grad)
+    # ---- the same on plain tensors
+    torch.manual_seed(5)
+    accum, denom = torch.zeros(P).cuda(), torch.zeros(P).cuda()
+    accum[seen] += torch.norm(m2d_grad[seen, :2], dim=-1)
+    denom[seen] += 1
+    grads = accum / denom
+    grads[grads.isnan()] = 0.0
+    to_clone = (grads >= 0.0002) & (torch.exp(ref["log_scales"]).max(dim=1).values <= 0.01)
+    zeros_like_rows = lambda t, n: torch.zeros((n,) + tuple(t.shape[1:]), device="cuda")
+    for k in ref:
+        n_new = int(to_clone.sum())
+        mom[k] = tuple(torch.cat((t, zeros_like_rows(t, n_new))) for t in mom[k])
+        ref[k] = torch.cat((ref[k], ref[k][to_clone]))
+    num = ref["means3D"].shape[0]
+    padded = torch.zeros(num).cuda()
+    padded[:P] = grads
+    to_split = (padded >= 0.0002) & (torch.exp(ref["log_scales"]).max(dim=1).values > 0.01)
+    new = {k: v[to_split].repeat(2, 1) for k, v in ref.items()}
+    stds = torch.exp(ref["log_scales"])[to_split].repeat(2, 3)
+    samples = torch.normal(mean=torch.zeros((stds.size(0), 3), device="cuda"), std=stds)
+    rots = _rotation_matrices(ref["unnorm_rotations"][to_split]).repeat(2, 1, 1)
+    new["means3D"] = new["means3D"] + torch.bmm(rots, samples.unsqueeze(-1)).squeeze(-1)
+    new["log_scales"] = torch.log(torch.exp(new["log_scales"]) / (0.8 * 2))
+    k_split = int(to_split.sum())
+    assert int(to_clone.sum()) > 100 and k_split > 100
+    to_remove = torch.cat((to_split, torch.zeros(2 * k_split, dtype=torch.bool, device="cuda")))
+    for k in ref:
+        ref[k] = torch.cat((ref[k], new[k]))[~to_remove]
+        mom[k] = tuple(torch.cat((t, zeros_like_rows(t, 2 * k_split)))[~to_remove] for t in mom[k])
+    low = (torch.sigmoid(ref["logit_opacities"]) < 0.005).squeeze() | (torch.exp(ref["log_scales"]).max(dim=1).values > 0.1)
+    assert int(low.sum()) > 10
+    for k in ref:
+        ref[k] = ref[k][~low]
+        mom[k] = tuple(t[~low] for t in mom[k])
+    for k in ref:
+        assert torch.equal(opt.params.leaves[k].detach(), ref[k]), k
+        m, v = opt.state(k)
+        assert torch.equal(m, mom[k][0]) and torch.equal(v, mom[k][1]), k
+    n_final = ref["means3D"].shape[0]
+    assert all(variables[k].shape == (n_final,) and float(variables[k].abs().max()) == 0.0
+               for k in ("means2D_gradient_accum", "denom", "max_2D_radius"))
+    # ---- prune_gaussians at a pruning iteration, and the opacity reset
+    before = {k: opt.params.leaves[k].detach().clone() for k in ref}
+    prune_gaussians(opt, variables, 20, dict(start_after=0, remove_big_after=0, stop_after=20, prune_every=20,
+                                             removal_opacity_threshold=0.005, final_removal_opacity_threshold=0.3,
+                                             reset_opacities=True, reset_opacities_every=20))
+    gone = (torch.sigmoid(before["logit_opacities"]) < 0.3).squeeze() | (torch.exp(before["log_scales"]).max(dim=1).values > 0.1)
+    assert 0 < int(gone.sum()) < n_final
+    assert torch.equal(opt.params.leaves["means3D"].detach(), before["means3D"][~gone])
+    assert variables["denom"].shape[0] == n_final - int(gone.sum())
+    lo = opt.params.leaves["logit_opacities"].detach()
+    assert torch.allclose(torch.sigmoid(lo), torch.full_like(lo, 0.01)) and float(opt.state("logit_opacities")[0].abs().max()) == 0.0
+
+
 def test_full_size_properties_c2():
     """BASELINE.json config 2 at full size (1200x680, 300K Gaussians, S=26): properties that need no oracle."""
     C, Settings = new_impl()
