@@ -78,6 +78,7 @@ class async_binning:
 
 
 _recorder: Optional[list] = None
+_last_rendered: dict = {}   # (P, H, W, device) -> num_rendered of the previous forward of that shape (binning-buffer guess)
 
 
 class record_binning:
@@ -252,6 +253,17 @@ def _forward(background, means3D, colors, semantics, opacity, scales, rotations,
         img_bytes = lib.hs_image_state_bytes(H, W)
         imgBuffer = torch.empty(img_bytes, **byte)
         cap = None if SORT_GLOBAL else _capacity
+        # Everything that does not depend on num_rendered is allocated BEFORE the read-back, and the binning buffer is
+        # sized from the previous frame of this shape (+25 %), so the GPU idles only for the copy and two launches
+        # between hs_forward_geometry's sync and the first kernel of hs_forward_render.
+        out_color = torch.empty(3, H, W, **fopt)
+        out_sem = torch.empty(S, H, W, **fopt) if semantic else None
+        out_depth = torch.empty(1, H, W, **fopt)
+        out_median = torch.empty(1, H, W, **fopt)
+        out_opacity = torch.empty(1, H, W, **fopt)
+        out_mask = None if semantic else torch.empty(1, H, W, **fopt)
+        guess = cap.instances if cap is not None else _last_rendered.get((P, H, W, device.index), 0) * 5 // 4
+        binningBuffer = torch.empty(lib.hs_binning_state_bytes(guess), **byte) if guess > 0 else None
         R = ctypes.c_int(cap.instances if cap is not None else 0)
         hint = ctypes.c_int(cap.longest_tile if cap is not None else 0)
         gflags = _lib.HS_SORT_GLOBAL if SORT_GLOBAL else (_lib.HS_ASYNC_BINNING if cap is not None else 0)
@@ -263,16 +275,13 @@ def _forward(background, means3D, colors, semantics, opacity, scales, rotations,
         num_rendered = int(R.value)          # capacity mode: the capacity (the counts stay on the device)
         if cap is not None:
             cap.infos.append(binning_info(imgBuffer, H, W))
+        else:
+            _last_rendered[(P, H, W, device.index)] = num_rendered
         if _recorder is not None and not SORT_GLOBAL:
             _recorder.append(binning_info(imgBuffer, H, W))
-        bin_bytes = lib.hs_binning_state_bytes(num_rendered)
-        binningBuffer = torch.empty(bin_bytes, **byte)
-        out_color = torch.empty(3, H, W, **fopt)
-        out_sem = torch.empty(S, H, W, **fopt) if semantic else None
-        out_depth = torch.empty(1, H, W, **fopt)
-        out_median = torch.empty(1, H, W, **fopt)
-        out_opacity = torch.empty(1, H, W, **fopt)
-        out_mask = None if semantic else torch.empty(1, H, W, **fopt)
+        if binningBuffer is None or num_rendered > guess:
+            binningBuffer = torch.empty(lib.hs_binning_state_bytes(num_rendered), **byte)
+        bin_bytes = binningBuffer.numel()
         flags = _lib.HS_NO_CULL if NO_CULL else 0
         _lib.check(lib.hs_forward_render(ctypes.byref(cam), P, S, num_rendered, int(hint.value), _ptr(colors_c),
                                          _ptr(sem_c),
