@@ -848,6 +848,80 @@ def test_prune_and_densify_match_a_plain_tensor_restatement():
     assert torch.allclose(torch.sigmoid(lo), torch.full_like(lo, 0.01)) and float(opt.state("logit_opacities")[0].abs().max()) == 0.0
 
 
+def test_mapping_loop_integration():
+    """All pieces of a mapping loop together, in Hier-SLAM's parametrisation (log-scales, logit-opacities, unnormalised
+    rotations; scripts/hierslam.py:1986-2059): FlatParams + gradient sinks -> render -> fused losses (depth L1, L1 + SSIM,
+    level + leaf cross-entropy) -> backward -> FlatAdam -> prune_gaussians (new parameter set, sinks re-registered) ->
+    more iterations.  The loss must fall between the pruning iterations, the map must shrink at them, nothing may become non-finite."""
+    import torch.nn.functional as F
+    import diff_gaussian_rasterization as ours
+    from hier_slam_b200.densify import prune_gaussians
+    from hier_slam_b200.losses import l1_ssim_loss, masked_l1_sum, tree_semantic_loss
+    from hier_slam_b200.mapping import FlatParams
+    from hier_slam_b200.optim import FlatAdam
+    cfg = CONFIGS["small"]
+    sc = make_scene(cfg, 11, device="cuda")
+    H, W, sizes, leaves_n = cfg.height, cfg.width, [4, 5, 5, 6, 6], 102
+    raster = ours.GaussianRasterizer_semantic(pt.make_settings(ours.GaussianRasterizationSettings, cfg, "cuda"))
+
+    def render(p):
+        m3 = p["means3D"]
+        return raster(means3D=m3, means2D=torch.zeros_like(m3), opacities=torch.sigmoid(p["logit_opacities"]),
+                      colors_precomp=p["rgb_colors"], scales=torch.exp(torch.tile(p["log_scales"], (1, 3))),
+                      rotations=F.normalize(p["unnorm_rotations"]), semantics_precomp=p["semantic"])
+    truth = dict(means3D=sc["means3D"], rgb_colors=sc["colors_precomp"], semantic=sc["semantics_precomp"],
+                 unnorm_rotations=sc["rotations"], logit_opacities=torch.logit(sc["opacities"].clamp(1e-4, 1 - 1e-4)),
+                 log_scales=torch.log(sc["scales"][:, :1]))
+    with torch.no_grad():
+        gt_im, _, gt_sem, gt_depth, _, _ = render(truth)
+        labels, beg = [], 0
+        for n in sizes:
+            labels.append(gt_sem[beg:beg + n].argmax(0))
+            beg += n
+        labels.append(torch.randint(0, leaves_n, (H, W), generator=torch.Generator().manual_seed(3)).cuda())
+        labels = torch.stack(labels).int()
+    g = torch.Generator().manual_seed(12)
+    start = {k: v.clone() for k, v in truth.items()}
+    start["rgb_colors"] = (start["rgb_colors"] + 0.2 * torch.randn(start["rgb_colors"].shape, generator=g).cuda()).clamp(0, 1)
+    start["means3D"] = start["means3D"] + 0.01 * torch.randn(start["means3D"].shape, generator=g).cuda()
+    start["semantic"] = torch.rand(start["semantic"].shape, generator=g).cuda()
+    opt = FlatAdam(FlatParams(start), dict(means3D=1e-4, rgb_colors=2.5e-3, semantic=2.5e-3, unnorm_rotations=1e-3,
+                                           logit_opacities=5e-2, log_scales=1e-3), eps=1e-15)
+    conv = torch.nn.Conv2d(sum(sizes), leaves_n, kernel_size=1).cuda()
+    conv_opt = torch.optim.Adam(conv.parameters(), lr=5e-3)
+    variables = dict(means2D_gradient_accum=torch.zeros(cfg.num_gaussians).cuda(), denom=torch.zeros(cfg.num_gaussians).cuda(),
+                     max_2D_radius=torch.zeros(cfg.num_gaussians).cuda(), scene_radius=2.0)
+    prune_cfg = dict(start_after=0, remove_big_after=0, stop_after=20, prune_every=6, removal_opacity_threshold=0.2,
+                     final_removal_opacity_threshold=0.2, reset_opacities=False, reset_opacities_every=500)
+    mask = gt_depth > 0
+    n_mask = float(mask.sum())
+    history, sizes_p = [], []
+    for it in range(14):
+        opt.zero_grad()
+        conv_opt.zero_grad(set_to_none=True)
+        p = opt.params.leaves
+        im, radii, sem, depth, _, _ = render(p)
+        loss = (masked_l1_sum(depth, gt_depth, mask) / n_mask + 0.5 * l1_ssim_loss(im, gt_im)
+                + 0.2 * tree_semantic_loss(sem, labels, sizes, conv.weight, conv.bias, 1.0, 5.0, num_valid=H * W,
+                                           level_valid=H * W))
+        loss.backward()
+        assert bool(torch.isfinite(opt.params.flat_grad).all()) and float(opt.params.flat_grad.abs().max()) > 0
+        history.append(float(loss.detach()))
+        if it in (6, 12):                                  # the reference prunes BEFORE the optimizer step (:2040-2049)
+            prune_gaussians(opt, variables, it, prune_cfg)
+            opt.zero_grad()                                # gradients belong to the old row set: skip this step's update
+        else:
+            opt.step()
+        conv_opt.step()
+        sizes_p.append(opt.params.leaves["means3D"].shape[0])
+    assert sizes_p[6] < sizes_p[5] and sizes_p[-1] <= sizes_p[6]
+    assert variables["denom"].shape[0] == sizes_p[-1]
+    # the loss falls within every stretch of optimizer steps (pruning a quarter of the map changes the render, and the
+    # leaf term against random labels keeps a floor of ~ln(102), so no comparison across the pruning iterations)
+    assert history[5] < history[0] and history[11] < history[7], history
+    assert bool(torch.isfinite(opt.params.flat).all())
+
+
 def test_full_size_properties_c2():
     """BASELINE.json config 2 at full size (1200x680, 300K Gaussians, S=26): properties that need no oracle."""
     C, Settings = new_impl()
