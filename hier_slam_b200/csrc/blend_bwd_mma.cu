@@ -97,9 +97,9 @@ __global__ void __launch_bounds__(32 * NW, (MmaCfg<S>::B_IN_REGS ? (S == 0 ? HS_
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int SLABS = 8 / NW;                                // CTAs per tile
     const int tile_x = blockIdx.x, tile_y = blockIdx.y / SLABS;
-    const int row0 = (blockIdx.y % SLABS) * (2 * NW) + 2 * warp;   // first tile row of this warp's 16x2 strip
-    const uint32_t px = tile_x * HS_TILE_X + (lane & 15);
-    const uint32_t py = tile_y * HS_TILE_Y + row0 + (lane >> 4);
+    const int region = (blockIdx.y % SLABS) * NW + warp;         // this warp's pixel region of the tile (hs_common.cuh)
+    const uint32_t px = tile_x * HS_TILE_X + HS_PX_X(region, lane);
+    const uint32_t py = tile_y * HS_TILE_Y + HS_PX_Y(region, lane);
     const uint32_t pix_id = W * py + px;
     const float2 pixf = {(float)px, (float)py};
     const bool inside = px < (uint32_t)W && py < (uint32_t)H;
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(32 * NW, (MmaCfg<S>::B_IN_REGS ? (S == 0 ? HS_
     };
     // global pixel index of pixel p (0..31) of this warp's 16x2 strip, -1 outside the image
     auto pixel_of = [&](int p) -> int {
-        const uint32_t x = tile_x * HS_TILE_X + (p & 15), y = tile_y * HS_TILE_Y + row0 + (p >> 4);
+        const uint32_t x = tile_x * HS_TILE_X + HS_PX_X(region, p), y = tile_y * HS_TILE_Y + HS_PX_Y(region, p);
         return (x < (uint32_t)W && y < (uint32_t)H) ? (int)(W * y + x) : -1;
     };
 
@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(32 * NW, (MmaCfg<S>::B_IN_REGS ? (S == 0 ? HS_
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             const int p = 8 * kb + qk + 4 * h;
-            const float x = (float)(p & 15) - 7.5f, y = (float)(row0 + (p >> 4)) - 7.5f;
+            const float x = (float)HS_PX_X(region, p) - 7.5f, y = (float)HS_PX_Y(region, p) - 7.5f;
             mfrag[kb * 2 + h] = qn == 0 ? 1.f : qn == 1 ? x : qn == 2 ? y : qn == 3 ? x * x : qn == 4 ? x * y
                                 : qn == 5 ? y * y : 0.f;
         }

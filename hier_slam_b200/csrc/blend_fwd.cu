@@ -76,8 +76,8 @@ __global__ void __launch_bounds__(256, (S <= 26 ? HS_FWD_OCC : S <= 74 ? HS_FWD_
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
     const int tile_x = blockIdx.x, tile_y = blockIdx.y;
-    const uint32_t px = tile_x * HS_TILE_X + (tid & 15);
-    const uint32_t py = tile_y * HS_TILE_Y + (tid >> 4);
+    const uint32_t px = tile_x * HS_TILE_X + HS_PX_X(warp, tid & 31);
+    const uint32_t py = tile_y * HS_TILE_Y + HS_PX_Y(warp, tid & 31);
     const uint32_t pix_id = W * py + px;
     const float2 pixf = {(float)px, (float)py};
     const bool inside = px < (uint32_t)W && py < (uint32_t)H;
@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(256, (S <= 26 ? HS_FWD_OCC : S <= 74 ? HS_FWD_
         const float4* s_co = s_co2 + (i & 1) * B;
         const float* s_feat = s_feat2 + (size_t)(i & 1) * B * FS;
         if (tid < nb) {
-            // which of the 8 warp strips (16 x 2 pixels) can this Gaussian reach with alpha >= 1/255 ?
+            // which of the 8 warp regions (HS_REGION_W x HS_REGION_H pixels) can this Gaussian reach with alpha >= 1/255 ?
             uint32_t mk = 0xffu;
             if (cull) {
                 const float4 bx = footprint_box(s_xy[tid], s_co[tid]);
@@ -178,8 +178,10 @@ __global__ void __launch_bounds__(256, (S <= 26 ? HS_FWD_OCC : S <= 74 ? HS_FWD_
                 if (!(bx.x > tx0 + 15.f || bx.y < tx0)) {
 #pragma unroll
                     for (int w8 = 0; w8 < 8; w8++) {
-                        const float y0 = ty0 + 2.f * w8;
-                        if (!(bx.z > y0 + 1.f || bx.w < y0)) mk |= 1u << w8;
+                        const float x0 = tx0 + (float)HS_REGION_X0(w8), y0 = ty0 + (float)HS_REGION_Y0(w8);
+                        if (!(bx.x > x0 + (float)(HS_REGION_W - 1) || bx.y < x0) &&
+                            !(bx.z > y0 + (float)(HS_REGION_H - 1) || bx.w < y0))
+                            mk |= 1u << w8;
                     }
                 }
             }

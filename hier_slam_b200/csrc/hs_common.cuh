@@ -8,6 +8,28 @@
 #define HS_TILE_X 16          // reference: cuda_rasterizer/config.h:16  (BLOCK_X)
 #define HS_TILE_Y 16          // reference: cuda_rasterizer/config.h:17  (BLOCK_Y)
 #define HS_TILE_PIX 256
+// Pixels of a warp inside a 16x16 tile.  Region r (0..7) is what the strip masks / strip_hits are indexed by; lane p (0..31).
+//   HS_REGION_8x4 = 1: 8 wide x 4 high blocks (2 columns x 4 rows of regions) -- a pixel-sized Gaussian (footprint ~8x8)
+//                      overlaps ~6 such blocks = 192 lane evaluations;
+//   HS_REGION_8x4 = 0: 16 x 2 strips -- the same Gaussian overlaps ~7.5 strips = 240 lane evaluations.
+#ifndef HS_REGION_8x4
+#define HS_REGION_8x4 1
+#endif
+#if HS_REGION_8x4
+#define HS_REGION_X0(r) (((r) & 1) << 3)
+#define HS_REGION_Y0(r) (((r) >> 1) << 2)
+#define HS_REGION_W 8
+#define HS_REGION_H 4
+#define HS_PX_X(r, p) (HS_REGION_X0(r) + ((p) & 7))
+#define HS_PX_Y(r, p) (HS_REGION_Y0(r) + ((p) >> 3))
+#else
+#define HS_REGION_X0(r) 0
+#define HS_REGION_Y0(r) (2 * (r))
+#define HS_REGION_W 16
+#define HS_REGION_H 2
+#define HS_PX_X(r, p) ((p) & 15)
+#define HS_PX_Y(r, p) (2 * (r) + ((p) >> 4))
+#endif
 #define HS_MAX_SEGMENTS 16     // parameter tensors in one flat buffer (hs_adam_step, hs_compact_gather)
 #define HS_MAX_LEVELS 8        // levels of the hierarchical semantic encoding (hs_hier_cross_entropy)
 #define HS_ALIGN 256          // every array inside an opaque state buffer is 256-B aligned
