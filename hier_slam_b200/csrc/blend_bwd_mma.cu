@@ -6,7 +6,7 @@
 //     dL/dfeat[j][c]  = sum_pix w[j,pix] * dL/dout[pix][c]          c in {sem 0..S-1, r, g, b, depth, silhouette}
 //     moments[j][m]   = sum_pix g[j,pix] * phi_m(pix)               phi = {1, x, y, x^2, x y, y^2} (tile-centred)
 // with w = alpha * T_front and g = dL/dG * G.  The 2D-mean, conic and opacity gradients are closed-form functions of
-// the six moments (dx = x_j - x, so sum g dx^2 = x_j^2 M0 - 2 x_j M1 + M3, ...).  Each warp owns a 16x2 pixel strip:
+// the six moments (dx = x_j - x, so sum g dx^2 = x_j^2 M0 - 2 x_j M1 + M3, ...).  Each warp owns one pixel region of the tile (an 8x4 block; "strip" below, hs_common.cuh):
 //   phase 1 (SIMT, one pixel per lane): walk, back to front and with the reference's alpha / T arithmetic, the list
 //            entries that the forward blended into this strip (strip_hits: ~37 % of the (strip, entry) pairs), and write
 //            w and g into two per-warp shared-memory matrices [16][32] whose rows are packed (row r <-> r-th hit entry);
@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(32 * NW, (MmaCfg<S>::B_IN_REGS ? (S == 0 ? HS_
         if (c == S + 4) return dL_dpixel_opacitys;
         return nullptr;
     };
-    // global pixel index of pixel p (0..31) of this warp's 16x2 strip, -1 outside the image
+    // global pixel index of pixel p (0..31) of this warp's pixel region, -1 outside the image
     auto pixel_of = [&](int p) -> int {
         const uint32_t x = tile_x * HS_TILE_X + HS_PX_X(region, p), y = tile_y * HS_TILE_Y + HS_PX_Y(region, p);
         return (x < (uint32_t)W && y < (uint32_t)H) ? (int)(W * y + x) : -1;
@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(32 * NW, (MmaCfg<S>::B_IN_REGS ? (S == 0 ? HS_
             s_hit3[(r % 3) * B + tid] = strip_hits[list_pos(r, tid)];
         }
     };
-    const int strip = (blockIdx.y % SLABS) * NW + warp;   // this warp's 16x2 strip of the tile
+    const int strip = region;                                // the forward's strip_hits are indexed by the region number
     fetch_ids(0);
     fetch_ids(1);
     __pipeline_commit();

@@ -8,7 +8,7 @@
 // [r g b depth s0..s(S-1)], is staged once per batch in shared memory and consumed with 128-bit broadcast
 // loads (the reference re-reads colour and semantic rows from global memory for every contributing pixel,
 // forward.cu:505-508), batches double-buffered with cp.async; a conservative footprint box per Gaussian gives an
-// 8-bit strip mask, and a warp (a 16x2 pixel strip) iterates only over the set bits of its ballot of 32 entries; the
+// 8-bit region mask, and a warp (one pixel region of the tile: an 8x4 block, hs_common.cuh) iterates only over the set bits of its ballot of 32 entries; the
 // inner loop has no divergent branch (non-contributing lanes blend with weight 0, votes are warp-uniform); channels
 // are blended in pairs with the packed FFMA2; and the strips that actually blended an entry are recorded
 // (strip_hits) so that the backward visits exactly those (strip, entry) pairs.
@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(256, (S <= 26 ? HS_FWD_OCC : S <= 74 ? HS_FWD_
     float* s_feat2 = reinterpret_cast<float*>(s_co2 + 2 * B);        // [2][B][FS]
     float2* s_xy2 = reinterpret_cast<float2*>(s_feat2 + 2 * B * FS); // [2][B]
     int* s_id3 = reinterpret_cast<int*>(s_xy2 + 2 * B);              // [3][B]
-    uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_id3 + 3 * B);   // [B] bit w: Gaussian may touch warp w's strip
+    uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_id3 + 3 * B);   // [B] bit w: Gaussian may touch warp w's pixel region
     uint32_t* s_hit2 = s_mask + B;   // [2][B/32][8] bit j%32 of word (j/32, w): warp w blended Gaussian j of the batch
 
     const int tid = threadIdx.x;
