@@ -78,7 +78,7 @@ class async_binning:
 
 
 _recorder: Optional[list] = None
-_last_rendered: dict = {}   # (P, H, W, device) -> num_rendered of the previous forward of that shape (binning-buffer guess)
+_last_rendered: dict = {}   # (H, W, device) -> num_rendered of the previous forward at that image size (binning-buffer guess)
 
 
 class record_binning:
@@ -254,7 +254,7 @@ def _forward(background, means3D, colors, semantics, opacity, scales, rotations,
         imgBuffer = torch.empty(img_bytes, **byte)
         cap = None if SORT_GLOBAL else _capacity
         # Everything that does not depend on num_rendered is allocated BEFORE the read-back, and the binning buffer is
-        # sized from the previous frame of this shape (+25 %), so the GPU idles only for the copy and two launches
+        # sized from the previous frame at this image size (+25 %; the map grows slowly from frame to frame), so the GPU idles only for the copy and two launches
         # between hs_forward_geometry's sync and the first kernel of hs_forward_render.
         out_color = torch.empty(3, H, W, **fopt)
         out_sem = torch.empty(S, H, W, **fopt) if semantic else None
@@ -262,7 +262,7 @@ def _forward(background, means3D, colors, semantics, opacity, scales, rotations,
         out_median = torch.empty(1, H, W, **fopt)
         out_opacity = torch.empty(1, H, W, **fopt)
         out_mask = None if semantic else torch.empty(1, H, W, **fopt)
-        guess = cap.instances if cap is not None else _last_rendered.get((P, H, W, device.index), 0) * 5 // 4
+        guess = cap.instances if cap is not None else _last_rendered.get((H, W, device.index), 0) * 5 // 4
         binningBuffer = torch.empty(lib.hs_binning_state_bytes(guess), **byte) if guess > 0 else None
         R = ctypes.c_int(cap.instances if cap is not None else 0)
         hint = ctypes.c_int(cap.longest_tile if cap is not None else 0)
@@ -276,7 +276,7 @@ def _forward(background, means3D, colors, semantics, opacity, scales, rotations,
         if cap is not None:
             cap.infos.append(binning_info(imgBuffer, H, W))
         else:
-            _last_rendered[(P, H, W, device.index)] = num_rendered
+            _last_rendered[(H, W, device.index)] = num_rendered
         if _recorder is not None and not SORT_GLOBAL:
             _recorder.append(binning_info(imgBuffer, H, W))
         if binningBuffer is None or num_rendered > guess:
