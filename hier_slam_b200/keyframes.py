@@ -38,17 +38,18 @@ def keyframe_overlap_counts(pts_world: torch.Tensor, est_w2c: torch.Tensor, intr
 
 def backproject_samples(depth: torch.Tensor, intrinsics: torch.Tensor, w2c: torch.Tensor,
                         sampled_indices: torch.Tensor) -> torch.Tensor:
-    """World points of the sampled pixels (reference get_pointcloud, utils/keyframe_selection.py:10-37, including the
-    removal of points that coincide with the camera origin after rounding to 4 decimals)."""
+    """World points of the sampled pixels (reference get_pointcloud, utils/keyframe_selection.py:10-37).  The reference's
+    "remove points at the camera origin" step is reproduced as it behaves: after |round(p, 4)| every point that coincides
+    with ANOTHER row -- the appended origin, but also a pixel that torch.randint drew twice -- is dropped, all copies."""
     cx, cy, fx, fy = intrinsics[0][2], intrinsics[1][2], intrinsics[0][0], intrinsics[1][1]
-    xx = (sampled_indices[:, 1] - cx) / fx
-    yy = (sampled_indices[:, 0] - cy) / fy
-    z = depth[0, sampled_indices[:, 0], sampled_indices[:, 1]]
-    cam = torch.stack((xx * z, yy * z, z), dim=-1)
-    pts4 = torch.cat([cam, torch.ones_like(cam[:, :1])], dim=1)
-    pts = (torch.inverse(w2c) @ pts4.T).T[:, :3]
-    keep = torch.abs(torch.round(pts, decimals=4)).sum(1) != 0          # == "not a duplicate of the (0,0,0) row"
-    return pts[keep]
+    rows, cols = sampled_indices[:, 0], sampled_indices[:, 1]
+    z = depth[0, rows, cols]
+    cam = torch.stack(((cols - cx) / fx * z, (rows - cy) / fy * z, z), dim=-1)
+    pts = (torch.inverse(w2c) @ torch.cat([cam, torch.ones_like(cam[:, :1])], dim=1).T).T[:, :3]
+    keyed = torch.cat([torch.abs(torch.round(pts, decimals=4)), torch.zeros((1, 3), dtype=pts.dtype, device=pts.device)], dim=0)
+    _, inverse, counts = keyed.unique(dim=0, return_inverse=True, return_counts=True)
+    duplicated = counts[inverse][:pts.shape[0]] > 1
+    return pts[~duplicated]
 
 
 def keyframe_selection_overlap(gt_depth, w2c, intrinsics, keyframe_list, k, pixels=1600):

@@ -131,3 +131,20 @@ def test_keyframe_overlap_counts_match_numpy_loops():
         want.append(c)
     got = SO.keyframe_overlap_counts(pts, w2cs, K, W, H)
     assert all(abs(a - b) <= 1 for a, b in zip(got, want)) and got[2] == 0 and got[0] > 10
+
+
+def test_backproject_samples_reproduces_the_reference_duplicate_removal():
+    """hier_slam_b200.keyframes.backproject_samples (host torch code, runs on CPU) == get_pointcloud of
+    utils/keyframe_selection.py:10-37 restated step by step, including its removal of every duplicated row."""
+    from hier_slam_b200.keyframes import backproject_samples
+    g = torch.Generator().manual_seed(7)
+    H, W = 12, 16
+    K = torch.tensor([[20.0, 0, 7.5], [0, 20.0, 5.5], [0, 0, 1]])
+    depth = 1 + torch.rand(1, H, W, generator=g)
+    depth[0, 3, 4] = 0.0                                   # a zero-depth pixel back-projects onto the camera centre
+    w2c = torch.eye(4)                                     # camera at the world origin: that point IS (0, 0, 0)
+    idx = torch.tensor([[3, 4], [2, 2], [5, 9], [2, 2], [7, 1], [11, 15]])       # (2, 2) drawn twice
+    got = backproject_samples(depth, K, w2c, idx)
+    z = depth[0, idx[:, 0], idx[:, 1]]
+    want = torch.stack(((idx[:, 1] - 7.5) / 20 * z, (idx[:, 0] - 5.5) / 20 * z, z), 1)[[2, 4, 5]]
+    assert got.shape == (3, 3) and torch.allclose(got, want, atol=1e-6)
