@@ -87,7 +87,7 @@ def load() -> ctypes.CDLL:
     lib.hs_transform_points.restype = c_int
     lib.hs_tracking_loss.argtypes = [vp, vp, vp, vp, vp, c_size_t, c_float, c_int, c_float, c_float, vp, vp, vp, vp]
     lib.hs_tracking_loss.restype = c_int
-    lib.hs_pose_step.argtypes = [vp, vp, vp, vp, vp, vp, c_float, c_float, c_float, c_float, c_float, c_int, vp]
+    lib.hs_pose_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, c_float, c_float, c_float, c_float, c_float, c_int, vp]
     lib.hs_pose_step.restype = c_int
     lib.hs_keyframe_overlap.argtypes = [vp, c_int, vp, c_int, c_float, c_float, c_float, c_float, c_int, c_int, c_int, vp, vp]
     lib.hs_keyframe_overlap.restype = c_int
@@ -110,7 +110,7 @@ def load() -> ctypes.CDLL:
     lib.hs_profile_read.argtypes = [POINTER(c_float), POINTER(c_int)]
     lib.hs_kernel_launch_count.restype = ctypes.c_longlong
     lib.hs_library_call_count.restype = ctypes.c_longlong
-    if lib.hs_abi_version() != 3:
+    if lib.hs_abi_version() != 4:
         raise ImportError("libhsraster.so ABI version mismatch; rebuild with `python -m hier_slam_b200.build --force`")
     _lib = lib
     return lib

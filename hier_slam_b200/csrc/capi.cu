@@ -391,14 +391,15 @@ int hs_tracking_loss(const float* im, const float* depth, const float* silhouett
 }
 
 int hs_pose_step(float* cam_rot, float* cam_tran, const float* dL_dpose, float* loss, float* state, float* w2c,
-                 float lr_rot, float lr_tran, float beta1, float beta2, float eps, int mode, void* stream_) {
+                 const unsigned int* binning_info, float lr_rot, float lr_tran, float beta1, float beta2, float eps, int mode,
+                 void* stream_) {
     if (cam_rot == nullptr || cam_tran == nullptr || w2c == nullptr ||
         (mode != 0 && (dL_dpose == nullptr || loss == nullptr || state == nullptr))) {
         set_error("hs_pose_step: NULL argument");
         return 1;
     }
-    return launch_pose_step(cam_rot, cam_tran, dL_dpose, loss, state, w2c, lr_rot, lr_tran, beta1, beta2, eps, mode,
-                            (cudaStream_t)stream_);
+    return launch_pose_step(cam_rot, cam_tran, dL_dpose, loss, state, w2c, binning_info, lr_rot, lr_tran, beta1, beta2,
+                            eps, mode, (cudaStream_t)stream_);
 }
 
 int hs_keyframe_overlap(const float* points, int num_points, const float* w2c, int keyframes, float fx, float fy, float cx,

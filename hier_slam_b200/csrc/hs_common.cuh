@@ -163,7 +163,7 @@ int launch_tracking_loss(const float* im, const float* depth, const float* sil, 
                          size_t HW, float sil_thres, int use_sil, float w_depth, float w_im, float* loss, float* grad_im,
                          float* grad_depth, cudaStream_t stream);
 int launch_pose_step(float* cam_rot, float* cam_tran, const float* dL_dpose, float* loss, float* state, float* w2c,
-                     float lr_rot, float lr_tran, float beta1, float beta2, float eps, int mode, cudaStream_t stream);
+                     const uint32_t* binning_info, float lr_rot, float lr_tran, float beta1, float beta2, float eps, int mode, cudaStream_t stream);
 int launch_keyframe_overlap(const float* pts, int N, const float* w2c, int K, float fx, float fy, float cx, float cy, int width,
                             int height, int edge, int* counts, cudaStream_t stream);
 int launch_adam_flat(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, int n_seg,

@@ -43,14 +43,17 @@ __global__ void __launch_bounds__(256) tracking_loss_kernel(const float* __restr
     for (size_t p = (size_t)blockIdx.x * 256 + threadIdx.x; p < HW; p += (size_t)gridDim.x * 256) {
         const float d = depth[p], gd = gt_depth[p];
         const bool m = gd > 0.f && !isnan(d) && (!use_sil || sil[p] > sil_thres);
+        // colour term: masked like the depth only when the silhouette mask is in use; otherwise the reference sums
+        // |gt_im - im| over EVERY pixel (scripts/hierslam.py:789-794 with ignore_outlier_depth_loss = False)
+        const bool mc = use_sil ? m : true;
         const float dd = d - gd;
         acc += m ? w_depth * fabsf(dd) : 0.f;
         grad_depth[p] = m ? w_depth * (dd > 0.f ? 1.f : (dd < 0.f ? -1.f : 0.f)) : 0.f;
 #pragma unroll
         for (int c = 0; c < 3; c++) {
             const float di = im[c * HW + p] - gt_im[c * HW + p];
-            acc += m ? w_im * fabsf(di) : 0.f;
-            grad_im[c * HW + p] = m ? w_im * (di > 0.f ? 1.f : (di < 0.f ? -1.f : 0.f)) : 0.f;
+            acc += mc ? w_im * fabsf(di) : 0.f;
+            grad_im[c * HW + p] = mc ? w_im * (di > 0.f ? 1.f : (di < 0.f ? -1.f : 0.f)) : 0.f;
         }
     }
 #pragma unroll
@@ -97,10 +100,11 @@ __device__ __forceinline__ void write_pose_matrix(const float* q, const float* t
 }
 
 // state (HS_POSE_STATE_FLOATS floats): exp_avg rot[4] tran[3] | exp_avg_sq rot[4] tran[3] | step | min_loss |
-// cand_rot[4] | cand_tran[3] | last_loss
+// cand_rot[4] | cand_tran[3] | last_loss | overflow (sticky) | max num_rendered | max longest tile list | reserved
 __global__ void pose_step_kernel(float* __restrict__ cam_rot, float* __restrict__ cam_tran, const float* __restrict__ dL_dpose,
-                                 float* __restrict__ loss, float* __restrict__ state, float* __restrict__ w2c, float lr_rot,
-                                 float lr_tran, float beta1, float beta2, float eps, int mode) {
+                                 float* __restrict__ loss, float* __restrict__ state, float* __restrict__ w2c,
+                                 const uint32_t* __restrict__ binning_info, float lr_rot, float lr_tran, float beta1,
+                                 float beta2, float eps, int mode) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     float q[4] = {cam_rot[0], cam_rot[1], cam_rot[2], cam_rot[3]}, t[3] = {cam_tran[0], cam_tran[1], cam_tran[2]};
     if (mode == 0) {               // frame start: only the matrix of the current pose
@@ -110,15 +114,19 @@ __global__ void pose_step_kernel(float* __restrict__ cam_rot, float* __restrict_
     float* m = state;
     float* v = state + 7;
     const float l = loss[0];
-    if (l < state[15]) {           // the candidate is the pose that PRODUCED this loss (before the step)
-        state[15] = l;
-#pragma unroll
-        for (int k = 0; k < 4; k++) state[16 + k] = q[k];
-#pragma unroll
-        for (int k = 0; k < 3; k++) state[20 + k] = t[k];
+    loss[0] = 0.f;                 // ready for the next iteration's accumulation
+    // Capacity-mode binning: an iteration that outgrew the capacity rendered EMPTY (loss 0, gradients 0).  The binning
+    // flag is rewritten by every forward, so it is latched here for the whole frame, and the iteration neither becomes a
+    // candidate nor moves the pose or the optimiser state.
+    if (binning_info != nullptr) {   // largest counts any iteration of the frame needed: sizes the re-capture
+        state[25] = fmaxf(state[25], (float)binning_info[0]);
+        state[26] = fmaxf(state[26], (float)binning_info[1]);
+        if (binning_info[3] != 0u) {
+            state[24] = 1.f;
+            return;
+        }
     }
     state[23] = l;
-    loss[0] = 0.f;                 // ready for the next iteration's accumulation
     // dL/dR (rows of dL_dpose[3,4]) -> normalised quaternion (r, x, y, z) -> unnormalised quaternion
     const float n = fmaxf(sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]), 1e-12f);
     const float r = q[0] / n, x = q[1] / n, y = q[2] / n, z = q[3] / n;
@@ -153,13 +161,24 @@ __global__ void pose_step_kernel(float* __restrict__ cam_rot, float* __restrict_
     for (int k = 0; k < 4; k++) cam_rot[k] = q[k];
 #pragma unroll
     for (int k = 0; k < 3; k++) cam_tran[k] = t[k];
+    // Best candidate exactly as the reference keeps it (scripts/hierslam.py:1851-1858): loss.backward(), optimizer.step(),
+    // THEN `if loss < current_min_loss` saves cam_unnorm_rots / cam_trans -- i.e. the pose AFTER the step, paired with the
+    // loss evaluated before it.
+    if (l < state[15]) {
+        state[15] = l;
+#pragma unroll
+        for (int k = 0; k < 4; k++) state[16 + k] = q[k];
+#pragma unroll
+        for (int k = 0; k < 3; k++) state[20 + k] = t[k];
+    }
     write_pose_matrix(q, t, w2c);
 }
 
 int launch_pose_step(float* cam_rot, float* cam_tran, const float* dL_dpose, float* loss, float* state, float* w2c,
-                     float lr_rot, float lr_tran, float beta1, float beta2, float eps, int mode, cudaStream_t stream) {
-    pose_step_kernel<<<1, 32, 0, stream>>>(cam_rot, cam_tran, dL_dpose, loss, state, w2c, lr_rot, lr_tran, beta1, beta2, eps,
-                                           mode);
+                     const uint32_t* binning_info, float lr_rot, float lr_tran, float beta1, float beta2, float eps, int mode,
+                     cudaStream_t stream) {
+    pose_step_kernel<<<1, 32, 0, stream>>>(cam_rot, cam_tran, dL_dpose, loss, state, w2c, binning_info, lr_rot, lr_tran,
+                                           beta1, beta2, eps, mode);
     HS_LAUNCH_OK(stream, false);
     return 0;
 }

@@ -122,7 +122,8 @@ class GraphedTracker:
     [& (silhouette > sil_thres)] -> loss = depth_weight * sum|gt_depth - depth|[mask] + im_weight * sum|gt_im - im|[mask]
     (get_loss_semantic(tracking=True), :765-796) -> best-candidate bookkeeping (:1850-1856) -> backward with the pose
     gradient reduced in the per-Gaussian kernel -> Adam on the unnormalised quaternion and the translation
-    (configs/replica/hierslam_semantic_run.py:85-95).
+    (configs/replica/hierslam_semantic_run.py:85-95) -> best-candidate bookkeeping (:1851-1858: the pose after the step is
+    kept when the loss before it was the smallest so far).
 
     Nothing in it needs autograd or the host: the steps between the rasterizer calls are three kernels of the library
     (hs_transform_points, hs_tracking_loss, hs_pose_step; in torch they are ~200 tiny launches per iteration) and the
@@ -145,15 +146,15 @@ class GraphedTracker:
         self.captures = 0
         self._P = None
 
-    def _pose_step(self, mode: int, d_pose=None):
+    def _pose_step(self, mode: int, d_pose=None, info=None):
         import ctypes
         from . import _lib
         st = self.st
         vp = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
         dev = st["cam_rot"].device
         _lib.check(_lib.load().hs_pose_step(vp(st["cam_rot"]), vp(st["cam_tran"]), vp(d_pose), vp(st["loss"]),
-                                            vp(st["state"]), vp(st["w2c"]), self.lr_rot, self.lr_trans, self.betas[0],
-                                            self.betas[1], self.eps, mode,
+                                            vp(st["state"]), vp(st["w2c"]), vp(info), self.lr_rot, self.lr_trans,
+                                            self.betas[0], self.betas[1], self.eps, mode,
                                             ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "hs_pose_step")
 
     # -- one iteration on the static buffers (runs eagerly for warm-up, and once under capture); returns the image buffer
@@ -161,7 +162,7 @@ class GraphedTracker:
     def _iteration(self):
         import ctypes
         from . import _lib
-        lib, st, rs = _lib.load(), self.st, self.rs
+        lib, st, rs = _lib.load(), self.st, self.cam
         dev = st["means3D"].device
         vp = lambda t: ctypes.c_void_p(t.data_ptr())
         stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
@@ -180,7 +181,9 @@ class GraphedTracker:
             rs.bg, st["means_cam"], radii, st["rgb_colors"], st["scales"], st["rotations"], rs.scale_modifier, e,
             rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, g_im, g_depth, None, None, e, rs.sh_degree, rs.campos,
             gb, n, bb, ib, rs.debug, H, W, pose_points=st["means3D"])
-        self._pose_step(1, grads[-1])
+        # the forward's binning counts go to the pose step: an iteration that outgrew the capacity is discarded there and
+        # latched into the pose state (the flag itself is rewritten by every forward)
+        self._pose_step(1, grads[-1], _C.binning_info(ib, H, W))
         return ib
 
     def _allocate(self, P: int, dev):
@@ -190,7 +193,14 @@ class GraphedTracker:
                        rgb_colors=torch.zeros(P, 3, **f), scales=torch.zeros(P, 3, **f), rotations=torch.zeros(P, 4, **f),
                        gt_im=torch.zeros(3, H, W, **f), gt_depth=torch.zeros(1, H, W, **f), cam_rot=torch.zeros(4, **f),
                        cam_tran=torch.zeros(3, **f), w2c=torch.zeros(16, **f), loss=torch.zeros(1, **f),
-                       state=torch.zeros(24, **f))
+                       state=torch.zeros(32, **f))
+        # Camera tensors whose addresses are baked into the captured graph are OWNED here (contiguous float32 copies that
+        # live as long as the tracker); track() refreshes their contents from the caller's settings before every frame,
+        # so in-place edits of rs.viewmatrix / rs.projmatrix are honoured and nothing the graph reads can be freed.
+        rs = self.rs
+        own = lambda t: t.detach().to(device=dev, dtype=torch.float32).contiguous().clone()
+        self.cam = rs._replace(bg=own(rs.bg), viewmatrix=own(rs.viewmatrix), projmatrix=own(rs.projmatrix),
+                               campos=own(rs.campos))
         self._P = P
         self.graph = None
 
@@ -233,6 +243,8 @@ class GraphedTracker:
         for k, v in (("means3D", means3D), ("rgb_colors", rgb_colors), ("opacities", opacities), ("scales", scales),
                      ("rotations", rotations), ("gt_im", gt_im), ("gt_depth", gt_depth)):
             st[k].copy_(v.detach().reshape(st[k].shape))
+        for k in ("bg", "viewmatrix", "projmatrix", "campos"):
+            getattr(self.cam, k).copy_(getattr(self.rs, k).detach().reshape(getattr(self.cam, k).shape))
 
     def track(self, means3D, rgb_colors, opacities, scales, rotations, gt_im, gt_depth, init_rot, init_tran,
               num_iters: int = 40, max_retries: int = 3):
@@ -255,14 +267,15 @@ class GraphedTracker:
                 for _ in range(num_iters):
                     self.graph.replay()
                 st = self.st
-                flag = self.capacity.infos[0][3:4].to(torch.float32)
-                host = torch.cat((st["state"], st["cam_rot"], st["cam_tran"], flag)).cpu()     # the frame's one sync
-                if host[31] == 0 or retries >= max_retries:
+                # state[24]: overflow latch of the WHOLE frame (any iteration), written by hs_pose_step
+                host = torch.cat((st["state"], st["cam_rot"], st["cam_tran"])).cpu()     # the frame's one sync
+                if host[24] == 0 or retries >= max_retries:
                     break
-                retries += 1          # the frame outgrew the binning capacity: re-capture larger and repeat it
-                at_least = _C.BinningCapacity.from_info(self.capacity.infos[0], 1.3)
+                retries += 1          # some iteration outgrew the binning capacity: re-capture larger and repeat the frame
+                # state[25:27]: the largest counts any iteration of the frame needed (an overflowed forward still reports them)
+                at_least = _C.BinningCapacity(int(float(host[25]) * 1.3) + 65536, int(float(host[26]) * 1.3) + 256)
                 self.graph = None
-            if host[31] != 0:
+            if host[24] != 0:
                 raise RuntimeError("tracking frame does not fit the binning capacity after re-captures")
-        return dict(rot=host[16:20].clone(), tran=host[20:23].clone(), loss=float(host[15]), last_rot=host[24:28].clone(),
-                    last_tran=host[28:31].clone(), last_loss=float(host[23]), retries=retries)
+        return dict(rot=host[16:20].clone(), tran=host[20:23].clone(), loss=float(host[15]), last_rot=host[32:36].clone(),
+                    last_tran=host[36:39].clone(), last_loss=float(host[23]), retries=retries)

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define HS_RASTER_ABI_VERSION 3
+#define HS_RASTER_ABI_VERSION 4
 
 /* flags (bit-or) */
 #define HS_SEM_ALPHA_EXACT 1 /* backward: semantic channels contribute to dL/dalpha (the mathematically intended
@@ -143,20 +143,26 @@ int hs_hier_cross_entropy(const float* sem, const int* labels, int levels, const
  * each as one kernel so that a whole iteration is ~14 launches and stream-capturable.
  * hs_transform_points: cam[P,3] = R world + t for the row-major 4x4 w2c (device).
  * hs_tracking_loss: mask = gt_depth > 0 && !isnan(depth) [&& silhouette > sil_thres]; loss[0] (device, accumulated) +=
- *   depth_weight * sum_mask |gt_depth - depth| + im_weight * sum_mask sum_c |gt_im - im|; grad_im[3,pixels], grad_depth[pixels]
- *   = d loss / d im, d loss / d depth.
- * hs_pose_step (mode 1): best-candidate bookkeeping with loss[0], which is then reset to 0; dL_dpose[3,4] (hs_backward) ->
- *   gradient of the unnormalised quaternion cam_rot[4] (r,x,y,z) and translation cam_tran[3]; torch.optim.Adam's update with
- *   per-tensor learning rates; w2c[16] of the updated pose.  state: HS_POSE_STATE_FLOATS floats (device) = exp_avg[7] |
- *   exp_avg_sq[7] | step | min_loss | candidate rot[4] | candidate tran[3] | last loss; the caller zeroes it and sets
- *   min_loss large at frame start.  mode 0: only write w2c for the current pose. */
-#define HS_POSE_STATE_FLOATS 24
+ *   depth_weight * sum_mask |gt_depth - depth| + im_weight * sum_c |gt_im - im| (over the same mask when use_silhouette,
+ *   over EVERY pixel otherwise: scripts/hierslam.py:789-794); grad_im[3,pixels], grad_depth[pixels] = d loss / d im,
+ *   d loss / d depth.  The reference's `ignore_outlier_depth_loss` option (a median over the depth error) is not offered.
+ * hs_pose_step (mode 1): loss[0] is read and reset to 0; dL_dpose[3,4] (hs_backward) -> gradient of the unnormalised
+ *   quaternion cam_rot[4] (r,x,y,z) and translation cam_tran[3]; torch.optim.Adam's update with per-tensor learning rates;
+ *   best-candidate bookkeeping as the reference does it (scripts/hierslam.py:1851-1858: the pose AFTER the step is saved
+ *   when the loss evaluated before it is the smallest so far); w2c[16] of the updated pose.  binning_info (NULL = not
+ *   used): the uint32[4] counts of the iteration's forward (hs_image_state_info_offset); when its overflow word is set
+ *   (capacity-mode binning: the frame rendered empty) the iteration is discarded -- no candidate, no update -- and
+ *   state[24] is latched to 1 for the caller to read once per frame.  state: HS_POSE_STATE_FLOATS floats (device) =
+ *   exp_avg[7] | exp_avg_sq[7] | step | min_loss | candidate rot[4] | candidate tran[3] | last loss | overflow latch |
+ *   largest num_rendered | longest tile list seen in the frame (as floats) | reserved[5]; the caller zeroes it and sets min_loss large at frame start.  mode 0: only write w2c for the current pose. */
+#define HS_POSE_STATE_FLOATS 32
 int hs_transform_points(const float* w2c, const float* world, int P, float* cam, void* stream);
 int hs_tracking_loss(const float* im, const float* depth, const float* silhouette, const float* gt_im,
                      const float* gt_depth, size_t pixels, float sil_thres, int use_silhouette, float depth_weight,
                      float im_weight, float* loss, float* grad_im, float* grad_depth, void* stream);
 int hs_pose_step(float* cam_rot, float* cam_tran, const float* dL_dpose, float* loss, float* state, float* w2c,
-                 float lr_rot, float lr_tran, float beta1, float beta2, float eps, int mode, void* stream);
+                 const unsigned int* binning_info, float lr_rot, float lr_tran, float beta1, float beta2, float eps, int mode,
+                 void* stream);
 
 /* Extension: keyframe selection by re-projection (utils/keyframe_selection.py:40-96).
  * counts[k] (int32, device) = number of the num_points world points[.,3] that project into keyframe k's image

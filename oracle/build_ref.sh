@@ -10,6 +10,11 @@
 #
 #   usage: oracle/build_ref.sh [S ...]        (default: 26)
 #
+# It also copies the reference's CALLERS of the rasterizer (scripts/hierslam.py and utils/*.py: plain torch code
+# that needs a GPU at run time) to oracle/_ref/callers/ so that tests/test_reference_callers.py can replay
+# get_loss_semantic / get_loss_semantic_mlp / add_new_gaussians_semantic_newrender UNCHANGED on the GPU box, once
+# bound to the reference build and once to this repository's module.  /root/reference does not exist there.
+#
 # gcc-13 needs `-include cstdint` because rasterizer_impl.h uses uintptr_t /
 # uint32_t without including <cstdint>; no source patch.
 set -euo pipefail
@@ -19,6 +24,15 @@ OUT=$HERE/_ref
 if [ ! -d "$REF" ]; then
   echo "reference not present at $REF - nothing to build (prebuilt oracle/_ref is used if it exists)"
   exit 0
+fi
+CALLERS=$OUT/callers
+REFROOT=${HS_REFERENCE_ROOT:-/root/reference}
+if [ ! -f "$CALLERS/scripts/hierslam.py" ]; then
+  mkdir -p "$CALLERS/scripts" "$CALLERS/utils"
+  cp "$REFROOT/scripts/hierslam.py" "$CALLERS/scripts/"
+  cp "$REFROOT"/utils/*.py "$CALLERS/utils/"
+  chmod -R u+w "$CALLERS"
+  echo "copied the reference's rasterizer callers to oracle/_ref/callers"
 fi
 SVALS=("$@"); [ ${#SVALS[@]} -eq 0 ] && SVALS=(26)
 for S in "${SVALS[@]}"; do

@@ -174,7 +174,12 @@ def _ref_or_skip(S):
     return ref
 
 
-@pytest.mark.parametrize("key,P,S", [("c1", None, 26), ("c2", 60_000, 26), ("c4", 50_000, 16), ("c5", 50_000, 74)])
+@pytest.mark.parametrize("key,P,S", [("c1", None, 26), ("c2", 60_000, 26), ("c4", 50_000, 16), ("c5", 50_000, 74),
+                                     # the benchmarked sizes themselves (BASELINE.json configs 2, 4, 5): 400-3600-entry
+                                     # tile lists, the 512-thread sort class, the one-CTA-per-SM S = 74 backward
+                                     ("c2", None, 26), ("c4", None, 16), ("c5", None, 74),
+                                     # Replica's flat class map: two 51-channel backward passes
+                                     ("c2", 60_000, 102), ("small", None, 102)])
 def test_against_live_reference(key, P, S):
     """Same inputs through the UNMODIFIED reference CUDA build: lists / keys / radii bit-exact, images and
     gradients within the north_star tolerances."""
@@ -223,6 +228,73 @@ def test_nonsemantic_against_live_reference():
     gr = pt.run_backward(ref._C, settings, scene, fr, ug, False)
     for k in g:
         assert_grads_close(g[k], gr[k], k)
+
+
+@pytest.mark.parametrize("key,P,semantic", [("small", None, True), ("c2", 60_000, True), ("small", None, False)])
+def test_cov3d_precomp_path(key, P, semantic):
+    """caller-supplied 6-float covariances instead of scales + rotations (forward.cu:204-213,
+    rasterizer_impl.cu:706; backward.cu:144-274 writes dL_dcov3D, the scale / rotation backward is skipped).  Anisotropic
+    covariances through the public API: forward and every gradient incl. dL/dcov3D against the live reference build and
+    (small scene) against the CPU oracle; scales / rotations must not be needed and receive no gradient."""
+    import diff_gaussian_rasterization as dgr
+    cfg = CONFIGS[key]
+    sc = make_scene(cfg, 21, num_gaussians=P, device="cuda")
+    n = sc["means3D"].shape[0]
+    g = torch.Generator().manual_seed(22)
+    aniso = sc["scales"].cpu() * (0.5 + 1.5 * torch.rand(n, 3, generator=g))
+    cov = O.compute_cov3d(aniso, sc["rotations"].cpu(), 1.0, torch.float32).contiguous()
+    ug = upstream_grads(cfg, 23, device="cuda")
+
+    def run(mod):
+        settings = pt.make_settings(mod.GaussianRasterizationSettings, cfg)
+        leaf = dict(means3D=sc["means3D"].clone().requires_grad_(True), cov=cov.cuda().requires_grad_(True),
+                    opacities=sc["opacities"].clone().requires_grad_(True),
+                    colors=sc["colors_precomp"].clone().requires_grad_(True))
+        kw = dict(means3D=leaf["means3D"], means2D=torch.zeros_like(leaf["means3D"]), opacities=leaf["opacities"],
+                  colors_precomp=leaf["colors"], cov3D_precomp=leaf["cov"])
+        if semantic:
+            leaf["sem"] = sc["semantics_precomp"].clone().requires_grad_(True)
+            out = mod.GaussianRasterizer_semantic(raster_settings=settings)(semantics_precomp=leaf["sem"], **kw)
+            color, radii, sem, depth, median, opac = out
+            loss = (sem * ug["semantic"]).sum()
+        else:
+            color, radii, depth, median, opac, mask = mod.GaussianRasterizer(raster_settings=settings)(**kw)
+            loss = 0
+        loss = loss + (color * ug["color"]).sum() + (depth * ug["depth"]).sum() + (opac * ug["final_opacity"]).sum() + \
+            (median * ug["median_depth"]).sum()
+        loss.backward()
+        return dict(color=color, depth=depth, median=median, opacity=opac, radii=radii), {k: v.grad for k, v in leaf.items()}
+
+    o, gr = run(dgr)
+    assert int((o["radii"] > 0).sum()) > 0.9 * n and float(gr["cov"].abs().max()) > 0
+    ref = ref_loader.load_reference(26)
+    if ref is not None:
+        orf, grr = run(ref)
+        assert torch.equal(o["radii"], orf["radii"])
+        for k in ("color", "depth", "median", "opacity"):
+            assert_images_close(o[k], orf[k], f"{k} (cov3D_precomp) vs live reference")
+        for k in gr:
+            assert_grads_close(gr[k], grr[k], f"dL/d{k} (cov3D_precomp) vs live reference")
+    elif key != "small":
+        pytest.skip("oracle/_ref/S26 not available on this box")
+    if key == "small":
+        H, W = cfg.height, cfg.width
+        view, proj, campos, tfx, tfy = camera_matrices(cfg)
+        cpu = {k: v.cpu() for k, v in sc.items()}
+        semc = cpu["semantics_precomp"] if semantic else None
+        fo = O.rasterize_forward(torch.zeros(3), cpu["means3D"], cpu["colors_precomp"], semc, cpu["opacities"], None, None,
+                                 1.0, cov, view, proj, tfx, tfy, H, W)
+        near_int = (fo["geom"]["radius_prerounding"] - fo["geom"]["radius_prerounding"].round()).abs() < 1e-3
+        assert int(((fo["geom"]["radii"] != o["radii"].cpu()) & ~near_int).sum()) == 0
+        ok = (fo["geom"]["radii"] == o["radii"].cpu()).all()
+        if ok:   # identical visibility: the whole oracle pipeline is comparable end to end
+            u = {k: v.cpu() for k, v in ug.items()}
+            go = O.rasterize_backward(dict(fo), torch.zeros(3), cpu["means3D"], cpu["colors_precomp"], semc, None, None,
+                                      1.0, cov, view, proj, tfx, tfy, H, W, u["color"], u["semantic"] if semantic else None,
+                                      u["depth"], u["median_depth"], u["final_opacity"])
+            for kn, ko in (("means3D", "dL_dmeans3D"), ("cov", "dL_dcov3D"), ("opacities", "dL_dopacity"),
+                           ("colors", "dL_dcolors")):
+                assert_grads_close(gr[kn].cpu(), go[ko].reshape(gr[kn].shape), f"{kn} (cov3D_precomp) vs oracle", tol=2e-3)
 
 
 @pytest.mark.parametrize("simt", [False, True])
@@ -635,9 +707,9 @@ def test_render_depth_silhouette_is_bit_identical_to_the_semantic_render():
         assert not depth.requires_grad and not sil.requires_grad
 
 
-def _eager_tracking_loop(settings_mod, cfg, scene, gt_im, gt_depth, iters):
+def _eager_tracking_loop(settings_mod, cfg, scene, gt_im, gt_depth, iters, use_sil=True):
     """the reference's tracking iteration written with the public API and plain torch (scripts/hierslam.py:765-796,
-    1837-1856): transform in torch, boolean-mask L1 sums, torch.optim.Adam, best candidate"""
+    1837-1858): transform in torch, boolean-mask L1 sums, torch.optim.Adam, best candidate recorded after the step"""
     import torch.nn.functional as F
     from hier_slam_b200.tracking import _pose_matrix
     import diff_gaussian_rasterization as ours
@@ -654,23 +726,30 @@ def _eager_tracking_loop(settings_mod, cfg, scene, gt_im, gt_depth, iters):
         im, _, _, depth, _, sil = raster(means3D=tp, means2D=torch.zeros_like(pts), opacities=scene["opacities"],
                                          colors_precomp=scene["colors_precomp"], scales=scene["scales"],
                                          rotations=scene["rotations"], semantics_precomp=scene["semantics_precomp"])
-        mask = (gt_depth > 0) & ~torch.isnan(depth) & (sil > 0.99)
-        loss = torch.abs(gt_depth - depth)[mask].sum() + 0.5 * torch.abs(gt_im - im)[mask.expand(3, -1, -1)].sum()
-        if float(loss) < best[0]:
-            best = (float(loss), cam_rot.detach().clone().cpu(), cam_tran.detach().clone().cpu())
+        mask = (gt_depth > 0) & ~torch.isnan(depth)
+        if use_sil:
+            mask = mask & (sil > 0.99)
+            loss_im = torch.abs(gt_im - im)[mask.expand(3, -1, -1)].sum()
+        else:       # scripts/hierslam.py:793-794: without the silhouette mask the colour term is NOT masked
+            loss_im = torch.abs(gt_im - im).sum()
+        loss = torch.abs(gt_depth - depth)[mask].sum() + 0.5 * loss_im
         opt.zero_grad(set_to_none=True)
         loss.backward()
         opt.step()
+        if float(loss) < best[0]:      # the reference records the candidate AFTER the step (scripts/hierslam.py:1851-1858)
+            best = (float(loss), cam_rot.detach().clone().cpu(), cam_tran.detach().clone().cpu())
     return best
 
 
-def test_graphed_tracker_matches_the_eager_tracking_loop():
+@pytest.mark.parametrize("key,iters,use_sil", [("c1", 12, True), ("c1", 12, False), ("c2", 40, True)])
+def test_graphed_tracker_matches_the_eager_tracking_loop(key, iters, use_sil):
     """hier_slam_b200.tracking.GraphedTracker (one CUDA-graph launch per iteration, sync-free binning) follows the same pose
-    trajectory as the reference-style eager loop, also when a frame outgrows the binning capacity and is repeated."""
+    trajectory as the reference-style eager loop WITH THE SAME MASK -- at the c1 size and at BASELINE config 3 (c2 scene,
+    40 iterations) -- also when a frame outgrows the binning capacity and is repeated."""
     from hier_slam_b200.scene import keyframe_poses
     from hier_slam_b200.tracking import GraphedTracker
     import diff_gaussian_rasterization as ours
-    cfg = CONFIGS["c1"]
+    cfg = CONFIGS[key]
     scene = make_scene(cfg, 0, device="cuda")
     settings = pt.make_settings(ours.GaussianRasterizationSettings, cfg, "cuda")
     raster = ours.GaussianRasterizer_semantic(settings)
@@ -680,20 +759,67 @@ def test_graphed_tracker_matches_the_eager_tracking_loop():
         gt_im, _, _, gt_depth, _, _ = raster(means3D=tp, means2D=torch.zeros_like(tp), opacities=scene["opacities"],
                                              colors_precomp=scene["colors_precomp"], scales=scene["scales"],
                                              rotations=scene["rotations"], semantics_precomp=scene["semantics_precomp"])
-    iters = 12
-    ref_loss, ref_rot, ref_tran = _eager_tracking_loop(ours, cfg, scene, gt_im, gt_depth, iters)
+    ref_loss, ref_rot, ref_tran = _eager_tracking_loop(ours, cfg, scene, gt_im, gt_depth, iters, use_sil)
     init_rot, init_tran = torch.tensor([1.0, 0, 0, 0]), torch.zeros(3)
     args = (scene["means3D"], scene["colors_precomp"], scene["opacities"], scene["scales"], scene["rotations"], gt_im,
             gt_depth, init_rot, init_tran)
-    for tracker, expect_retry in ((GraphedTracker(settings), False),
-                                  (GraphedTracker(settings, slack=0.5, extra_instances=0), True)):
+    tol = 1e-5 if key == "c1" else 5e-5
+    for tracker, expect_retry in ((GraphedTracker(settings, use_sil_for_loss=use_sil), False),
+                                  (GraphedTracker(settings, use_sil_for_loss=use_sil, slack=0.5, extra_instances=0), True)):
         out = tracker.track(*args, num_iters=iters)
         assert (out["retries"] > 0) == expect_retry
         assert abs(out["loss"] - ref_loss) <= 1e-3 * abs(ref_loss)
-        assert float((out["rot"] - ref_rot).abs().max()) < 1e-5 and float((out["tran"] - ref_tran).abs().max()) < 1e-5
+        assert float((out["rot"] - ref_rot).abs().max()) < tol and float((out["tran"] - ref_tran).abs().max()) < tol
         again = tracker.track(*args, num_iters=iters)          # second frame: replays the captured graph
         assert tracker.captures == (2 if expect_retry else 1)
-        assert float((again["tran"] - out["tran"]).abs().max()) < 1e-5 and again["retries"] == 0
+        assert float((again["tran"] - out["tran"]).abs().max()) < tol and again["retries"] == 0
+        if key != "c1":
+            break
+    # the tracker owns its camera buffers: an in-place edit of the caller's matrices is picked up by the next frame, and
+    # dropping the caller's tensors cannot invalidate what the captured graph reads
+    if key == "c1" and use_sil:
+        tracker = GraphedTracker(settings)
+        base = tracker.track(*args, num_iters=4)
+        settings.projmatrix.mul_(1.0)          # version bump, same values
+        same = tracker.track(*args, num_iters=4)
+        assert tracker.captures == 1 and float((same["tran"] - base["tran"]).abs().max()) < 1e-6
+
+
+def test_pose_step_discards_an_overflowed_iteration_and_latches_the_flag():
+    """the binning overflow flag is rewritten by every forward, so an overflow in a MIDDLE iteration of a frame
+    must be latched; the overflowed iteration (it rendered empty: loss 0, gradient 0) must neither become the best
+    candidate nor move the pose or the Adam state.  Drives hs_pose_step through the C ABI with a synthetic sequence."""
+    import ctypes
+    from hier_slam_b200 import _lib
+    lib = _lib.load()
+    f = dict(dtype=torch.float32, device="cuda")
+    vp = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    g = torch.Generator().manual_seed(3)
+
+    def run(sequence):
+        rot, tran = torch.tensor([1.0, 0.02, -0.01, 0.03], **f), torch.tensor([0.1, -0.2, 0.05], **f)
+        state, w2c, loss = torch.zeros(32, **f), torch.zeros(16, **f), torch.zeros(1, **f)
+        state[15] = 1e20
+        for lval, dpose, info in sequence:
+            loss.fill_(lval)
+            _lib.check(lib.hs_pose_step(vp(rot), vp(tran), vp(dpose), vp(loss), vp(state), vp(w2c), vp(info), 4e-4, 2e-3, 0.9,
+                                        0.999, 1e-8, 1, stream), "hs_pose_step")
+        torch.cuda.synchronize()
+        return rot.cpu(), tran.cpu(), state.cpu()
+    d1, d2 = torch.randn(3, 4, generator=g).cuda(), torch.randn(3, 4, generator=g).cuda()
+    ok = torch.tensor([1000, 50, 3, 0], dtype=torch.int32, device="cuda")
+    over = torch.tensor([9000, 700, 3, 1], dtype=torch.int32, device="cuda")
+    zero = torch.zeros(3, 4, **f)
+    r_a, t_a, s_a = run([(5.0, d1, ok), (0.0, zero, over), (4.0, d2, ok)])
+    r_b, t_b, s_b = run([(5.0, d1, ok), (4.0, d2, ok)])
+    assert s_a[24] == 1 and s_b[24] == 0                                  # latched although the LAST iteration fitted
+    assert s_a[25] == 9000 and s_a[26] == 700                             # what the frame needed, for the re-capture
+    assert torch.equal(r_a, r_b) and torch.equal(t_a, t_b)                # the overflowed iteration moved nothing
+    assert torch.equal(s_a[:24], s_b[:24]) and s_a[15] == 4.0             # ... and loss 0 did not become the best candidate
+    assert s_a[14] == 2                                                   # two optimiser steps, not three
+    # the candidate is the pose AFTER the step that followed the smallest loss (scripts/hierslam.py:1851-1858)
+    assert torch.equal(s_b[16:20], r_b) and torch.equal(s_b[20:23], t_b)
 
 
 def test_keyframe_overlap_counts_match_the_reference_loop():
