@@ -186,7 +186,7 @@ def _camera(background, scale_modifier, viewmatrix, projmatrix, tan_fovx, tan_fo
     return cam, keep
 
 
-_BUILT_S = (16, 26, 74, 102)   # semantic channel counts instantiated in libhsraster (hs_supports_semantic_channels)
+_BUILT_S = (16, 26, 32, 48, 64, 74, 102)   # semantic channel counts instantiated in libhsraster (hs_supports_semantic_channels)
 
 
 def _padded_channels(S: int) -> int:
@@ -196,7 +196,7 @@ def _padded_channels(S: int) -> int:
     for b in _BUILT_S:
         if S <= b:
             return b
-    raise RuntimeError(f"semantic channel count S={S} is not instantiated in libhsraster (built: 0,16,26,74,102; "
+    raise RuntimeError(f"semantic channel count S={S} is not instantiated in libhsraster (built: 0,16,26,32,48,64,74,102; "
                        f"other values up to 102 are zero-padded)")
 
 
@@ -215,7 +215,7 @@ def _forward(background, means3D, colors, semantics, opacity, scales, rotations,
     if semantic and semantics.numel() > 0 and (semantics.dim() != 2 or semantics.size(0) != P):
         raise RuntimeError("semantics_precomp must have dimensions (num_points, S)")
     if not lib.hs_supports_semantic_channels(S):
-        raise RuntimeError(f"semantic channel count S={S} is not instantiated in libhsraster (built: 0,16,26,74,102)")
+        raise RuntimeError(f"semantic channel count S={S} is not instantiated in libhsraster (built: 0,16,26,32,48,64,74,102)")
     use_sh = colors.numel() == 0
     if use_sh and P > 0:
         # spherical-harmonics colour path (reference forward.cu:20-71): sh is [P, M, 3]

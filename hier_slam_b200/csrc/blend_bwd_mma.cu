@@ -507,9 +507,12 @@ int launch_blend_backward_mma(int S, const Camera& cam, const GeomView& g, const
         HS_BWDM_CASE(0)
         HS_BWDM_CASE(16)
         HS_BWDM_CASE(26)
+        HS_BWDM_CASE(32)
+        HS_BWDM_CASE(48)
+        HS_BWDM_CASE(64)
         HS_BWDM_CASE(74)
         default:
-            set_error("tensor-core blend backward: S=%d is not instantiated (built: 0,16,26,74)", S);
+            set_error("tensor-core blend backward: S=%d is not instantiated (built: 0,16,26,32,48,64,74)", S);
             return 3;
     }
 #undef HS_BWDM_CASE

@@ -310,10 +310,13 @@ int launch_blend_forward(int S, const Camera& cam, const GeomView& g, const Binn
         HS_FWD_CASE(0)
         HS_FWD_CASE(16)
         HS_FWD_CASE(26)
+        HS_FWD_CASE(32)
+        HS_FWD_CASE(48)
+        HS_FWD_CASE(64)
         HS_FWD_CASE(74)
         HS_FWD_CASE(102)
         default:
-            set_error("semantic channel count S=%d is not instantiated (built: 0,16,26,74,102)", S);
+            set_error("semantic channel count S=%d is not instantiated (built: 0,16,26,32,48,64,74,102)", S);
             return 3;
     }
 #undef HS_FWD_CASE

@@ -53,7 +53,7 @@ extern "C" {
 int hs_abi_version(void) { return HS_RASTER_ABI_VERSION; }
 const char* hs_last_error(void) { return hs::last_error(); }
 
-int hs_supports_semantic_channels(int S) { return S == 0 || S == 16 || S == 26 || S == 74 || S == 102; }
+int hs_supports_semantic_channels(int S) { return S == 0 || S == 16 || S == 26 || S == 32 || S == 48 || S == 64 || S == 74 || S == 102; }
 
 size_t hs_geom_state_bytes(int P) {
     GeomView v;
@@ -225,7 +225,7 @@ int hs_forward_render(const hs_camera* c, int P, int S, int R, int binning_hint,
     Camera cam;
     if (make_camera(c, &cam)) return 1;
     if (!hs_supports_semantic_channels(S)) {
-        set_error("semantic channel count S=%d is not instantiated (built: 0,16,26,74,102)", S);
+        set_error("semantic channel count S=%d is not instantiated (built: 0,16,26,32,48,64,74,102)", S);
         return 3;
     }
     if (image_state == nullptr || out_color == nullptr || out_depth == nullptr || out_median_depth == nullptr ||
@@ -298,7 +298,7 @@ int hs_backward(const hs_camera* c, int P, int S, int R, const float* means3D, c
     if (make_camera(c, &cam)) return 1;
     if (P <= 0) return 0;
     if (!hs_supports_semantic_channels(S)) {
-        set_error("semantic channel count S=%d is not instantiated (built: 0,16,26,74,102)", S);
+        set_error("semantic channel count S=%d is not instantiated (built: 0,16,26,32,48,64,74,102)", S);
         return 3;
     }
     const size_t N = (size_t)cam.W * cam.H;

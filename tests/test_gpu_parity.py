@@ -103,7 +103,9 @@ def test_against_reference_golden(path):
 
 @pytest.mark.parametrize("key,S,semantic", [("tiny", 26, True), ("small", 26, True), ("tiny", 16, True),
                                             ("small", 74, True), ("tiny", 102, True), ("small", 102, True),
-                                            ("small", 0, False)])
+                                            ("small", 0, False),
+                                            # channel counts between the reference's four (config.h:18): own instantiations
+                                            ("small", 32, True), ("tiny", 48, True), ("small", 64, True)])
 def test_against_cpu_oracle(key, S, semantic):
     C, Settings = new_impl()
     cfg = CONFIGS[key]
