@@ -81,7 +81,7 @@ def test_padded_channel_counts():
     """Channel counts without their own kernel instantiation map to the next larger one (zero-padded); more than the
     largest instantiation is an error, not a fallback."""
     from hier_slam_b200 import _C
-    assert [_C._padded_channels(s) for s in (1, 5, 16, 17, 26, 27, 74, 75, 102)] == [16, 16, 16, 26, 26, 74, 74, 102, 102]
+    assert [_C._padded_channels(s) for s in (1, 5, 16, 17, 26, 27, 33, 50, 65, 74, 75, 102)] == [16, 16, 16, 26, 26, 32, 48, 64, 74, 74, 102, 102]
     with pytest.raises(RuntimeError, match="not instantiated"):
         _C._padded_channels(103)
 
