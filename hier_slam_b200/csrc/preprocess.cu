@@ -271,10 +271,30 @@ int launch_mark_visible(int P, const float* means3D, const float* view, const fl
 }
 
 // ------------------------------------------------------------------------------------------------------
-// Per-Gaussian backward: computeCov2DCUDA + preprocessCUDA(bwd) + computeCov3D(bwd) fused into one pass
-// (reference: cuda_rasterizer/backward.cu:144-274, 278-341, 346-412).  Every output row is written
-// (zeros for culled Gaussians), so the output tensors need no memset.
+// Per-Gaussian backward (reference behaviour: cuda_rasterizer/backward.cu:144-274, 278-341, 346-412 -- three kernels
+// there, one pass here).  Every output row is written (zeros for culled Gaussians), so the outputs need no memset.
+//
+// Written from the math in vector form, not from the reference's expanded scalar expressions:
+//   A      = J2 Rw            2x3, rows a0, a1: the affine map camera-frame covariance -> pixel covariance,
+//                             J2 = [[fx/tz, 0, -fx cx/tz], [0, fy/tz, -fy cy/tz]], cx = clamp(tx/tz), cy = clamp(ty/tz)
+//   cov2D  = A Sigma A^T + 0.3 I = [[a, b], [b, c]],  conic = adj(cov2D) / det
+//   H      = dL/dcov2D (symmetric 2x2) = -adj G adj^T / (det^2 + 1e-7),  G = [[g.x, g.y], [g.y, g.w]] = dL/dconic
+//   N      = dL/dSigma (symmetric 3x3) = A^T H A            -> dL_dcov3D = (N00, 2 N01, 2 N02, N11, 2 N12, N22)
+//   D      = dL/dA = 2 H (A Sigma)                          -> dL/dJ2 = D Rw^T -> dL/dt -> dL/dmean = Rw^T dL/dt
+//   Sigma  = Q diag(s^2) Q^T, Q = rotation of the (unnormalised) quaternion, s = modifier * scale:
+//            dL/ds_k = 2 s_k q_k^T N q_k,  dL/dQ = E with E[:,k] = 2 s_k^2 N q_k,  dL/dquat from E's symmetric / antisymmetric parts.
+// Like the reference, the clamped tx, ty are treated as independent variables (their gradient is masked where the clamp
+// was active) and no normalisation backward is applied to the quaternion.
 // ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float dot3(const float3 a, const float3 b) { return fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)); }
+__device__ __forceinline__ float3 comb2(const float s, const float3 a, const float t, const float3 b) {   // s a + t b
+    return {fmaf(t, b.x, s * a.x), fmaf(t, b.y, s * a.y), fmaf(t, b.z, s * a.z)};
+}
+__device__ __forceinline__ float3 sym3_apply(const float* S6, const float3 v) {   // (xx xy xz yy yz zz) v
+    return {fmaf(S6[2], v.z, fmaf(S6[1], v.y, S6[0] * v.x)), fmaf(S6[4], v.z, fmaf(S6[3], v.y, S6[1] * v.x)),
+            fmaf(S6[5], v.z, fmaf(S6[4], v.y, S6[2] * v.x))};
+}
+
 __global__ void __launch_bounds__(256) geom_backward_kernel(
     int P, const float* __restrict__ means3D, const int* __restrict__ radii, const float* __restrict__ scales,
     const float4* __restrict__ rotations, const float* __restrict__ cov3D_precomp, Camera cam,
@@ -296,127 +316,113 @@ __global__ void __launch_bounds__(256) geom_backward_kernel(
     float4 g_rot = {0.f, 0.f, 0.f, 0.f};
     if (valid && radii[idx] > 0) {
         const float3 mean = {means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]};
-        float cov3D[6];
+        float Sig[6];
         float3 sc = {0.f, 0.f, 0.f};
-        float4 rot = {0.f, 0.f, 0.f, 0.f};
+        float4 quat = {0.f, 0.f, 0.f, 0.f};
         if (has_scales) {
             sc = {scales[3 * idx], scales[3 * idx + 1], scales[3 * idx + 2]};
-            rot = __ldg(rotations + idx);
-            cov3d_from_scale_rot(sc, cam.scale_modifier, rot, cov3D);
+            quat = __ldg(rotations + idx);
+            cov3d_from_scale_rot(sc, cam.scale_modifier, quat, Sig);      // the forward's own function: same Sigma
         } else {
 #pragma unroll
-            for (int k = 0; k < 6; k++) cov3D[k] = __ldg(cov3D_precomp + (size_t)idx * 6 + k);
+            for (int k = 0; k < 6; k++) Sig[k] = __ldg(cov3D_precomp + (size_t)idx * 6 + k);
         }
-        // ---- conic -> cov2D -> cov3D / mean (backward.cu:144-274)
-        const float4 dc4 = __ldg(dL_dconic + idx);
-        const float3 dL_dcon = {dc4.x, dc4.y, dc4.w};
-        const float h_x = cam.focal_x, h_y = cam.focal_y;
-        float3 t = xform4x3(mean, s_view);
-        const float limx = 1.3f * cam.tanfovx;
-        const float limy = 1.3f * cam.tanfovy;
-        const float txtz = t.x / t.z;
-        const float tytz = t.y / t.z;
-        t.x = min(limx, max(-limx, txtz)) * t.z;
-        t.y = min(limy, max(-limy, tytz)) * t.z;
-        const float x_grad_mul = txtz < -limx || txtz > limx ? 0 : 1;
-        const float y_grad_mul = tytz < -limy || tytz > limy ? 0 : 1;
-        M3 J = m3_make(h_x / t.z, 0.0f, -(h_x * t.x) / (t.z * t.z), 0.0f, h_y / t.z, -(h_y * t.y) / (t.z * t.z), 0, 0, 0);
-        M3 W = m3_make(s_view[0], s_view[4], s_view[8], s_view[1], s_view[5], s_view[9], s_view[2], s_view[6], s_view[10]);
-        M3 Vrk = m3_make(cov3D[0], cov3D[1], cov3D[2], cov3D[1], cov3D[3], cov3D[4], cov3D[2], cov3D[4], cov3D[5]);
-        M3 T = m3_mul(W, J);
-        M3 cov2D = m3_mul(m3_mul(m3_transpose(T), m3_transpose(Vrk)), T);
-        float a = cov2D.m[0][0] += 0.3f;
-        float b = cov2D.m[0][1];
-        float c = cov2D.m[1][1] += 0.3f;
-        float denom = a * c - b * b;
-        float dL_da = 0, dL_db = 0, dL_dc = 0;
-        float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
-        if (denom2inv != 0) {
-            dL_da = denom2inv * (-c * c * dL_dcon.x + 2 * b * c * dL_dcon.y + (denom - a * c) * dL_dcon.z);
-            dL_dc = denom2inv * (-a * a * dL_dcon.z + 2 * a * b * dL_dcon.y + (denom - a * c) * dL_dcon.x);
-            dL_db = denom2inv * 2 * (b * c * dL_dcon.x - (denom + 2 * b * b) * dL_dcon.y + a * b * dL_dcon.z);
-            g_cov[0] = (T.m[0][0] * T.m[0][0] * dL_da + T.m[0][0] * T.m[1][0] * dL_db + T.m[1][0] * T.m[1][0] * dL_dc);
-            g_cov[3] = (T.m[0][1] * T.m[0][1] * dL_da + T.m[0][1] * T.m[1][1] * dL_db + T.m[1][1] * T.m[1][1] * dL_dc);
-            g_cov[5] = (T.m[0][2] * T.m[0][2] * dL_da + T.m[0][2] * T.m[1][2] * dL_db + T.m[1][2] * T.m[1][2] * dL_dc);
-            g_cov[1] = 2 * T.m[0][0] * T.m[0][1] * dL_da + (T.m[0][0] * T.m[1][1] + T.m[0][1] * T.m[1][0]) * dL_db + 2 * T.m[1][0] * T.m[1][1] * dL_dc;
-            g_cov[2] = 2 * T.m[0][0] * T.m[0][2] * dL_da + (T.m[0][0] * T.m[1][2] + T.m[0][2] * T.m[1][0]) * dL_db + 2 * T.m[1][0] * T.m[1][2] * dL_dc;
-            g_cov[4] = 2 * T.m[0][2] * T.m[0][1] * dL_da + (T.m[0][1] * T.m[1][2] + T.m[0][2] * T.m[1][1]) * dL_db + 2 * T.m[1][1] * T.m[1][2] * dL_dc;
+        // rows of the world-to-camera rotation (s_view is the transposed matrix, flat index 4 c + r)
+        const float3 w0 = {s_view[0], s_view[4], s_view[8]}, w1 = {s_view[1], s_view[5], s_view[9]},
+                     w2 = {s_view[2], s_view[6], s_view[10]};
+        const float3 t = xform4x3(mean, s_view);
+        const float iz = 1.0f / t.z;
+        const float limx = 1.3f * cam.tanfovx, limy = 1.3f * cam.tanfovy;
+        const float ux = t.x * iz, uy = t.y * iz;
+        const float cx = fminf(limx, fmaxf(-limx, ux)), cy = fminf(limy, fmaxf(-limy, uy));
+        const float keep_x = (ux < -limx || ux > limx) ? 0.f : 1.f, keep_y = (uy < -limy || uy > limy) ? 0.f : 1.f;
+        const float fxz = cam.focal_x * iz, fyz = cam.focal_y * iz;
+        const float3 a0 = comb2(fxz, w0, -fxz * cx, w2), a1 = comb2(fyz, w1, -fyz * cy, w2);
+        const float3 Sa0 = sym3_apply(Sig, a0), Sa1 = sym3_apply(Sig, a1);
+        const float ca = dot3(a0, Sa0) + 0.3f, cb = dot3(a0, Sa1), cc = dot3(a1, Sa1) + 0.3f;
+        const float det = ca * cc - cb * cb;
+        const float w = 1.0f / (det * det + 0.0000001f);
+        // H = -w adj G adj^T with adj = [[cc, -cb], [-cb, ca]]
+        const float4 gc = __ldg(dL_dconic + idx);     // (d/dconic.x, d/dconic.y, unused, d/dconic.z)
+        float H00 = 0.f, H01 = 0.f, H11 = 0.f;
+        if (w != 0.f) {
+            const float gu0 = gc.x * cc - gc.y * cb, gu1 = gc.y * cc - gc.w * cb;     // G (cc, -cb)^T
+            const float gv0 = gc.y * ca - gc.x * cb, gv1 = gc.w * ca - gc.y * cb;     // G (-cb, ca)^T
+            H00 = -w * (cc * gu0 - cb * gu1);
+            H01 = -w * (cc * gv0 - cb * gv1);
+            H11 = -w * (ca * gv1 - cb * gv0);
         }
-        float dL_dT00 = 2 * (T.m[0][0] * Vrk.m[0][0] + T.m[0][1] * Vrk.m[0][1] + T.m[0][2] * Vrk.m[0][2]) * dL_da +
-                        (T.m[1][0] * Vrk.m[0][0] + T.m[1][1] * Vrk.m[0][1] + T.m[1][2] * Vrk.m[0][2]) * dL_db;
-        float dL_dT01 = 2 * (T.m[0][0] * Vrk.m[1][0] + T.m[0][1] * Vrk.m[1][1] + T.m[0][2] * Vrk.m[1][2]) * dL_da +
-                        (T.m[1][0] * Vrk.m[1][0] + T.m[1][1] * Vrk.m[1][1] + T.m[1][2] * Vrk.m[1][2]) * dL_db;
-        float dL_dT02 = 2 * (T.m[0][0] * Vrk.m[2][0] + T.m[0][1] * Vrk.m[2][1] + T.m[0][2] * Vrk.m[2][2]) * dL_da +
-                        (T.m[1][0] * Vrk.m[2][0] + T.m[1][1] * Vrk.m[2][1] + T.m[1][2] * Vrk.m[2][2]) * dL_db;
-        float dL_dT10 = 2 * (T.m[1][0] * Vrk.m[0][0] + T.m[1][1] * Vrk.m[0][1] + T.m[1][2] * Vrk.m[0][2]) * dL_dc +
-                        (T.m[0][0] * Vrk.m[0][0] + T.m[0][1] * Vrk.m[0][1] + T.m[0][2] * Vrk.m[0][2]) * dL_db;
-        float dL_dT11 = 2 * (T.m[1][0] * Vrk.m[1][0] + T.m[1][1] * Vrk.m[1][1] + T.m[1][2] * Vrk.m[1][2]) * dL_dc +
-                        (T.m[0][0] * Vrk.m[1][0] + T.m[0][1] * Vrk.m[1][1] + T.m[0][2] * Vrk.m[1][2]) * dL_db;
-        float dL_dT12 = 2 * (T.m[1][0] * Vrk.m[2][0] + T.m[1][1] * Vrk.m[2][1] + T.m[1][2] * Vrk.m[2][2]) * dL_dc +
-                        (T.m[0][0] * Vrk.m[2][0] + T.m[0][1] * Vrk.m[2][1] + T.m[0][2] * Vrk.m[2][2]) * dL_db;
-        float dL_dJ00 = W.m[0][0] * dL_dT00 + W.m[0][1] * dL_dT01 + W.m[0][2] * dL_dT02;
-        float dL_dJ02 = W.m[2][0] * dL_dT00 + W.m[2][1] * dL_dT01 + W.m[2][2] * dL_dT02;
-        float dL_dJ11 = W.m[1][0] * dL_dT10 + W.m[1][1] * dL_dT11 + W.m[1][2] * dL_dT12;
-        float dL_dJ12 = W.m[2][0] * dL_dT10 + W.m[2][1] * dL_dT11 + W.m[2][2] * dL_dT12;
-        float tz = 1.f / t.z;
-        float tz2 = tz * tz;
-        float tz3 = tz2 * tz;
-        float dL_dtx = x_grad_mul * -h_x * tz2 * dL_dJ02;
-        float dL_dty = y_grad_mul * -h_y * tz2 * dL_dJ12;
-        float dL_dtz = -h_x * tz2 * dL_dJ00 - h_y * tz2 * dL_dJ11 + (2 * h_x * t.x) * tz3 * dL_dJ02 + (2 * h_y * t.y) * tz3 * dL_dJ12;
-        // transformVec4x3Transpose (auxiliary.h:89-97)
-        g_mean = {s_view[0] * dL_dtx + s_view[1] * dL_dty + s_view[2] * dL_dtz,
-                  s_view[4] * dL_dtx + s_view[5] * dL_dty + s_view[6] * dL_dtz,
-                  s_view[8] * dL_dtx + s_view[9] * dL_dty + s_view[10] * dL_dtz};
+        // N = A^T H A = a0 (x) y0 + a1 (x) y1 with y0 = H00 a0 + H01 a1, y1 = H01 a0 + H11 a1
+        const float3 y0 = comb2(H00, a0, H01, a1), y1 = comb2(H01, a0, H11, a1);
+        float N[6];
+        N[0] = fmaf(a1.x, y1.x, a0.x * y0.x);
+        N[1] = fmaf(a1.x, y1.y, a0.x * y0.y);
+        N[2] = fmaf(a1.x, y1.z, a0.x * y0.z);
+        N[3] = fmaf(a1.y, y1.y, a0.y * y0.y);
+        N[4] = fmaf(a1.y, y1.z, a0.y * y0.z);
+        N[5] = fmaf(a1.z, y1.z, a0.z * y0.z);
+        g_cov[0] = N[0];
+        g_cov[1] = 2.f * N[1];
+        g_cov[2] = 2.f * N[2];
+        g_cov[3] = N[3];
+        g_cov[4] = 2.f * N[4];
+        g_cov[5] = N[5];
+        // D = 2 H (A Sigma); only four entries of dL/dJ2 = D Rw^T are live
+        const float3 d0 = comb2(2.f * H00, Sa0, 2.f * H01, Sa1), d1 = comb2(2.f * H01, Sa0, 2.f * H11, Sa1);
+        const float e00 = dot3(d0, w0), e02 = dot3(d0, w2), e11 = dot3(d1, w1), e12 = dot3(d1, w2);
+        const float iz2 = iz * iz;
+        const float gtx = -cam.focal_x * iz2 * e02 * keep_x;
+        const float gty = -cam.focal_y * iz2 * e12 * keep_y;
+        const float gtz = iz2 * (2.f * (cam.focal_x * cx * e02 + cam.focal_y * cy * e12) - (cam.focal_x * e00 + cam.focal_y * e11));
+        g_mean = {fmaf(w2.x, gtz, fmaf(w1.x, gty, w0.x * gtx)), fmaf(w2.y, gtz, fmaf(w1.y, gty, w0.y * gtx)),
+                  fmaf(w2.z, gtz, fmaf(w1.z, gty, w0.z * gtx))};
 
-        // ---- mean2D path through the projection (backward.cu:368-389)
-        const float* proj = s_proj;
-        const float3 m = mean;
-        float4 m_hom = xform4x4(m, proj);
-        float m_w = 1.0f / (m_hom.w + 0.0000001f);
-        const float g2x = dL_dmean2D[3 * idx], g2y = dL_dmean2D[3 * idx + 1];
-        float mul1 = (proj[0] * m.x + proj[4] * m.y + proj[8] * m.z + proj[12]) * m_w * m_w;
-        float mul2 = (proj[1] * m.x + proj[5] * m.y + proj[9] * m.z + proj[13]) * m_w * m_w;
-        g_mean.x += (proj[0] * m_w - proj[3] * mul1) * g2x + (proj[1] * m_w - proj[3] * mul2) * g2y;
-        g_mean.y += (proj[4] * m_w - proj[7] * mul1) * g2x + (proj[5] * m_w - proj[7] * mul2) * g2y;
-        g_mean.z += (proj[8] * m_w - proj[11] * mul1) * g2x + (proj[9] * m_w - proj[11] * mul2) * g2y;
-        // ---- depth path through the view matrix (backward.cu:391-406)
-        const float* view = s_view;
-        const float gd = dL_ddepths[idx];
-        float mul3 = view[2] * m.x + view[6] * m.y + view[10] * m.z + view[14];
-        g_mean.x += (view[2] - view[3] * mul3) * gd;
-        g_mean.y += (view[6] - view[7] * mul3) * gd;
-        g_mean.z += (view[10] - view[11] * mul3) * gd;
+        // ---- pixel-centre path: ndc = hom.xy / (hom.w + eps); the incoming gradient is d/d(ndc) (the blend backward has
+        //      already applied the W/2, H/2 of the pixel mapping).  dL/dmean = P^T (gx iw, gy iw, 0, -(gx ndc.x + gy ndc.y) iw)
+        {
+            const float4 hom = xform4x4(mean, s_proj);
+            const float iw = 1.0f / (hom.w + 0.0000001f);
+            const float gx = dL_dmean2D[3 * idx], gy = dL_dmean2D[3 * idx + 1];
+            const float kx = gx * iw, ky = gy * iw;
+            const float kw = -(kx * hom.x + ky * hom.y) * iw;
+            g_mean.x += fmaf(s_proj[3], kw, fmaf(s_proj[1], ky, s_proj[0] * kx));
+            g_mean.y += fmaf(s_proj[7], kw, fmaf(s_proj[5], ky, s_proj[4] * kx));
+            g_mean.z += fmaf(s_proj[11], kw, fmaf(s_proj[9], ky, s_proj[8] * kx));
+        }
+        // ---- depth path: depth = third row of the view transform (its homogeneous row is kept, as the reference does)
+        {
+            const float gd = dL_ddepths[idx];
+            g_mean.x += (s_view[2] - s_view[3] * t.z) * gd;
+            g_mean.y += (s_view[6] - s_view[7] * t.z) * gd;
+            g_mean.z += (s_view[10] - s_view[11] * t.z) * gd;
+        }
 
-        // ---- cov3D -> scale / rotation (backward.cu:278-341)
+        // ---- Sigma = Q diag(s^2) Q^T  ->  scale and quaternion
         if (has_scales) {
-            float r = rot.x, x = rot.y, y = rot.z, z = rot.w;
-            M3 R = quat_to_rot(r, x, y, z);
+            const float r = quat.x, x = quat.y, y = quat.z, z = quat.w;
+            const M3 Qt = quat_to_rot(r, x, y, z);       // stored column-major as the TRANSPOSED rotation: Qt.m[k] = column k of Q
             const float3 s = {cam.scale_modifier * sc.x, cam.scale_modifier * sc.y, cam.scale_modifier * sc.z};
-            M3 S = m3_make(s.x, 0.f, 0.f, 0.f, s.y, 0.f, 0.f, 0.f, s.z);
-            M3 M = m3_mul(S, R);
-            M3 dSig = m3_make(g_cov[0], 0.5f * g_cov[1], 0.5f * g_cov[2], 0.5f * g_cov[1], g_cov[3], 0.5f * g_cov[4],
-                              0.5f * g_cov[2], 0.5f * g_cov[4], g_cov[5]);
-            M3 dM = m3_mul(M, dSig);
+            const float sk[3] = {s.x, s.y, s.z};
+            float E[3][3];                               // E[i][k] = dL/dQ[i][k]
+            float gs[3];
 #pragma unroll
-            for (int cc = 0; cc < 3; cc++)
-#pragma unroll
-                for (int q = 0; q < 3; q++) dM.m[cc][q] *= 2.0f;
-            M3 Rt = m3_transpose(R);
-            M3 dMt = m3_transpose(dM);
-            g_scale.x = Rt.m[0][0] * dMt.m[0][0] + Rt.m[0][1] * dMt.m[0][1] + Rt.m[0][2] * dMt.m[0][2];
-            g_scale.y = Rt.m[1][0] * dMt.m[1][0] + Rt.m[1][1] * dMt.m[1][1] + Rt.m[1][2] * dMt.m[1][2];
-            g_scale.z = Rt.m[2][0] * dMt.m[2][0] + Rt.m[2][1] * dMt.m[2][1] + Rt.m[2][2] * dMt.m[2][2];
-#pragma unroll
-            for (int q = 0; q < 3; q++) {
-                dMt.m[0][q] *= s.x;
-                dMt.m[1][q] *= s.y;
-                dMt.m[2][q] *= s.z;
+            for (int k = 0; k < 3; k++) {
+                const float3 qk = {Qt.m[0][k], Qt.m[1][k], Qt.m[2][k]};
+                const float3 nq = sym3_apply(N, qk);
+                gs[k] = 2.f * sk[k] * dot3(qk, nq);
+                const float f = 2.f * sk[k] * sk[k];
+                E[0][k] = f * nq.x;
+                E[1][k] = f * nq.y;
+                E[2][k] = f * nq.z;
             }
-            g_rot.x = 2 * z * (dMt.m[0][1] - dMt.m[1][0]) + 2 * y * (dMt.m[2][0] - dMt.m[0][2]) + 2 * x * (dMt.m[1][2] - dMt.m[2][1]);
-            g_rot.y = 2 * y * (dMt.m[1][0] + dMt.m[0][1]) + 2 * z * (dMt.m[2][0] + dMt.m[0][2]) + 2 * r * (dMt.m[1][2] - dMt.m[2][1]) - 4 * x * (dMt.m[2][2] + dMt.m[1][1]);
-            g_rot.z = 2 * x * (dMt.m[1][0] + dMt.m[0][1]) + 2 * r * (dMt.m[2][0] - dMt.m[0][2]) + 2 * z * (dMt.m[1][2] + dMt.m[2][1]) - 4 * y * (dMt.m[2][2] + dMt.m[0][0]);
-            g_rot.w = 2 * r * (dMt.m[0][1] - dMt.m[1][0]) + 2 * x * (dMt.m[2][0] + dMt.m[0][2]) + 2 * y * (dMt.m[1][2] + dMt.m[2][1]) - 4 * z * (dMt.m[1][1] + dMt.m[0][0]);
+            g_scale = {gs[0], gs[1], gs[2]};
+            // antisymmetric part (axial vector) and symmetric sums of E
+            const float ax = E[2][1] - E[1][2], ay = E[0][2] - E[2][0], az = E[1][0] - E[0][1];
+            const float sxy = E[0][1] + E[1][0], sxz = E[0][2] + E[2][0], syz = E[1][2] + E[2][1];
+            g_rot.x = 2.f * (x * ax + y * ay + z * az);
+            g_rot.y = 2.f * (r * ax + y * sxy + z * sxz) - 4.f * x * (E[1][1] + E[2][2]);
+            g_rot.z = 2.f * (r * ay + x * sxy + z * syz) - 4.f * y * (E[0][0] + E[2][2]);
+            g_rot.w = 2.f * (r * az + x * sxz + y * syz) - 4.f * z * (E[0][0] + E[1][1]);
         }
     }
     if (valid) {

@@ -71,7 +71,7 @@ __device__ inline float hi_part(float x) { return __uint_as_float(__float_as_uin
 // dynamic shared memory: sA[M*K] sAlo[M*K] sB[N*K] sBlo[N*K]
 __global__ void __launch_bounds__(128) probe_kernel(const float* __restrict__ A, const float* __restrict__ B,
                                                     float* __restrict__ D, int* __restrict__ err, int N, int K, int a_mode,
-                                                    int b_mode, int split) {
+                                                    int b_mode, int split, int swap_mn) {
     extern __shared__ __align__(128) float dsm[];
     float* sA = dsm;
     float* sAlo = sA + M * K;
@@ -132,7 +132,8 @@ __global__ void __launch_bounds__(128) probe_kernel(const float* __restrict__ A,
             const uint32_t idesc = instr_desc_tf32(N, a_mode == 1, b_mode == 1);
             // byte distances of the canonical layouts
             const uint32_t lbo_k = 128, sbo_k = (uint32_t)(K / 4) * 128;       // K-major
-            const uint32_t lbo_mn = 128, sbo_mn = (uint32_t)(K / 8) * 128;     // MN-major
+            uint32_t lbo_mn = 128, sbo_mn = (uint32_t)(K / 8) * 128;           // MN-major
+            if (swap_mn) { const uint32_t t_ = lbo_mn; lbo_mn = sbo_mn; sbo_mn = t_; }   // experiment: the two fields exchanged
             bool first = true;
             for (int pass = 0; pass < (split ? 3 : 1); pass++) {               // hi*hi, lo*hi, hi*lo
                 const float* pa = pass == 1 ? sAlo : sA;
@@ -140,8 +141,8 @@ __global__ void __launch_bounds__(128) probe_kernel(const float* __restrict__ A,
                 const uint32_t a0 = (uint32_t)__cvta_generic_to_shared(pa), b0 = (uint32_t)__cvta_generic_to_shared(pb);
                 for (int k = 0; k < K / UMMA_K; k++) {
                     // K-major: 8 tf32 along K = 2 core matrices = 2 LBO; MN-major: one 8-row K group = 1 LBO
-                    const uint64_t da = a_mode == 1 ? smem_desc(a0 + k * lbo_mn, lbo_mn, sbo_mn) : smem_desc(a0 + k * 2 * lbo_k, lbo_k, sbo_k);
-                    const uint64_t db = b_mode == 1 ? smem_desc(b0 + k * lbo_mn, lbo_mn, sbo_mn) : smem_desc(b0 + k * 2 * lbo_k, lbo_k, sbo_k);
+                    const uint64_t da = a_mode == 1 ? smem_desc(a0 + k * 128, lbo_mn, sbo_mn) : smem_desc(a0 + k * 2 * lbo_k, lbo_k, sbo_k);
+                    const uint64_t db = b_mode == 1 ? smem_desc(b0 + k * 128, lbo_mn, sbo_mn) : smem_desc(b0 + k * 2 * lbo_k, lbo_k, sbo_k);
                     const uint32_t accumulate = first ? 0u : 1u;
                     first = false;
                     if (a_mode == 2) {
@@ -190,7 +191,7 @@ __global__ void __launch_bounds__(128) probe_kernel(const float* __restrict__ A,
 static float trunc_tf32(float x) { uint32_t u; memcpy(&u, &x, 4); u &= 0xffffe000u; float r; memcpy(&r, &u, 4); return r; }
 static float round_tf32(float x) { uint32_t u; memcpy(&u, &x, 4); u += 0x1000u; u &= 0xffffe000u; float r; memcpy(&r, &u, 4); return r; }
 
-struct Case { const char* name; int N, K, a_mode, b_mode, split, exact_ints; };
+struct Case { const char* name; int N, K, a_mode, b_mode, split, exact_ints, swap_mn; };
 
 int main() {
     const Case cases[] = {
@@ -205,6 +206,11 @@ int main() {
         {"SS  A MN-major  B K-major   N=192 K=80 random, 3xTF32", 192, 80, 1, 0, 1, 0},
         {"TS  A in TMEM   B MN-major  N=80  K=96 random, 3xTF32", 80, 96, 2, 1, 1, 0},
         {"SS  A K-major   B K-major   N=256 K=32 ints", 256, 32, 0, 0, 0, 1},
+        {"SS  A K-major   B K-major   N=192 K=80 random, 3xTF32", 192, 80, 0, 0, 1, 0},
+        {"TS  A in TMEM   B K-major   N=80  K=96 random, 3xTF32", 80, 96, 2, 0, 1, 0},
+        {"SS  A K-major   B K-major   N=192 K=80 random, single tf32", 192, 80, 0, 0, 0, 0},
+        {"SS  A MN-major  B K-major   N=64  K=32 ints, LBO/SBO swapped", 64, 32, 1, 0, 0, 1, 1},
+        {"SS  A K-major   B MN-major  N=64  K=32 ints, LBO/SBO swapped", 64, 32, 0, 1, 0, 1, 1},
     };
     int failures = 0;
     for (const Case& c : cases) {
@@ -225,7 +231,7 @@ int main() {
         cudaMemset(dD, 0, sizeof(float) * M * N); cudaMemset(dErr, 0, sizeof(int));
         const size_t smem = sizeof(float) * (size_t)(2 * M * K + 2 * N * K);
         cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        probe_kernel<<<1, 128, smem>>>(dA, dB, dD, dErr, N, K, c.a_mode, c.b_mode, c.split);
+        probe_kernel<<<1, 128, smem>>>(dA, dB, dD, dErr, N, K, c.a_mode, c.b_mode, c.split, c.swap_mn);
         const cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { printf("%s: CUDA error: %s\n", c.name, cudaGetErrorString(e)); return 2; }
         cudaMemcpy(hD, dD, sizeof(float) * M * N, cudaMemcpyDeviceToHost);
@@ -249,6 +255,12 @@ int main() {
         printf("tcgen05 probe [%s]: max|D-ref| = %.3g (|ref|max %.3g), vs truncated-input ref %.3g, vs rounded-input ref %.3g  %s\n",
                c.name, worst, scale, worst_trunc, worst_round, ok ? "OK" : "MISMATCH");
         failures += !ok;
+        if (!ok) {
+            printf("    D[0][0..7]   :"); for (int n = 0; n < 8; n++) printf(" %g", hD[n]); printf("\n    ref[0][0..7] :");
+            for (int n = 0; n < 8; n++) { double r = 0; for (int k = 0; k < K; k++) r += (double)hA[k] * hB[n * K + k]; printf(" %g", r); }
+            printf("\n    D[1][0..3] D[8][0..3]:"); for (int n = 0; n < 4; n++) printf(" %g", hD[N + n]); for (int n = 0; n < 4; n++) printf(" %g", hD[8 * N + n]);
+            printf("\n");
+        }
         cudaFree(dA); cudaFree(dB); cudaFree(dD); cudaFree(dErr); free(hA); free(hB); free(hD);
     }
     return failures == 0 ? 0 : 1;
