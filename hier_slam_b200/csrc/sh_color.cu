@@ -1,7 +1,8 @@
 // Spherical-harmonics colour path: view-dependent RGB of every visible Gaussian from degree <= 3 SH coefficients,
 // and its backward (coefficient gradients + the view-direction term that flows into dL/dmean).
 // Reference behaviour: cuda_rasterizer/forward.cu:20-71 (computeColorFromSH, +0.5, clamp at 0, `clamped` flags),
-// backward.cu:20-139 and auxiliary.h:107-117 (dnormvdv).  Hier-SLAM itself always passes precomputed colours
+// backward.cu:20-139 and auxiliary.h:107-117 (dnormvdv); the backward here is derived from the basis polynomials
+// (sh_basis_gradient) and the tangent-plane projector of the normalisation, not from the reference's expanded terms.  Hier-SLAM itself always passes precomputed colours
 // (utils/slam_helpers.py:211), so this path exists for API completeness; it is a plain one-thread-per-Gaussian pass
 // that runs only when `shs` is given.  One basis evaluation is shared by the forward and the backward.
 #include "hs_common.cuh"
@@ -42,6 +43,30 @@ __device__ __forceinline__ void sh_basis(int deg, float x, float y, float z, flo
             }
         }
     }
+}
+
+// j[k] = gradient of the k-th basis polynomial of sh_basis with respect to (x, y, z); entries 1 .. (deg+1)^2 - 1 are written
+__device__ __forceinline__ void sh_basis_gradient(int deg, float x, float y, float z, float (*j)[3]) {
+    auto set = [&](int k, float dx, float dy, float dz) { j[k][0] = dx; j[k][1] = dy; j[k][2] = dz; };
+    if (deg < 1) return;
+    set(1, 0.f, -kC1, 0.f);                     // -C1 y
+    set(2, 0.f, 0.f, kC1);                      //  C1 z
+    set(3, -kC1, 0.f, 0.f);                     // -C1 x
+    if (deg < 2) return;
+    set(4, kC2[0] * y, kC2[0] * x, 0.f);                                   // xy
+    set(5, 0.f, kC2[1] * z, kC2[1] * y);                                   // yz
+    set(6, -2.f * kC2[2] * x, -2.f * kC2[2] * y, 4.f * kC2[2] * z);        // 2zz - xx - yy
+    set(7, kC2[3] * z, 0.f, kC2[3] * x);                                   // xz
+    set(8, 2.f * kC2[4] * x, -2.f * kC2[4] * y, 0.f);                      // xx - yy
+    if (deg < 3) return;
+    const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+    set(9, 6.f * kC3[0] * xy, 3.f * kC3[0] * (xx - yy), 0.f);                                      // y (3xx - yy)
+    set(10, kC3[1] * yz, kC3[1] * xz, kC3[1] * xy);                                                // xyz
+    set(11, -2.f * kC3[2] * xy, kC3[2] * (4.f * zz - xx - 3.f * yy), 8.f * kC3[2] * yz);           // y (4zz - xx - yy)
+    set(12, -6.f * kC3[3] * xz, -6.f * kC3[3] * yz, 3.f * kC3[3] * (2.f * zz - xx - yy));          // z (2zz - 3xx - 3yy)
+    set(13, kC3[4] * (4.f * zz - 3.f * xx - yy), -2.f * kC3[4] * xy, 8.f * kC3[4] * xz);           // x (4zz - xx - yy)
+    set(14, 2.f * kC3[5] * xz, -2.f * kC3[5] * yz, kC3[5] * (xx - yy));                            // z (xx - yy)
+    set(15, 3.f * kC3[6] * (xx - yy), -6.f * kC3[6] * xy, 0.f);                                    // x (xx - 3yy)
 }
 
 __global__ void __launch_bounds__(256) sh_forward_kernel(int P, int deg, int M, const float* __restrict__ means3D,
@@ -106,34 +131,23 @@ __global__ void __launch_bounds__(256) sh_backward_kernel(int P, int deg, int M,
         out[3 * k + 2] = w * g.z;
     }
     if (deg == 0) return;   // degree 0 is view independent
-    // s[k] = <sh[k], dL/dRGB>: the colour gradient seen through coefficient k
+    // View-direction term: colour = sum_k b_k(dir) sh_k, so dL/ddir = sum_k s_k grad b_k(dir) with
+    // s_k = <sh_k, dL/dRGB> (the colour gradient seen through coefficient k) and grad b_k the gradient of the k-th real
+    // SH polynomial (sh_basis_gradient, derived term by term from sh_basis).
     const float* sh = shs + (size_t)idx * M * 3;
-    float s[16];
-    for (int k = 0; k < n; k++) s[k] = sh[3 * k] * g.x + sh[3 * k + 1] * g.y + sh[3 * k + 2] * g.z;
-    // d colour / d direction (backward.cu:58-123), contracted with dL/dRGB
-    float gx = -kC1 * s[3], gy = -kC1 * s[1], gz = kC1 * s[2];
-    if (deg > 1) {
-        gx += kC2[0] * y * s[4] + kC2[2] * 2.f * -x * s[6] + kC2[3] * z * s[7] + kC2[4] * 2.f * x * s[8];
-        gy += kC2[0] * x * s[4] + kC2[1] * z * s[5] + kC2[2] * 2.f * -y * s[6] + kC2[4] * 2.f * -y * s[8];
-        gz += kC2[1] * y * s[5] + kC2[2] * 2.f * 2.f * z * s[6] + kC2[3] * x * s[7];
-        if (deg > 2) {
-            const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
-            gx += kC3[0] * s[9] * 3.f * 2.f * xy + kC3[1] * s[10] * yz + kC3[2] * s[11] * -2.f * xy +
-                  kC3[3] * s[12] * -3.f * 2.f * xz + kC3[4] * s[13] * (-3.f * xx + 4.f * zz - yy) +
-                  kC3[5] * s[14] * 2.f * xz + kC3[6] * s[15] * 3.f * (xx - yy);
-            gy += kC3[0] * s[9] * 3.f * (xx - yy) + kC3[1] * s[10] * xz + kC3[2] * s[11] * (-3.f * yy + 4.f * zz - xx) +
-                  kC3[3] * s[12] * -3.f * 2.f * yz + kC3[4] * s[13] * -2.f * xy + kC3[5] * s[14] * -2.f * yz +
-                  kC3[6] * s[15] * -3.f * 2.f * xy;
-            gz += kC3[1] * s[10] * xy + kC3[2] * s[11] * 4.f * 2.f * yz + kC3[3] * s[12] * 3.f * (2.f * zz - xx - yy) +
-                  kC3[4] * s[13] * 4.f * 2.f * xz + kC3[5] * s[14] * (xx - yy);
-        }
+    float jac[16][3];
+    sh_basis_gradient(deg, x, y, z, jac);
+    float3 gdir = {0.f, 0.f, 0.f};
+    for (int k = 1; k < n; k++) {
+        const float sk = sh[3 * k] * g.x + sh[3 * k + 1] * g.y + sh[3 * k + 2] * g.z;
+        gdir.x = fmaf(sk, jac[k][0], gdir.x);
+        gdir.y = fmaf(sk, jac[k][1], gdir.y);
+        gdir.z = fmaf(sk, jac[k][2], gdir.z);
     }
-    // through the normalisation of the direction (auxiliary.h:107-117)
-    const float sum2 = d0.x * d0.x + d0.y * d0.y + d0.z * d0.z;
-    const float inv32 = 1.0f / sqrtf(sum2 * sum2 * sum2);
-    const float3 dm = {((sum2 - d0.x * d0.x) * gx - d0.y * d0.x * gy - d0.z * d0.x * gz) * inv32,
-                       (-d0.x * d0.y * gx + (sum2 - d0.y * d0.y) * gy - d0.z * d0.y * gz) * inv32,
-                       (-d0.x * d0.z * gx - d0.y * d0.z * gy + (sum2 - d0.z * d0.z) * gz) * inv32};
+    // dir = d0 / |d0|: the Jacobian is the tangent-plane projector (I - dir dir^T) / |d0|
+    const float radial = x * gdir.x + y * gdir.y + z * gdir.z;
+    const float il = 1.0f / len;
+    const float3 dm = {(gdir.x - x * radial) * il, (gdir.y - y * radial) * il, (gdir.z - z * radial) * il};
     dL_dmeans3D[3 * idx] += dm.x;
     dL_dmeans3D[3 * idx + 1] += dm.y;
     dL_dmeans3D[3 * idx + 2] += dm.z;
