@@ -469,6 +469,25 @@ int hs_leaf_cross_entropy(const float* sem, const int* labels, const float* weig
                                      (cudaStream_t)stream_);
 }
 
+void hs_leaf_tc_debug(long long* stamps) { leaf_tc_set_debug(stamps); }
+size_t hs_leaf_ce_workspace_bytes(int channels, int classes) { return leaf_tc_workspace_bytes(channels, classes); }
+
+int hs_leaf_cross_entropy_tc(const float* sem, const int* labels, const float* weight, const float* bias, int channels,
+                             int classes, size_t pixels, float scale, float* loss, float* lse, float* grad_sem, int flags,
+                             float* grad_weight, float* grad_bias, void* workspace, size_t workspace_bytes, void* stream_) {
+    if (sem == nullptr || labels == nullptr || weight == nullptr || loss == nullptr || lse == nullptr ||
+        grad_sem == nullptr) {
+        set_error("hs_leaf_cross_entropy_tc: NULL argument");
+        return 1;
+    }
+    int rc = launch_leaf_cross_entropy_tc(sem, labels, weight, bias, channels, classes, pixels, scale, loss, lse, grad_sem,
+                                          flags & HS_LEAF_ACCUMULATE, (float*)workspace, workspace_bytes,
+                                          (cudaStream_t)stream_);
+    if (rc || grad_weight == nullptr) return rc;
+    return launch_leaf_weight_grad(sem, labels, weight, bias, lse, channels, classes, pixels, scale, grad_weight, grad_bias,
+                                   (flags & HS_LEAF_TF32) != 0, (cudaStream_t)stream_);
+}
+
 int hs_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
                     unsigned char* present, void* stream_) {
     return launch_mark_visible(P, means3D, viewmatrix, projmatrix, (bool*)present, (cudaStream_t)stream_, false);

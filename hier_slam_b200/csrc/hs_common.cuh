@@ -179,6 +179,14 @@ int launch_l1_ssim(const float* pred, const float* target, int C, int H, int W, 
 int launch_leaf_cross_entropy(const float* sem, const int* labels, const float* weight, const float* bias, int S, int L,
                               size_t HW, float scale, float* loss, float* lse, float* grad_sem, int accumulate,
                               float* grad_weight, float* grad_bias, int single_tf32, cudaStream_t stream);
+size_t leaf_tc_workspace_bytes(int S, int L);
+void leaf_tc_set_debug(long long* p);
+int launch_leaf_cross_entropy_tc(const float* sem, const int* labels, const float* weight, const float* bias, int S, int L,
+                                 size_t HW, float scale, float* loss, float* lse, float* grad_sem, int accumulate,
+                                 float* workspace, size_t workspace_bytes, cudaStream_t stream);
+int launch_leaf_weight_grad(const float* sem, const int* labels, const float* weight, const float* bias, const float* lse,
+                            int S, int L, size_t HW, float scale, float* grad_weight, float* grad_bias, int single_tf32,
+                            cudaStream_t stream);
 int launch_mark_visible(int P, const float* means3D, const float* view, const float* proj, bool* present,
                         cudaStream_t stream, bool debug);
 

@@ -562,14 +562,16 @@ __global__ void __launch_bounds__(32 * NWARP, 2) leaf_ce_weight_kernel(
     }
 }
 
+// pixel_pass = false: only the weight-gradient kernel (lse comes from an earlier pixel pass, e.g. the tcgen05 kernel)
 template <int NJ, bool P3>
 static int launch_t(const float* sem, const int* labels, const float* weight, const float* bias, int S, int L, size_t HW,
                     float scale, float* loss, float* lse, float* grad_sem, int accumulate, float* grad_weight,
-                    float* grad_bias, cudaStream_t stream) {
+                    float* grad_bias, cudaStream_t stream, bool pixel_pass = true) {
     using C = Cfg<NJ>;
     const size_t n_blocks = (HW + C::BPX - 1) / C::BPX;
     constexpr int LT = 7;                     // one-pass variant: up to 112 classes
-    if (NJ <= 4 && L <= 16 * LT) {
+    if (!pixel_pass) {
+    } else if (NJ <= 4 && L <= 16 * LT) {
         using C1 = Cfg<NJ, 1>;
         auto k = leaf_ce_pixel_onepass_kernel<NJ, P3, (NJ <= 4 ? LT : 1)>;
         const size_t sh = (size_t)(2 * C1::SP * C1::XS + 16 * LT * C1::WS) * sizeof(float);
@@ -600,6 +602,27 @@ static int launch_t(const float* sem, const int* labels, const float* weight, co
 }
 
 }  // namespace leaf
+
+int launch_leaf_weight_grad(const float* sem, const int* labels, const float* weight, const float* bias, const float* lse,
+                            int S, int L, size_t HW, float scale, float* grad_weight, float* grad_bias, int single_tf32,
+                            cudaStream_t stream) {
+    if (HW == 0 || L <= 0 || grad_weight == nullptr) return 0;
+    if (S < 1 || S > 79) {
+        set_error("leaf cross-entropy: 1 <= S <= 79 semantic channels supported, got %d", S);
+        return 1;
+    }
+    const int nj = (S + 1 + 7) / 8;
+    float* l = const_cast<float*>(lse);
+#define HS_LEAFW_CASE(NJV)                                                                                              \
+    return single_tf32 ? leaf::launch_t<NJV, false>(sem, labels, weight, bias, S, L, HW, scale, nullptr, l, nullptr, 0,  \
+                                                     grad_weight, grad_bias, stream, false)                              \
+                       : leaf::launch_t<NJV, true>(sem, labels, weight, bias, S, L, HW, scale, nullptr, l, nullptr, 0,   \
+                                                    grad_weight, grad_bias, stream, false)
+    if (nj <= 3) { HS_LEAFW_CASE(3); }
+    if (nj <= 4) { HS_LEAFW_CASE(4); }
+    HS_LEAFW_CASE(10);
+#undef HS_LEAFW_CASE
+}
 
 int launch_leaf_cross_entropy(const float* sem, const int* labels, const float* weight, const float* bias, int S, int L,
                               size_t HW, float scale, float* loss, float* lse, float* grad_sem, int accumulate,

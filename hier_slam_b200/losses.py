@@ -94,6 +94,9 @@ def hierarchical_cross_entropy(sem: torch.Tensor, labels: torch.Tensor, level_si
 # HS_LEAF_TF32=1: one TF32 product per contraction in the leaf loss (torch's default convolution precision) instead of the
 # fp32-accurate 3xTF32 split
 LEAF_TF32 = os.environ.get("HS_LEAF_TF32", "0") == "1"
+# HS_LEAF_LEGACY=1: the mma.sync generation of the per-pixel pass (csrc/leaf_loss.cu) instead of the tcgen05 / TMEM / TMA
+# kernel (csrc/leaf_loss_tc.cu) -- kept for A/B measurements; both are fp32-accurate 3xTF32
+LEAF_LEGACY = os.environ.get("HS_LEAF_LEGACY", "0") == "1"
 
 
 def _stream(dev):
@@ -128,11 +131,18 @@ def _run_leaf(lib, s, lab, w2, bias, loss_weight, num_valid, loss, grad, accumul
     gw = torch.zeros(L, S, dtype=torch.float32, device=s.device) if want_wgrad else None
     gb = torch.zeros(L, dtype=torch.float32, device=s.device) if (want_wgrad and bias is not None) else None
     p = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
-    _lib.check(lib.hs_leaf_cross_entropy(p(s), p(lab), p(w2), p(bias), int(S), int(L), HW,
-                                         float(loss_weight) / max(int(num_valid), 1), p(loss), p(lse), p(grad),
-                                         (1 if accumulate else 0) | (2 if LEAF_TF32 else 0), p(gw), p(gb),
-                                         _stream(s.device)),
-               "hs_leaf_cross_entropy")
+    flags = (1 if accumulate else 0) | (2 if LEAF_TF32 else 0)
+    if LEAF_LEGACY:
+        _lib.check(lib.hs_leaf_cross_entropy(p(s), p(lab), p(w2), p(bias), int(S), int(L), HW,
+                                             float(loss_weight) / max(int(num_valid), 1), p(loss), p(lse), p(grad),
+                                             flags, p(gw), p(gb), _stream(s.device)), "hs_leaf_cross_entropy")
+        return gw, gb
+    nbytes = int(lib.hs_leaf_ce_workspace_bytes(int(S), int(L)))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=s.device)     # caching allocator: 512-byte aligned
+    _lib.check(lib.hs_leaf_cross_entropy_tc(p(s), p(lab), p(w2), p(bias), int(S), int(L), HW,
+                                            float(loss_weight) / max(int(num_valid), 1), p(loss), p(lse), p(grad),
+                                            flags, p(gw), p(gb), p(ws), nbytes, _stream(s.device)),
+               "hs_leaf_cross_entropy_tc")
     return gw, gb
 
 

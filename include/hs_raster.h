@@ -217,6 +217,18 @@ int hs_leaf_cross_entropy(const float* sem, const int* labels, const float* weig
                           int classes, size_t pixels, float scale, float* loss, float* lse, float* grad_sem,
                           int flags, float* grad_weight, float* grad_bias, void* stream);
 
+/* The same loss with the per-pixel pass (logits, softmax statistics, loss, d loss / d sem) on the 5th-generation tensor
+ * cores: tcgen05.mma kind::tf32 with the accumulators in tensor memory (TMEM), 3xTF32 (fp32-accurate), the weights laid
+ * out once per call as UMMA operand tiles in `workspace` (device, 128-byte aligned, hs_leaf_ce_workspace_bytes(channels,
+ * classes) bytes) and streamed to shared memory with TMA bulk copies (hier_slam_b200/csrc/leaf_loss_tc.cu).  Arguments
+ * and results as hs_leaf_cross_entropy; the weight / bias gradients come from the same kernel as there. */
+size_t hs_leaf_ce_workspace_bytes(int channels, int classes);
+/* Debugging aid: device buffer of 60 int64 that receives clock64 stamps of CTA 0's first phases (NULL = off). */
+void hs_leaf_tc_debug(long long* stamps);
+int hs_leaf_cross_entropy_tc(const float* sem, const int* labels, const float* weight, const float* bias, int channels,
+                             int classes, size_t pixels, float scale, float* loss, float* lse, float* grad_sem, int flags,
+                             float* grad_weight, float* grad_bias, void* workspace, size_t workspace_bytes, void* stream);
+
 /* present[P] (bool, device) = view-space z > 0.2 (reference: rasterizer_impl.cu:54-66). */
 int hs_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
                     unsigned char* present, void* stream);
