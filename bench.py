@@ -189,6 +189,11 @@ def run_ours(a, rank, world, local):
     settings = pt.make_settings(GaussianRasterizationSettings, cfg, dev)
     raster = GaussianRasterizer_semantic(raster_settings=settings)
     params = FlatParams({k: v.to(dev) for k, v in scene_cpu.items()})
+    symm_note = None
+    if world > 1 and a.allreduce != "nccl":
+        from hier_slam_b200.mapping import enable_symmetric_allreduce
+        if enable_symmetric_allreduce(params, multicast=(a.allreduce != "p2p")) is None:
+            symm_note = getattr(params, "symm_error", None)
     up = {k: v.to(dev) for k, v in grads_cpu.items()}
     up_tuple = (up["color"], up["semantic"], up["depth"], up["median_depth"], up["final_opacity"])
     means2D = torch.zeros(P, 3, device=dev)
@@ -320,6 +325,9 @@ def run_ours(a, rank, world, local):
     ms_e2e, wall_e2e, _, _, _ = timed(step_e2e, n_e2e, 3, drain=drain_e2e)
     drain_e2e()
 
+    ar_ms = None
+    if world > 1:      # the collective alone, back to back (device time, max over ranks)
+        ar_ms = timed(lambda: allreduce_gradients(params), 20, 3)[0] / 20
     verify = None
     if world > 1 and not a.no_verify:
         # SURVEY.md section 8e criterion on the real GPUs: the all-reduced flat gradient == the sum of the N single-keyframe
@@ -395,9 +403,12 @@ def run_ours(a, rank, world, local):
         if verify is not None:
             out["verify"] = verify
         if world > 1:
-            ar_ms = ms / a.steps - sum(stage_ms.values()) if stage_ms else None
-            out["allreduce"] = {"bytes": params.grad_bytes(), "collective": allreduce_name(),
-                                "exposed_ms_upper_bound": ar_ms,
+            exposed = ms / a.steps - sum(stage_ms.values()) if stage_ms else None
+            out["allreduce"] = {"bytes": params.grad_bytes(), "collective": allreduce_name(), "symmetric_memory_error": symm_note,
+                                "ms_alone": ar_ms,
+                                "bus_bandwidth_GBps": (2 * (world - 1) / world * params.grad_bytes() / (ar_ms * 1e-3) / 1e9
+                                                       if ar_ms else None),
+                                "exposed_ms_upper_bound": exposed,
                                 "what": "one all-reduce (SUM, fp32) of the flat gradient buffer per step; exposed time <= step time "
                                         "minus the sum of this library's kernels"}
     return out, (scene_cpu, grads_cpu, cfg)
@@ -690,6 +701,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "ref-cuda"])
     ap.add_argument("--config", default="c2")
     ap.add_argument("--no-baselines", action="store_true", help="skip the cpu_baseline / ref_cuda legs")
+    ap.add_argument("--allreduce", default="symm", choices=["symm", "p2p", "nccl"],
+                    help="N > 1: this library's NVLink kernel with NVSwitch multicast (symm), with peer loads/stores (p2p), or NCCL")
     ap.add_argument("--no-verify", action="store_true",
                     help="N > 1: skip the check that the all-reduced gradient equals the sum of the N single-keyframe gradients")
     a = ap.parse_args()

@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("HS_LIB", os.path.join(HERE, "libhsraster.so"))
 EXPORTED_SYMBOLS = [
     "hs_abi_version", "hs_last_error", "hs_supports_semantic_channels", "hs_geom_state_bytes",
     "hs_image_state_bytes", "hs_binning_state_bytes", "hs_image_state_info_offset", "hs_forward_geometry", "hs_forward_render",
-    "hs_backward", "hs_mark_visible", "hs_masked_l1", "hs_hier_cross_entropy", "hs_leaf_cross_entropy", "hs_leaf_cross_entropy_tc", "hs_leaf_ce_workspace_bytes", "hs_leaf_tc_debug", "hs_l1_ssim", "hs_adam_step", "hs_transform_points", "hs_tracking_loss", "hs_pose_step", "hs_keyframe_overlap",
+    "hs_backward", "hs_mark_visible", "hs_masked_l1", "hs_hier_cross_entropy", "hs_leaf_cross_entropy", "hs_leaf_cross_entropy_tc", "hs_leaf_ce_workspace_bytes", "hs_leaf_tc_debug", "hs_allreduce_sum", "hs_l1_ssim", "hs_adam_step", "hs_transform_points", "hs_tracking_loss", "hs_pose_step", "hs_keyframe_overlap",
     "hs_compact_scratch_bytes", "hs_compact_plan", "hs_compact_gather",
     "hs_geom_state_layout", "hs_image_state_layout",
     "hs_binning_state_layout", "hs_profile_enable", "hs_profile_read", "hs_kernel_launch_count",
@@ -83,6 +83,8 @@ def load() -> ctypes.CDLL:
     lib.hs_leaf_cross_entropy_tc.restype = c_int
     lib.hs_leaf_ce_workspace_bytes.argtypes = [c_int, c_int]
     lib.hs_leaf_ce_workspace_bytes.restype = c_size_t
+    lib.hs_allreduce_sum.argtypes = [vp, vp, vp, c_int, c_int, c_size_t, ctypes.c_uint, c_int, vp]
+    lib.hs_allreduce_sum.restype = c_int
     lib.hs_leaf_tc_debug.argtypes = [vp]
     lib.hs_leaf_tc_debug.restype = None
     lib.hs_l1_ssim.argtypes = [vp, vp, c_int, c_int, c_int, POINTER(c_float), c_float, c_float, vp, vp, vp, vp]

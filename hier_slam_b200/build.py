@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "build" + ("_" + hashlib.md5(os.environ["HS_NVCC_EXTRA"].encode()).hexdigest()[:8]
                                        if os.environ.get("HS_NVCC_EXTRA") else ""))
 LIB = os.environ.get("HS_LIB", os.path.join(HERE, "libhsraster.so"))   # HS_LIB / HS_NVCC_EXTRA: tuning variants
-SOURCES = ["preprocess.cu", "binning.cu", "blend_fwd.cu", "blend_bwd.cu", "blend_bwd_mma.cu", "sh_color.cu", "loss.cu", "leaf_loss.cu", "leaf_loss_tc.cu", "ssim.cu", "optim.cu", "tracking.cu",
+SOURCES = ["preprocess.cu", "binning.cu", "blend_fwd.cu", "blend_bwd.cu", "blend_bwd_mma.cu", "sh_color.cu", "loss.cu", "leaf_loss.cu", "leaf_loss_tc.cu", "allreduce.cu", "ssim.cu", "optim.cu", "tracking.cu",
            "capi.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

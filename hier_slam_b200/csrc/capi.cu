@@ -469,6 +469,12 @@ int hs_leaf_cross_entropy(const float* sem, const int* labels, const float* weig
                                      (cudaStream_t)stream_);
 }
 
+int hs_allreduce_sum(void* multicast_ptr, void* const* peer_buffers, void* const* peer_signal_pads, int rank, int world_size,
+                     size_t count, unsigned int epoch, int blocks, void* stream_) {
+    return launch_allreduce_sum(multicast_ptr, peer_buffers, peer_signal_pads, rank, world_size, count, epoch, blocks,
+                                (cudaStream_t)stream_);
+}
+
 void hs_leaf_tc_debug(long long* stamps) { leaf_tc_set_debug(stamps); }
 size_t hs_leaf_ce_workspace_bytes(int channels, int classes) { return leaf_tc_workspace_bytes(channels, classes); }
 

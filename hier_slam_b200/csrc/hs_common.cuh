@@ -187,6 +187,8 @@ int launch_leaf_cross_entropy_tc(const float* sem, const int* labels, const floa
 int launch_leaf_weight_grad(const float* sem, const int* labels, const float* weight, const float* bias, const float* lse,
                             int S, int L, size_t HW, float scale, float* grad_weight, float* grad_bias, int single_tf32,
                             cudaStream_t stream);
+int launch_allreduce_sum(void* multicast_ptr, void* const* peer_bufs, void* const* peer_pads, int rank, int world, size_t n,
+                         unsigned epoch, int blocks, cudaStream_t stream);
 int launch_mark_visible(int P, const float* means3D, const float* view, const float* proj, bool* present,
                         cudaStream_t stream, bool debug);
 

@@ -5,7 +5,8 @@
 // 550 classes for the ScanNet tree).  leaf_loss.cu holds the mma.sync generation of this loss; this file is the
 // Blackwell-native pixel pass (logits, softmax statistics, loss, dL/dsem).  The weight gradient stays in leaf_loss.cu.
 //
-// One CTA (4 warps) owns 128 pixels = the 128 TMEM lanes; thread t <-> pixel t <-> TMEM lane t.  Per pixel tile:
+// One CTA owns 128 pixels = the 128 TMEM lanes: 8 softmax warps (two per quarter of the lanes, each working on half of
+// the columns) + 1 issuer warp.  Per pixel tile:
 //   X      the pixel rows [128 x K] (K = S + 1 "ones" channel for the bias, padded to 16) are written to TMEM with
 //          tcgen05.st as hi / lo tf32 parts and stay there for all class chunks (A operand from TMEM, "TS" form);
 //   Z_c    = X W_c^T for a chunk of 64 classes: tcgen05.mma kind::tf32, M = 128, N = 64, accumulator in TMEM, three
@@ -57,6 +58,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// one lane of a converged warp (elect.sync): the form ptxas recognises as "exactly one active thread", so that the
+// tcgen05.mma sequences below are emitted back to back instead of inside a per-instruction elect / branch waterfall
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
@@ -156,16 +168,51 @@ __device__ __forceinline__ void tmem_ld64(uint32_t addr, float (&v)[64]) {
     for (int i = 0; i < 64; i++) v[i] = __uint_as_float(r[i]);
 }
 
-// Warp roles: warps 0-3 = softmax / epilogue warps (thread t <-> pixel t <-> TMEM lane t), warp 4 = issuer (one elected
-// lane issues the TMA bulk copies and every tcgen05.mma; it never touches pixel data).  They meet only on mbarriers:
-//   bar_x      (128 arrivals)  the tile's X rows are in TMEM                      softmax -> issuer
+__device__ __forceinline__ void tmem_ld8(uint32_t addr, float (&v)[8]) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(addr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; i++) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t addr, float (&v)[32]) {     // two 16-column loads in flight, one wait
+    uint32_t r[32];
+#pragma unroll
+    for (int q = 0; q < 2; q++)
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+            : "=r"(r[16 * q + 0]), "=r"(r[16 * q + 1]), "=r"(r[16 * q + 2]), "=r"(r[16 * q + 3]), "=r"(r[16 * q + 4]),
+              "=r"(r[16 * q + 5]), "=r"(r[16 * q + 6]), "=r"(r[16 * q + 7]), "=r"(r[16 * q + 8]), "=r"(r[16 * q + 9]),
+              "=r"(r[16 * q + 10]), "=r"(r[16 * q + 11]), "=r"(r[16 * q + 12]), "=r"(r[16 * q + 13]),
+              "=r"(r[16 * q + 14]), "=r"(r[16 * q + 15])
+            : "r"(addr + 16 * q));
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void pair_sync(int quarter) {      // the two warps that share a quarter of the TMEM lanes
+    asm volatile("bar.sync %0, 64;\n" ::"r"(1 + quarter) : "memory");
+}
+
+constexpr int SOFTMAX_THREADS = 256;
+constexpr int HALF = NC / 2;
+
+// Warp roles: warps 0-7 = softmax / epilogue warps, warps 8 / 9 = issuers (one elected lane each issues the TMA bulk
+// copies and tcgen05.mma of the logits / of dX; they never touch pixel data).  A warp can only address the TMEM lanes 32 (warp % 4) .. + 31, so the
+// pixel rows of a tile are shared by TWO warps: thread (h, quarter, lane), h = warp / 4, owns pixel 32 quarter + lane
+// together with its partner in the other half, and works on half h of everything that has a column index -- the channels
+// of X and dX, the 32 classes [32 h, 32 h + 32) of every chunk.  The two exchange their chunk maxima / row sums through
+// shared memory behind a 64-thread named barrier.  Roles meet only on mbarriers:
+//   bar_x      (256 arrivals)  the tile's X rows are in TMEM                      softmax -> issuer
 //   bar_z[2]   (commit)        logits of a chunk are complete in Z[slot]          issuer  -> softmax (and issuer: B1 slot free)
-//   bar_zf[2]  (128 arrivals)  Z[slot] has been read into registers               softmax -> issuer
-//   bar_p      (128 arrivals)  P of a chunk is in TMEM                            softmax -> issuer
+//   bar_zf[2]  (256 arrivals)  Z[slot] has been read into registers               softmax -> issuer
+//   bar_p      (256 arrivals)  P of a chunk is in TMEM                            softmax -> issuer
 //   bar_d      (commit)        dX MMAs of a chunk are complete                    issuer  -> softmax (and issuer: B2 slot free)
-//   bar_t      (128 arrivals)  the tile's dX has been read out of TMEM            softmax -> issuer
+//   bar_t      (256 arrivals)  the tile's dX has been read out of TMEM            softmax -> issuer
 //   bar_b1[2], bar_b2[2]       TMA full barriers (expect_tx)                      TMA     -> issuer
-__global__ void __launch_bounds__(TILE + 32, 1) leaf_ce_pixel_tc_kernel(
+__global__ void __launch_bounds__(SOFTMAX_THREADS + 64, 1) leaf_ce_pixel_tc_kernel(
     const float* __restrict__ sem, const int* __restrict__ labels, const float* __restrict__ weight,
     const float* __restrict__ bias, const float* __restrict__ ws, int S, int L, int K, int chunks, size_t HW, float scale,
     float* __restrict__ loss, float* __restrict__ lse_out, float* __restrict__ grad_sem, int accumulate,
@@ -175,7 +222,8 @@ __global__ void __launch_bounds__(TILE + 32, 1) leaf_ce_pixel_tc_kernel(
     float* sB2 = sB1 + (size_t)4 * NC * K;                          // [2][2][K * NC]
     __shared__ __align__(8) uint64_t bar_b1[2], bar_b2[2], bar_z[2], bar_zf[2], bar_d, bar_p, bar_x, bar_t;
     __shared__ uint32_t s_tmem;
-    __shared__ float s_loss[4];
+    __shared__ float s_loss[8];
+    __shared__ float s_xchg[2][2][TILE];      // [parity][half][pixel]: chunk maxima / row sums / label logits of the partner
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     int dbg_n = 0;
 #define HS_STAMP() do { if (dbg != nullptr && blockIdx.x == 0 && tid == 0 && dbg_n < 60) dbg[dbg_n++] = clock64(); } while (0)
@@ -186,12 +234,12 @@ __global__ void __launch_bounds__(TILE + 32, 1) leaf_ce_pixel_tc_kernel(
             mbar_init(&bar_b1[i], 1);
             mbar_init(&bar_b2[i], 1);
             mbar_init(&bar_z[i], 1);
-            mbar_init(&bar_zf[i], TILE);
+            mbar_init(&bar_zf[i], SOFTMAX_THREADS);
         }
         mbar_init(&bar_d, 1);
-        mbar_init(&bar_p, TILE);
-        mbar_init(&bar_x, TILE);
-        mbar_init(&bar_t, TILE);
+        mbar_init(&bar_p, SOFTMAX_THREADS);
+        mbar_init(&bar_x, SOFTMAX_THREADS);
+        mbar_init(&bar_t, SOFTMAX_THREADS);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     if (warp == 0) {
@@ -212,24 +260,20 @@ __global__ void __launch_bounds__(TILE + 32, 1) leaf_ce_pixel_tc_kernel(
     tm.dx = tm.p_lo + NC;
     const size_t n_tiles = (HW + TILE - 1) / TILE;
 
-    if (warp == 4) {
-        // ================================ issuer warp ================================================================
-        if (lane == 0) {
-            const uint32_t idesc_z = idesc_tf32(NC), idesc_dx = idesc_tf32(K);
-            const uint32_t b1_sbo = (uint32_t)(K >> 2) * 128, b2_sbo = (uint32_t)(NC >> 2) * 128;
+    if (warp == 8) {
+        // ================================ logits issuer: B1 copies + Z MMAs ===========================================
+        // (a single thread issues a tcgen05.mma in ~100 cycles -- uniform-datapath address arithmetic, elect, the
+        // instruction itself -- while an M = 128, N = 64, K = 8 MMA is 32 cycles of tensor work, so the two MMA streams
+        // of a chunk are issued by two different warps)
+        if (elect_one()) {
+            const uint32_t idesc_z = idesc_tf32(NC);
+            const uint32_t b1_sbo = (uint32_t)(K >> 2) * 128;
             const int ksteps_z = K / 8;
-            uint32_t g = 0;                       // chunks issued so far by this CTA: ring slot = g & 1, phase = (g >> 1) & 1
-            uint32_t n_p = 0, n_d = 0, n_t = 0, n_x = 0;      // completed phases waited so far on bar_p / bar_d / bar_t / bar_x
+            uint32_t g = 0, n_x = 0;              // chunks issued so far: ring slot = g & 1, phase = (g >> 1) & 1
             auto load_b1 = [&](uint32_t gg, int c) {
                 const int slot = gg & 1;
                 mbar_expect_tx(&bar_b1[slot], tile_bytes);
                 tma_bulk_g2s(sB1 + (size_t)slot * 2 * NC * K, ws + (size_t)c * chunk_floats(K), tile_bytes, &bar_b1[slot]);
-            };
-            auto load_b2 = [&](uint32_t gg, int c) {
-                const int slot = gg & 1;
-                mbar_expect_tx(&bar_b2[slot], tile_bytes);
-                tma_bulk_g2s(sB2 + (size_t)slot * 2 * NC * K, ws + (size_t)c * chunk_floats(K) + (size_t)2 * NC * K,
-                             tile_bytes, &bar_b2[slot]);
             };
             auto issue_z = [&](uint32_t gg) {     // logits of chunk gg into Z[gg & 1]:  X_hi W_hi + X_lo W_hi + X_hi W_lo
                 const int slot = gg & 1;
@@ -245,25 +289,11 @@ __global__ void __launch_bounds__(TILE + 32, 1) leaf_ce_pixel_tc_kernel(
                 for (int k = 0; k < ksteps_z; k++) mma_ts(dz, tm.x_hi + 8 * k, d_lo + (uint64_t)(16 * k), idesc_z, true);
                 tc_commit(&bar_z[slot]);
             };
-            auto issue_dx = [&](uint32_t gg, bool first) {    // dX (+)= P_hi W_hi + P_lo W_hi + P_hi W_lo
-                const int slot = gg & 1;
-                const uint32_t b_hi = smem_u32(sB2 + (size_t)slot * 2 * NC * K);
-                const uint64_t d_hi = kmajor_desc(b_hi, 128, b2_sbo);
-                const uint64_t d_lo = kmajor_desc(b_hi + (uint32_t)(NC * K * sizeof(float)), 128, b2_sbo);
-#pragma unroll
-                for (int k = 0; k < NC / 8; k++) mma_ts(tm.dx, tm.p_hi + 8 * k, d_hi + (uint64_t)(16 * k), idesc_dx, !(first && k == 0));
-#pragma unroll
-                for (int k = 0; k < NC / 8; k++) mma_ts(tm.dx, tm.p_lo + 8 * k, d_hi + (uint64_t)(16 * k), idesc_dx, true);
-#pragma unroll
-                for (int k = 0; k < NC / 8; k++) mma_ts(tm.dx, tm.p_hi + 8 * k, d_lo + (uint64_t)(16 * k), idesc_dx, true);
-                tc_commit(&bar_d);
-            };
+            if (blockIdx.x < n_tiles) {           // the first tile's operand tiles; later tiles get theirs one tile ahead
+                load_b1(0, 0);
+                if (chunks > 1) load_b1(1, 1);
+            }
             for (size_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                // every MMA of the previous tile has completed (all bar_z / bar_d phases were waited for below), so both
-                // rings are free
-                load_b1(g, 0);
-                load_b2(g, 0);
-                if (chunks > 1) load_b1(g + 1, 1);
                 mbar_wait(&bar_x, n_x & 1);       // X rows of this tile are in TMEM
                 n_x++;
                 tc_fence_after();
@@ -277,11 +307,44 @@ __global__ void __launch_bounds__(TILE + 32, 1) leaf_ce_pixel_tc_kernel(
                         tc_fence_after();
                         issue_z(g + 1);
                     }
-                    // B1 slot of chunk g is free once its MMAs are complete
-                    mbar_wait(&bar_z[g & 1], (g >> 1) & 1);
+                    mbar_wait(&bar_z[g & 1], (g >> 1) & 1);    // B1 slot of chunk g is free once its MMAs are complete
                     if (c + 2 < chunks) load_b1(g + 2, c + 2);
-                    // B2 slot of the previous chunk is free once ITS dX MMAs are complete
-                    if (c >= 1) {
+                }
+                if (tile + gridDim.x < n_tiles) {  // every logits MMA of this tile is complete: the ring is free
+                    load_b1(g, 0);
+                    if (chunks > 1) load_b1(g + 1, 1);
+                }
+            }
+        }
+    } else if (warp == 9) {
+        // ================================ dX issuer: B2 copies + dX MMAs ===============================================
+        if (elect_one()) {
+            const uint32_t idesc_dx = idesc_tf32(K);
+            const uint32_t b2_sbo = (uint32_t)(NC >> 2) * 128;
+            uint32_t g = 0, n_p = 0, n_d = 0, n_t = 0;
+            auto load_b2 = [&](uint32_t gg, int c) {
+                const int slot = gg & 1;
+                mbar_expect_tx(&bar_b2[slot], tile_bytes);
+                tma_bulk_g2s(sB2 + (size_t)slot * 2 * NC * K, ws + (size_t)c * chunk_floats(K) + (size_t)2 * NC * K,
+                             tile_bytes, &bar_b2[slot]);
+            };
+            auto issue_dx = [&](uint32_t gg, bool first) {    // dX (+)= P_hi W_hi + P_lo W_hi + P_hi W_lo
+                const int slot = gg & 1;
+                const uint32_t b_hi = smem_u32(sB2 + (size_t)slot * 2 * NC * K);
+                const uint64_t d_hi = kmajor_desc(b_hi, 128, b2_sbo);
+                const uint64_t d_lo = kmajor_desc(b_hi + (uint32_t)(NC * K * sizeof(float)), 128, b2_sbo);
+#pragma unroll
+                for (int k = 0; k < NC / 8; k++) mma_ts(tm.dx, tm.p_hi + 8 * k, d_hi + (uint64_t)(16 * k), idesc_dx, !(first && k == 0));
+#pragma unroll
+                for (int k = 0; k < NC / 8; k++) mma_ts(tm.dx, tm.p_lo + 8 * k, d_hi + (uint64_t)(16 * k), idesc_dx, true);
+#pragma unroll
+                for (int k = 0; k < NC / 8; k++) mma_ts(tm.dx, tm.p_hi + 8 * k, d_lo + (uint64_t)(16 * k), idesc_dx, true);
+                tc_commit(&bar_d);
+            };
+            if (blockIdx.x < n_tiles) load_b2(0, 0);
+            for (size_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                for (int c = 0; c < chunks; c++, g++) {
+                    if (c >= 1) {                 // B2 slot of the previous chunk is free once ITS dX MMAs are complete
                         mbar_wait(&bar_d, n_d & 1);
                         n_d++;
                     }
@@ -296,42 +359,46 @@ __global__ void __launch_bounds__(TILE + 32, 1) leaf_ce_pixel_tc_kernel(
                     tc_fence_after();
                     issue_dx(g, c == 0);
                 }
-                mbar_wait(&bar_d, n_d & 1);                   // last chunk's dX (frees its B2 slot for the next tile)
+                mbar_wait(&bar_d, n_d & 1);                   // last chunk's dX: both B2 slots are free
                 n_d++;
+                if (tile + gridDim.x < n_tiles) load_b2(g, 0);
             }
         }
     } else {
         // ================================ softmax / epilogue warps ===================================================
-        const uint32_t lane_off = (uint32_t)(warp * 32) << 16;         // a warp addresses its own 32 TMEM lanes
+        const int h = warp >> 2, quarter = warp & 3;
+        const int pix = quarter * 32 + lane;                            // pixel of the tile = TMEM lane
+        const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;       // a warp addresses the lanes 32 (warp % 4) ..
+        const int KH = K >> 1;                                          // channels of this half: [h KH, h KH + KH), KH % 8 == 0
+        const int ch0 = h * KH;
         float loss_acc = 0.f;
-        uint32_t g = 0, n_d = 0;
+        uint32_t g = 0, n_d = 0, xp = 0;
         for (size_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const size_t px = tile * TILE + tid;
+            const size_t px = tile * TILE + pix;
             const bool in = px < HW;
             HS_STAMP();   // tile start
-            // ---- X rows -> TMEM (hi / lo).  For a fixed channel the 32 lanes of a warp read 32 consecutive pixels; all
-            // loads of a 40-channel half are issued before the first TMEM store (one memory latency per half).
-#pragma unroll 1
-            for (int c0 = 0; c0 < K; c0 += 40) {
-                float v[40];
+            // ---- this half's channels of the pixel row -> TMEM (hi / lo).  For a fixed channel the 32 lanes of a warp
+            // read 32 consecutive pixels; all loads are issued before the first TMEM store (one memory latency).
+            {
+                float v[KMAX / 2];
 #pragma unroll
-                for (int q = 0; q < 40; q++) {
-                    const int s = c0 + q;
+                for (int q = 0; q < KMAX / 2; q++) {
+                    const int s = ch0 + q;
                     v[q] = 0.f;
-                    if (in && s < S) v[q] = __ldg(sem + (size_t)s * HW + px);
-                    else if (in && s == S) v[q] = 1.f;
+                    if (q < KH && in && s < S) v[q] = __ldg(sem + (size_t)s * HW + px);
+                    else if (q < KH && in && s == S) v[q] = 1.f;
                 }
 #pragma unroll
-                for (int q8 = 0; q8 < 40; q8 += 8) {
-                    if (c0 + q8 < K) {
+                for (int q8 = 0; q8 < KMAX / 2; q8 += 8) {
+                    if (q8 < KH) {
                         float hi[8], lo[8];
 #pragma unroll
                         for (int q = 0; q < 8; q++) {
                             hi[q] = tf32_hi(v[q8 + q]);
                             lo[q] = v[q8 + q] - hi[q];
                         }
-                        tmem_st8(tm.x_hi + lane_off + c0 + q8, hi);
-                        tmem_st8(tm.x_lo + lane_off + c0 + q8, lo);
+                        tmem_st8(tm.x_hi + lane_off + ch0 + q8, hi);
+                        tmem_st8(tm.x_lo + lane_off + ch0 + q8, lo);
                     }
                 }
             }
@@ -341,38 +408,44 @@ __global__ void __launch_bounds__(TILE + 32, 1) leaf_ce_pixel_tc_kernel(
             HS_STAMP();   // X stored
             const int lab_raw = in ? __ldg(labels + px) : -1;
             const bool use = lab_raw >= 0 && lab_raw < L;
-            const int y = use ? lab_raw : -1;
-            float m_ref = -1.0e30f, l_sum = 0.f, zy = 0.f;
+            const int y = use ? lab_raw : 0;
+            float m_ref = -1.0e30f, l_sum = 0.f;
             for (int c = 0; c < chunks; c++, g++) {
                 const int slot = g & 1;
                 mbar_wait(&bar_z[slot], (g >> 1) & 1);        // logits of chunk c are complete
                 tc_fence_after();
                 HS_STAMP();   // Z ready
-                float z[NC];
-                tmem_ld64(tm.z[slot] + lane_off, z);
+                float z[HALF];
+                tmem_ld32(tm.z[slot] + lane_off + h * HALF, z);
                 tc_fence_before();
                 mbar_arrive(&bar_zf[slot]);                   // Z[slot] may be overwritten by the logits of chunk c + 2
-                const int cls0 = c * NC;
-                float cmax = -3.0e38f;
+                const int cls0 = c * NC + h * HALF;
+                float cm[4] = {-3.0e38f, -3.0e38f, -3.0e38f, -3.0e38f};
+                if (cls0 + HALF <= L) {                       // warp-uniform: no class mask needed
 #pragma unroll
-                for (int i = 0; i < NC; i++) {
-                    const int cls = cls0 + i;
-                    if (cls < L) cmax = fmaxf(cmax, z[i]);
-                    if (cls == y) zy = z[i];
+                    for (int i = 0; i < HALF; i++) cm[i & 3] = fmaxf(cm[i & 3], z[i]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < HALF; i++) {
+                        if (cls0 + i >= L) z[i] = -3.0e38f;   // exp() of it is 0 below
+                        cm[i & 3] = fmaxf(cm[i & 3], z[i]);
+                    }
                 }
+                const float my_max = fmaxf(fmaxf(cm[0], cm[1]), fmaxf(cm[2], cm[3]));
+                s_xchg[xp][h][pix] = my_max;
+                pair_sync(quarter);
+                const float cmax = fmaxf(my_max, s_xchg[xp][h ^ 1][pix]);
+                xp ^= 1;
                 // lazily updated reference maximum: rescale only when the maximum grows by more than 8 (exp(8) = 2981:
-                // far from fp32 overflow; the result stays exact because every term uses the same reference)
+                // far from fp32 overflow; the result stays exact because every term uses the same reference).  Both warps
+                // of a pixel take the same decision from the same numbers.
                 float rescale = 1.f;
                 if (cmax > m_ref + 8.f) {
                     rescale = __expf(m_ref - cmax);           // 0 for the first chunk (m_ref = -1e30)
                     m_ref = cmax;
                 }
-                float ph[NC];
 #pragma unroll
-                for (int i = 0; i < NC; i++) {
-                    const float p = (cls0 + i < L) ? __expf(z[i] - m_ref) : 0.f;
-                    ph[i] = p;
-                }
+                for (int i = 0; i < HALF; i++) z[i] = __expf(z[i] - m_ref);
                 HS_STAMP();   // exponentials done
                 // the previous chunk's dX MMAs read P (and wrote dX): complete before P is overwritten / dX rescaled
                 if (c >= 1) {
@@ -382,72 +455,80 @@ __global__ void __launch_bounds__(TILE + 32, 1) leaf_ce_pixel_tc_kernel(
                 }
                 l_sum *= rescale;
                 // rare after the first chunk.  tcgen05.ld / st are warp-collective (.sync.aligned): the decision is made
-                // per warp (a warp owns its 32 lanes), lanes whose reference did not move multiply by 1
+                // per warp, lanes whose reference did not move multiply by 1; each half rescales its own dX columns
                 if (__any_sync(0xffffffffu, c >= 1 && rescale != 1.f)) {
 #pragma unroll 1
-                    for (int q = 0; q < K; q += 16) {
-                        float d[16];
-                        tmem_ld16(tm.dx + lane_off + q, d);
-                        float a8[8], b8[8];
+                    for (int q = 0; q < KH; q += 8) {
+                        float d[8];
+                        tmem_ld8(tm.dx + lane_off + ch0 + q, d);
 #pragma unroll
-                        for (int i = 0; i < 8; i++) {
-                            a8[i] = d[i] * rescale;
-                            b8[i] = d[8 + i] * rescale;
-                        }
-                        tmem_st8(tm.dx + lane_off + q, a8);
-                        tmem_st8(tm.dx + lane_off + q + 8, b8);
+                        for (int i = 0; i < 8; i++) d[i] *= rescale;
+                        tmem_st8(tm.dx + lane_off + ch0 + q, d);
                     }
                 }
+                float ls[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                for (int q = 0; q < NC; q += 8) {
+                for (int q = 0; q < HALF; q += 8) {
                     float h8[8], l8[8];
 #pragma unroll
                     for (int i = 0; i < 8; i++) {
-                        l_sum += ph[q + i];
-                        h8[i] = tf32_hi(ph[q + i]);
-                        l8[i] = ph[q + i] - h8[i];
+                        ls[i & 3] += z[q + i];
+                        h8[i] = tf32_hi(z[q + i]);
+                        l8[i] = z[q + i] - h8[i];
                     }
-                    tmem_st8(tm.p_hi + lane_off + q, h8);
-                    tmem_st8(tm.p_lo + lane_off + q, l8);
+                    tmem_st8(tm.p_hi + lane_off + h * HALF + q, h8);
+                    tmem_st8(tm.p_lo + lane_off + h * HALF + q, l8);
                 }
+                l_sum += (ls[0] + ls[1]) + (ls[2] + ls[3]);
                 tmem_st_wait();
                 tc_fence_before();
                 mbar_arrive(&bar_p);
                 HS_STAMP();   // P stored
             }
-            // ---- tile epilogue: dX complete
+            // ---- tile epilogue: row sums of both halves, then dX
+            s_xchg[xp][h][pix] = l_sum;
+            pair_sync(quarter);
+            const float l_tot = l_sum + s_xchg[xp][h ^ 1][pix];
+            xp ^= 1;
             mbar_wait(&bar_d, n_d & 1);
             n_d++;
             tc_fence_after();
             HS_STAMP();   // last dX done
-            const float lse = m_ref + __logf(l_sum);
             const float sc = use ? scale : 0.f;
-            const float inv = sc / l_sum;
-            if (in) {
-                lse_out[px] = lse;
-                loss_acc += sc * (lse - zy);
-            }
-            const float* wy = weight + (size_t)(use ? y : 0) * S;
+            const float inv = sc / l_tot;
+            const float* wy = weight + (size_t)y * S;
+            float zy_part = 0.f;                              // this half's share of the label's logit  <x, W[y]> (+ bias)
 #pragma unroll 1
-            for (int q = 0; q < K; q += 16) {
-                float d[16], wv[16], old[16];
-                tmem_ld16(tm.dx + lane_off + q, d);
-                if (q + 16 >= K) {                            // last read of this tile's dX
+            for (int q = 0; q < KH; q += 8) {
+                float d[8], wv[8], xv[8], old[8];
+                tmem_ld8(tm.dx + lane_off + ch0 + q, d);
+                if (q + 8 >= KH) {                            // last read of this tile's dX by this thread
                     tc_fence_before();
                     mbar_arrive(&bar_t);
                 }
 #pragma unroll
-                for (int i = 0; i < 16; i++) {
-                    const int s = q + i;
-                    wv[i] = (s < S) ? __ldg(wy + s) : 0.f;
+                for (int i = 0; i < 8; i++) {
+                    const int s = ch0 + q + i;
+                    wv[i] = (s < S) ? __ldg(wy + s) : ((s == S && bias != nullptr) ? __ldg(bias + y) : 0.f);
+                    xv[i] = (s < S && in) ? __ldg(sem + (size_t)s * HW + px) : (s == S ? 1.f : 0.f);
                     old[i] = (accumulate && s < S && in) ? grad_sem[(size_t)s * HW + px] : 0.f;
                 }
 #pragma unroll
-                for (int i = 0; i < 16; i++) {
-                    const int s = q + i;
+                for (int i = 0; i < 8; i++) {
+                    const int s = ch0 + q + i;
+                    zy_part = fmaf(xv[i], wv[i], zy_part);
                     if (s < S && in) grad_sem[(size_t)s * HW + px] = old[i] + (d[i] * inv - sc * wv[i]);
                 }
             }
+            s_xchg[xp][h][pix] = zy_part;
+            pair_sync(quarter);
+            if (h == 0 && in) {
+                const float zy = zy_part + s_xchg[xp][1][pix];
+                const float lse = m_ref + __logf(l_tot);
+                lse_out[px] = lse;
+                loss_acc += sc * (lse - zy);
+            }
+            xp ^= 1;
             HS_STAMP();   // outputs written
         }
 #pragma unroll
@@ -504,7 +585,7 @@ int launch_leaf_cross_entropy_tc(const float* sem, const int* labels, const floa
     }
     const size_t n_tiles = (HW + TILE - 1) / TILE;
     const int grid = (int)(n_tiles < (size_t)sms ? n_tiles : (size_t)sms);
-    k<<<grid, TILE + 32, smem, stream>>>(sem, labels, weight, bias, workspace, S, L, K, chunks, HW, scale, loss, lse, grad_sem,
+    k<<<grid, SOFTMAX_THREADS + 64, smem, stream>>>(sem, labels, weight, bias, workspace, S, L, K, chunks, HW, scale, loss, lse, grad_sem,
                                     accumulate, g_leaf_tc_dbg);
     HS_LAUNCH_OK(stream, false);
     return 0;

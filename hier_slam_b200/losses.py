@@ -94,9 +94,14 @@ def hierarchical_cross_entropy(sem: torch.Tensor, labels: torch.Tensor, level_si
 # HS_LEAF_TF32=1: one TF32 product per contraction in the leaf loss (torch's default convolution precision) instead of the
 # fp32-accurate 3xTF32 split
 LEAF_TF32 = os.environ.get("HS_LEAF_TF32", "0") == "1"
-# HS_LEAF_LEGACY=1: the mma.sync generation of the per-pixel pass (csrc/leaf_loss.cu) instead of the tcgen05 / TMEM / TMA
-# kernel (csrc/leaf_loss_tc.cu) -- kept for A/B measurements; both are fp32-accurate 3xTF32
-LEAF_LEGACY = os.environ.get("HS_LEAF_LEGACY", "0") == "1"
+# Per-pixel pass of the leaf loss: two kernels, both fp32-accurate 3xTF32, chosen by the class count.
+#   csrc/leaf_loss_tc.cu  tcgen05 / TMEM / TMA: classes stream through tensor memory in chunks of 64 -- any class count;
+#                         74 -> 550 classes at 640x480: 0.37 ms vs 1.94 ms (64 % of the measured TF32 peak, 3 products counted)
+#   csrc/leaf_loss.cu     mma.sync one-pass: all logits of a 16-pixel row tile stay in a warp's registers -- only up to 112
+#                         classes, where it is the faster one (26 -> 102 at 1200x680: 0.26 ms vs 0.30 ms)
+# LEAF_KERNEL / HS_LEAF_KERNEL = "auto" | "tcgen05" | "mma_sync" forces one of them (A/B measurements, tests).
+LEAF_KERNEL = os.environ.get("HS_LEAF_KERNEL", "auto")
+LEAF_TC_MIN_CLASSES = 113
 
 
 def _stream(dev):
@@ -132,7 +137,8 @@ def _run_leaf(lib, s, lab, w2, bias, loss_weight, num_valid, loss, grad, accumul
     gb = torch.zeros(L, dtype=torch.float32, device=s.device) if (want_wgrad and bias is not None) else None
     p = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
     flags = (1 if accumulate else 0) | (2 if LEAF_TF32 else 0)
-    if LEAF_LEGACY:
+    use_tc = LEAF_KERNEL == "tcgen05" or (LEAF_KERNEL == "auto" and L >= LEAF_TC_MIN_CLASSES)
+    if not use_tc:
         _lib.check(lib.hs_leaf_cross_entropy(p(s), p(lab), p(w2), p(bias), int(S), int(L), HW,
                                              float(loss_weight) / max(int(num_valid), 1), p(loss), p(lse), p(grad),
                                              flags, p(gw), p(gb), _stream(s.device)), "hs_leaf_cross_entropy")

@@ -97,6 +97,22 @@ class FlatParams:
     def zero_grad(self) -> None:
         self.flat_grad.zero_()
 
+    @torch.no_grad()
+    def use_grad_buffer(self, buf: torch.Tensor) -> None:
+        """Moves the flat gradient into `buf` (same size / dtype / device; e.g. a symmetric-memory allocation that the
+        NVLink all-reduce kernel can address on every rank) and re-points every leaf's .grad and gradient sink at it."""
+        if buf.shape != self.flat_grad.shape or buf.dtype != torch.float32 or buf.device != self.flat_grad.device:
+            raise RuntimeError("use_grad_buffer: need a float32 buffer of the flat gradient's size on its device")
+        buf.copy_(self.flat_grad)
+        self.flat_grad = buf
+        for k in self.names:
+            leaf = self.leaves[k]
+            o, n = self.offsets[k], leaf.numel()
+            leaf.grad = buf[o:o + n].view(self.shapes[k])
+            if self.direct_grads and leaf.is_cuda and n > 0:
+                from . import _C
+                _C.register_grad_sink(leaf, leaf.grad)
+
     def grad_bytes(self) -> int:
         return self.flat_grad.numel() * 4
 
@@ -106,10 +122,80 @@ def keyframes_of_rank(num_keyframes: int, rank: int, world_size: int) -> List[in
     return list(range(rank, num_keyframes, world_size))
 
 
+ALLREDUCE_IMPL = "nccl all_reduce (torch.distributed)"    # what allreduce_gradients used last (bench.py reports it)
+
+
+class SymmetricAllReduce:
+    """The flat gradient buffer in NVLink symmetric memory + the peer tables of `hs_allreduce_sum`
+    (hier_slam_b200/csrc/allreduce.cu: one kernel per rank; with NVSwitch multicast the reduction and the broadcast happen
+    inside the switch through multimem.ld_reduce / multimem.st).  torch.distributed._symmetric_memory is used for the
+    allocation, the rendezvous and the pointer tables only -- plumbing; the collective itself is this library's kernel."""
+
+    def __init__(self, params: FlatParams, group=None, blocks: int = 64, multicast: bool = True):
+        import ctypes
+        import torch.distributed._symmetric_memory as symm
+        group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        dev = params.flat_grad.device
+        n = params.flat_grad.numel()
+        name = group.group_name
+        try:
+            symm.enable_symm_mem_for_group(name)            # needed by older releases; a no-op / deprecated later
+        except Exception:
+            pass
+        self.buf = symm.empty(n, dtype=torch.float32, device=dev)
+        self.hdl = symm.rendezvous(self.buf, name)
+        self.pad = symm.empty(max(blocks * self.world, 1024), dtype=torch.int32, device=dev)
+        self.pad.zero_()
+        self.pad_hdl = symm.rendezvous(self.pad, name)
+        torch.cuda.synchronize(dev)
+        dist.barrier(group)                                  # every pad is zero before anybody signals into it
+        self.blocks, self.epoch = blocks, 1
+        self.multicast_ptr = int(self.hdl.multicast_ptr) if (multicast and self.hdl.has_multicast_support) else 0
+        vp = ctypes.c_void_p
+        self.peer_bufs = (vp * self.world)(*[vp(int(p)) for p in self.hdl.buffer_ptrs])
+        self.peer_pads = (vp * self.world)(*[vp(int(p)) for p in self.pad_hdl.buffer_ptrs])
+        params.use_grad_buffer(self.buf)
+        self.count = n
+
+    def __call__(self) -> None:
+        import ctypes
+        from . import _lib
+        dev = self.buf.device
+        _lib.check(_lib.load().hs_allreduce_sum(ctypes.c_void_p(self.multicast_ptr) if self.multicast_ptr else None,
+                                                self.peer_bufs, self.peer_pads, self.rank, self.world, self.count, self.epoch,
+                                                self.blocks, ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)),
+                   "hs_allreduce_sum")
+        self.epoch += 2
+
+    @property
+    def name(self) -> str:
+        return ("hs_allreduce_sum: one kernel per rank over NVLink symmetric memory, " +
+                ("NVSwitch multicast (multimem.ld_reduce + multimem.st)" if self.multicast_ptr else "peer loads / stores (two-shot)"))
+
+
+def enable_symmetric_allreduce(params: FlatParams, group=None, blocks: int = 64, multicast: bool = True):
+    """Switches `allreduce_gradients(params)` to this library's NVLink kernel.  Returns the SymmetricAllReduce object, or
+    None (with the reason in `.symm_error`) when symmetric memory cannot be set up -- NCCL's all_reduce is used then."""
+    try:
+        params._symm = SymmetricAllReduce(params, group, blocks, multicast)
+    except Exception as ex:          # no NVLink peer access / no fabric support: keep the NCCL collective
+        params._symm = None
+        params.symm_error = repr(ex)
+    return params._symm
+
+
 def allreduce_gradients(params: FlatParams, group=None) -> None:
     """ONE collective per mapping iteration on the flat gradient buffer (SUM, fp32)."""
+    global ALLREDUCE_IMPL
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        dist.all_reduce(params.flat_grad, op=dist.ReduceOp.SUM, group=group)
+        symm = getattr(params, "_symm", None)
+        if symm is not None:
+            symm()
+            ALLREDUCE_IMPL = symm.name
+        else:
+            dist.all_reduce(params.flat_grad, op=dist.ReduceOp.SUM, group=group)
+            ALLREDUCE_IMPL = "nccl all_reduce (torch.distributed)"
 
 
 def capacity_for(loss_fns, params: FlatParams, slack: float = 1.3):

@@ -229,6 +229,17 @@ int hs_leaf_cross_entropy_tc(const float* sem, const int* labels, const float* w
                              int classes, size_t pixels, float scale, float* loss, float* lse, float* grad_sem, int flags,
                              float* grad_weight, float* grad_bias, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Keyframe-parallel mapping (the reference has no multi-GPU mode): in-place SUM all-reduce of `count`
+ * floats (a multiple of 4) that live at the SAME offset of a symmetric-memory allocation on every rank, as one kernel per
+ * rank over NVLink peer memory (hier_slam_b200/csrc/allreduce.cu).  peer_buffers[r] / peer_signal_pads[r] (HOST arrays of
+ * world_size device pointers): rank r's buffer and signal pad as mapped into THIS process; multicast_ptr: the NVSwitch
+ * multicast mapping of the buffer (multimem.ld_reduce / multimem.st do the reduction and the broadcast in the switch) or
+ * NULL (peer loads / stores instead).  The signal pad needs 2 * blocks * world_size 32-bit words, zeroed once; `epoch`
+ * must grow by 2 from call to call, starting at 1, identically on every rank.  All ranks must call it in the same order.
+ * Waits are bounded (4 s): a missing peer raises a CUDA error instead of hanging. */
+int hs_allreduce_sum(void* multicast_ptr, void* const* peer_buffers, void* const* peer_signal_pads, int rank, int world_size,
+                     size_t count, unsigned int epoch, int blocks, void* stream);
+
 /* present[P] (bool, device) = view-space z > 0.2 (reference: rasterizer_impl.cu:54-66). */
 int hs_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
                     unsigned char* present, void* stream);

@@ -533,12 +533,17 @@ def float32_convolutions():
     torch.backends.cudnn.allow_tf32 = tf32
 
 
+@pytest.mark.parametrize("kernel", ["tcgen05", "mma_sync"])
 @pytest.mark.parametrize("S,L,H,W,use_bias", [(26, 102, 61, 83, True), (16, 41, 37, 45, True), (26, 102, 16, 16, False),
-                                              (74, 550, 33, 47, True), (7, 5, 20, 13, True), (31, 130, 29, 31, True)])
-def test_leaf_cross_entropy_matches_torch(S, L, H, W, use_bias, float32_convolutions):
+                                              (74, 550, 33, 47, True), (7, 5, 20, 13, True), (31, 130, 29, 31, True),
+                                              (79, 64, 40, 40, True), (74, 550, 130, 257, True)])
+def test_leaf_cross_entropy_matches_torch(S, L, H, W, use_bias, kernel, float32_convolutions, monkeypatch):
     """hier_slam_b200.losses.leaf_cross_entropy == Conv2d(S, L, 1) + CrossEntropyLoss in torch (float32): value and the
-    gradients w.r.t. the semantic map, the convolution weight and its bias; ragged image sizes, ignored labels."""
+    gradients w.r.t. the semantic map, the convolution weight and its bias; ragged image sizes, ignored labels.  Both
+    per-pixel kernels: the tcgen05 / TMEM / TMA one (csrc/leaf_loss_tc.cu) and the mma.sync one (csrc/leaf_loss.cu)."""
+    from hier_slam_b200 import losses
     from hier_slam_b200.losses import leaf_cross_entropy
+    monkeypatch.setattr(losses, "LEAF_KERNEL", kernel)
     g = torch.Generator().manual_seed(47 + S)
     sem = (2 * torch.randn(S, H, W, generator=g)).cuda().requires_grad_(True)
     weight = (0.5 * torch.randn(L, S, 1, 1, generator=g)).cuda().requires_grad_(True)

@@ -23,11 +23,11 @@ for (S, L, hh, ww) in ((74, 550, 480, 640), (26, 102, 680, 1200), (16, 41, 480, 
     loss = torch.zeros((), device="cuda"); grad = torch.empty_like(sem)
     row = dict(shape=[S, hh, ww], classes=L)
     for legacy in (False, True):
-        losses.LEAF_LEGACY = legacy
+        losses.LEAF_KERNEL = "mma_sync" if legacy else "tcgen05"
         for wg in (False, True):
             fn = lambda: losses._run_leaf(lib, sem, lab, w, b, 1.0, hh * ww, loss, grad, False, wg)
             row[("mma_sync" if legacy else "tcgen05") + ("_with_wgrad_ms" if wg else "_pixel_ms")] = round(t(fn), 4)
-    losses.LEAF_LEGACY = False
+    losses.LEAF_KERNEL = "auto"
     K = (S + 1 + 15) // 16 * 16
     chunks = (L + 63) // 64
     flops = 2.0 * hh * ww * K * 64 * chunks * 2          # logits + dX, one product each (3xTF32 counts once)

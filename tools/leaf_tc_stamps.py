@@ -2,6 +2,7 @@ import ctypes, os, sys, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 from hier_slam_b200 import _lib, losses
 lib = _lib.load()
+losses.LEAF_KERNEL = "tcgen05"
 S, L, hh, ww = (int(x) for x in (sys.argv[1:5] if len(sys.argv) > 4 else (74, 550, 480, 640)))
 g = torch.Generator().manual_seed(0)
 sem = torch.randn(S, hh, ww, generator=g).cuda(); w = (0.3 * torch.randn(L, S, generator=g)).cuda(); b = torch.randn(L, generator=g).cuda()

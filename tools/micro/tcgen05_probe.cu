@@ -32,6 +32,23 @@ __host__ __device__ inline uint32_t idx_mnmajor(int m, int k, int K) {     // fl
     return (uint32_t)((m / 4) * (K / 8) * 32 + (k / 8) * 32 + (k % 8) * 4 + (m % 4));
 }
 
+// SWIZZLE_128B K-major (LayoutType::B128: Swizzle<3,4,3> o ((8,m),(T,2)):((8T,SBO),(1,T))): a row holds 32 consecutive K
+// elements (128 B), 8 rows = one 1024-B swizzle atom in which the 16-byte chunk index is XORed with the row index; K extents
+// beyond 32 are further [rows x 32] blocks.  The base must be 1024-byte aligned.
+__host__ __device__ inline uint32_t idx_sw128(int r, int k, int rows) {
+    const int kb = k / 32, kk = k % 32;
+    return (uint32_t)(kb * rows * 32 + (r / 8) * 256 + (r % 8) * 32 + (((kk / 4) ^ (r % 8)) * 4) + (kk % 4));
+}
+__device__ inline uint64_t smem_desc_sw128(uint32_t smem_addr_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr_bytes >> 4) & 0x3fff);
+    d |= (uint64_t)1 << 16;                                       // LBO: unused for swizzled K-major (convention: 1)
+    d |= (uint64_t)(1024 >> 4) << 32;                             // SBO: 8-row group pitch
+    d |= (uint64_t)1 << 46;                                       // version
+    d |= (uint64_t)2 << 61;                                       // layout type SWIZZLE_128B
+    return d;
+}
+
 __device__ inline uint64_t smem_desc(uint32_t smem_addr_bytes, uint32_t lbo, uint32_t sbo) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr_bytes >> 4) & 0x3fff);            // [0,14)  start address >> 4
@@ -72,7 +89,7 @@ __device__ inline float hi_part(float x) { return __uint_as_float(__float_as_uin
 __global__ void __launch_bounds__(128) probe_kernel(const float* __restrict__ A, const float* __restrict__ B,
                                                     float* __restrict__ D, int* __restrict__ err, int N, int K, int a_mode,
                                                     int b_mode, int split, int swap_mn) {
-    extern __shared__ __align__(128) float dsm[];
+    extern __shared__ __align__(1024) float dsm[];
     float* sA = dsm;
     float* sAlo = sA + M * K;
     float* sB = sAlo + M * K;
@@ -82,13 +99,13 @@ __global__ void __launch_bounds__(128) probe_kernel(const float* __restrict__ A,
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     for (int i = tid; i < M * K; i += 128) {
         const float v = A[i];
-        const uint32_t o = a_mode == 1 ? idx_mnmajor(i / K, i % K, K) : idx_kmajor(i / K, i % K, K);
+        const uint32_t o = a_mode == 3 ? idx_sw128(i / K, i % K, M) : a_mode == 1 ? idx_mnmajor(i / K, i % K, K) : idx_kmajor(i / K, i % K, K);
         sA[o] = split ? hi_part(v) : v;
         sAlo[o] = v - hi_part(v);
     }
     for (int i = tid; i < N * K; i += 128) {
         const float v = B[i];
-        const uint32_t o = b_mode == 1 ? idx_mnmajor(i / K, i % K, K) : idx_kmajor(i / K, i % K, K);
+        const uint32_t o = b_mode == 3 ? idx_sw128(i / K, i % K, N) : b_mode == 1 ? idx_mnmajor(i / K, i % K, K) : idx_kmajor(i / K, i % K, K);
         sB[o] = split ? hi_part(v) : v;
         sBlo[o] = v - hi_part(v);
     }
@@ -141,8 +158,10 @@ __global__ void __launch_bounds__(128) probe_kernel(const float* __restrict__ A,
                 const uint32_t a0 = (uint32_t)__cvta_generic_to_shared(pa), b0 = (uint32_t)__cvta_generic_to_shared(pb);
                 for (int k = 0; k < K / UMMA_K; k++) {
                     // K-major: 8 tf32 along K = 2 core matrices = 2 LBO; MN-major: one 8-row K group = 1 LBO
-                    const uint64_t da = a_mode == 1 ? smem_desc(a0 + k * 128, lbo_mn, sbo_mn) : smem_desc(a0 + k * 2 * lbo_k, lbo_k, sbo_k);
-                    const uint64_t db = b_mode == 1 ? smem_desc(b0 + k * 128, lbo_mn, sbo_mn) : smem_desc(b0 + k * 2 * lbo_k, lbo_k, sbo_k);
+                    // SWIZZLE_128B: K step of 8 tf32 = 32 bytes inside the 128-byte row; every 4th step enters the next [rows x 32] block
+                    const uint64_t da3 = smem_desc_sw128(a0 + (k / 4) * M * 128 + (k % 4) * 32), db3 = smem_desc_sw128(b0 + (k / 4) * N * 128 + (k % 4) * 32);
+                    const uint64_t da = a_mode == 3 ? da3 : a_mode == 1 ? smem_desc(a0 + k * 128, lbo_mn, sbo_mn) : smem_desc(a0 + k * 2 * lbo_k, lbo_k, sbo_k);
+                    const uint64_t db = b_mode == 3 ? db3 : b_mode == 1 ? smem_desc(b0 + k * 128, lbo_mn, sbo_mn) : smem_desc(b0 + k * 2 * lbo_k, lbo_k, sbo_k);
                     const uint32_t accumulate = first ? 0u : 1u;
                     first = false;
                     if (a_mode == 2) {
@@ -196,21 +215,15 @@ struct Case { const char* name; int N, K, a_mode, b_mode, split, exact_ints, swa
 int main() {
     const Case cases[] = {
         {"SS  A K-major   B K-major   N=64  K=32 ints", 64, 32, 0, 0, 0, 1},
-        {"SS  A MN-major  B K-major   N=64  K=32 ints", 64, 32, 1, 0, 0, 1},
         {"TS  A in TMEM   B K-major   N=64  K=32 ints", 64, 32, 2, 0, 0, 1},
-        {"SS  A K-major   B MN-major  N=64  K=32 ints", 64, 32, 0, 1, 0, 1},
-        {"SS  A MN-major  B MN-major  N=80  K=64 ints", 80, 64, 1, 1, 0, 1},
-        {"SS  A MN-major  B K-major   N=192 K=80 ints", 192, 80, 1, 0, 0, 1},
-        {"TS  A in TMEM   B MN-major  N=80  K=96 ints", 80, 96, 2, 1, 0, 1},
-        {"SS  A MN-major  B K-major   N=192 K=80 random, single tf32", 192, 80, 1, 0, 0, 0},
-        {"SS  A MN-major  B K-major   N=192 K=80 random, 3xTF32", 192, 80, 1, 0, 1, 0},
-        {"TS  A in TMEM   B MN-major  N=80  K=96 random, 3xTF32", 80, 96, 2, 1, 1, 0},
         {"SS  A K-major   B K-major   N=256 K=32 ints", 256, 32, 0, 0, 0, 1},
         {"SS  A K-major   B K-major   N=192 K=80 random, 3xTF32", 192, 80, 0, 0, 1, 0},
         {"TS  A in TMEM   B K-major   N=80  K=96 random, 3xTF32", 80, 96, 2, 0, 1, 0},
         {"SS  A K-major   B K-major   N=192 K=80 random, single tf32", 192, 80, 0, 0, 0, 0},
-        {"SS  A MN-major  B K-major   N=64  K=32 ints, LBO/SBO swapped", 64, 32, 1, 0, 0, 1, 1},
-        {"SS  A K-major   B MN-major  N=64  K=32 ints, LBO/SBO swapped", 64, 32, 0, 1, 0, 1, 1},
+        {"SS  A SW128     B SW128     N=64  K=32 ints", 64, 32, 3, 3, 0, 1},
+        {"SS  A SW128     B K-major   N=64  K=32 ints", 64, 32, 3, 0, 0, 1},
+        {"SS  A SW128     B SW128     N=80  K=128 ints", 80, 128, 3, 3, 0, 1},
+        {"SS  A SW128     B SW128     N=80  K=128 random, 3xTF32", 80, 128, 3, 3, 1, 0},
     };
     int failures = 0;
     for (const Case& c : cases) {
