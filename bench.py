@@ -192,7 +192,7 @@ def run_ours(a, rank, world, local):
     symm_note = None
     if world > 1 and a.allreduce != "nccl":
         from hier_slam_b200.mapping import enable_symmetric_allreduce
-        if enable_symmetric_allreduce(params, multicast=(a.allreduce != "p2p")) is None:
+        if enable_symmetric_allreduce(params, multicast={"symm": None, "multimem": True, "p2p": False}[a.allreduce]) is None:
             symm_note = getattr(params, "symm_error", None)
     up = {k: v.to(dev) for k, v in grads_cpu.items()}
     up_tuple = (up["color"], up["semantic"], up["depth"], up["median_depth"], up["final_opacity"])
@@ -412,6 +412,106 @@ def run_ours(a, rank, world, local):
                                 "what": "one all-reduce (SUM, fp32) of the flat gradient buffer per step; exposed time <= step time "
                                         "minus the sum of this library's kernels"}
     return out, (scene_cpu, grads_cpu, cfg)
+
+
+def run_mapping_k8(a, rank, world, local):
+    """BASELINE.json configs 4 / 5: multi-keyframe mapping, K = 8 keyframes per iteration partitioned over the ranks (keyframe
+    k -> rank k mod N: strong scaling), every keyframe a different pose of the replicated Gaussian set, rendered through the
+    public API (mapping_iteration + GaussianRasterizer_semantic) with the gradient pattern of Hier-SLAM's losses (colour,
+    semantics, depth), ONE all-reduce of the flat gradient per iteration.  value = keyframes / s over all ranks."""
+    import parity_tools as pt
+    import diff_gaussian_rasterization as dgr
+    from hier_slam_b200 import _lib
+    from hier_slam_b200.mapping import (FlatParams, allreduce_gradients, enable_symmetric_allreduce, keyframes_of_rank,
+                                        mapping_iteration)
+    lib = _lib.load()
+    K = 8
+    dev = torch.device("cuda", local)
+    cfg = CONFIGS[a.config]
+    sc = make_scene(cfg, 0, device=dev)
+    ug = upstream_grads(cfg, 1, device=dev)
+    poses = keyframe_poses(K, seed=2)
+    P = sc["means3D"].shape[0]
+
+    def make_loss(k):
+        settings = pt.make_settings(dgr.GaussianRasterizationSettings, cfg, dev, w2c=poses[k])
+        r = dgr.GaussianRasterizer_semantic(settings)
+        m2d = torch.zeros(P, 3, device=dev)
+
+        def f(lv):
+            color, radii, sem, depth, median, opac = r(means3D=lv["means3D"], means2D=m2d, opacities=lv["opacities"],
+                                                       colors_precomp=lv["colors_precomp"], scales=lv["scales"],
+                                                       rotations=lv["rotations"], semantics_precomp=lv["semantics_precomp"])
+            return (color * ug["color"]).sum() + (sem * ug["semantic"]).sum() + (depth * ug["depth"]).sum()
+        return f
+    losses = [make_loss(k) for k in range(K)]
+    params = FlatParams(sc)
+    symm_note = None
+    if world > 1 and a.allreduce != "nccl":
+        if enable_symmetric_allreduce(params, multicast={"symm": None, "multimem": True, "p2p": False}[a.allreduce]) is None:
+            symm_note = getattr(params, "symm_error", None)
+    step = lambda: mapping_iteration(params, losses, rank, world)
+    for _ in range(a.warmup):
+        step()
+    barrier(world)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    k0 = lib.hs_kernel_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        step()
+    e1.record()
+    barrier(world)
+    ms = max_over_ranks(e0.elapsed_time(e1), world)
+    launches = lib.hs_kernel_launch_count() - k0
+    clocks = sampler.stop() if rank == 0 else None
+    verify = None
+    if world > 1 and not a.no_verify:
+        step()
+        torch.cuda.synchronize()
+        reduced = params.flat_grad.detach().clone()
+        if rank == 0:
+            acc = torch.zeros_like(reduced, dtype=torch.float64)
+            for k in range(K):
+                p1 = FlatParams(sc)
+                mapping_iteration(p1, [losses[k]], 0, 1)
+                acc += p1.flat_grad.double()
+                p1.release()
+            err = float((reduced.double() - acc).norm() / acc.norm())
+            verify = {"allreduce_vs_serial_sum_rel_err": err, "ok": err <= 1e-5, "keyframes": K}
+        barrier(world)
+    ar_ms = None
+    if world > 1:
+        for _ in range(3):
+            allreduce_gradients(params)
+        barrier(world)
+        e0.record()
+        for _ in range(20):
+            allreduce_gradients(params)
+        e1.record()
+        barrier(world)
+        ar_ms = max_over_ranks(e0.elapsed_time(e1), world) / 20
+    if rank != 0:
+        return None
+    t = ms / a.steps
+    out = {"metric": METRIC.replace("fwd+bwd raster iterations/s (mapping keyframes/s)", "multi-keyframe mapping keyframes/s (K=8 per iteration)"),
+           "value": K / (t * 1e-3), "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": t,
+           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": cfg.name, "gaussians": P, "image": [cfg.width, cfg.height], "semantic_channels": cfg.num_semantic,
+                      "keyframes_per_iteration": K, "keyframes_per_rank": len(keyframes_of_rank(K, 0, world)),
+                      "parallelism": f"keyframe-dp{world}" if world > 1 else "single-gpu",
+                      "upstream_grads": "Hier-SLAM's gradient pattern: colour + semantics + depth",
+                      "l2": "per-keyframe working set > 126 MB L2; no explicit flush"},
+           "gpu_launches": int(launches), "clocks": clocks, "e2e": None,
+           "note": "BASELINE.json config 4 / 5 (multi-GPU mapping); the driver's headline line is --config c2"}
+    if world > 1:
+        out["allreduce"] = {"bytes": params.grad_bytes(), "collective": allreduce_name(), "symmetric_memory_error": symm_note,
+                            "ms_alone": ar_ms,
+                            "bus_bandwidth_GBps": 2 * (world - 1) / world * params.grad_bytes() / (ar_ms * 1e-3) / 1e9}
+        out["verify"] = verify
+    return out
 
 
 def timed_loop(fn, n, warm=3):
@@ -701,8 +801,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "ref-cuda"])
     ap.add_argument("--config", default="c2")
     ap.add_argument("--no-baselines", action="store_true", help="skip the cpu_baseline / ref_cuda legs")
-    ap.add_argument("--allreduce", default="symm", choices=["symm", "p2p", "nccl"],
-                    help="N > 1: this library's NVLink kernel with NVSwitch multicast (symm), with peer loads/stores (p2p), or NCCL")
+    ap.add_argument("--allreduce", default="symm", choices=["symm", "multimem", "p2p", "nccl"],
+                    help="N > 1: this library's NVLink kernel (symm: multicast for N > 2, peer loads / stores for N = 2; "
+                         "multimem / p2p force one form), or NCCL")
     ap.add_argument("--no-verify", action="store_true",
                     help="N > 1: skip the check that the all-reduced gradient equals the sum of the N single-keyframe gradients")
     a = ap.parse_args()
@@ -745,6 +846,15 @@ def main():
         return
 
     rank, world, local = dist_setup(a.gpus)
+    if a.config in ("c4", "c5"):
+        out = run_mapping_k8(a, rank, world, local)
+        if rank == 0:
+            print(json.dumps(out), flush=True)
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+            dist.destroy_process_group()
+        return
     out, (scene_cpu, grads_cpu, cfg) = run_ours(a, rank, world, local)
     if rank == 0:
         if world == 1 and not a.no_baselines:

@@ -67,23 +67,45 @@ __global__ void __launch_bounds__(512, 1) allreduce_sum_kernel(Peers P, float* m
     // this rank's slice, in 16-byte vectors
     const size_t per = (n4 + world - 1) / world;
     const size_t lo = (size_t)rank * per, hi = min(n4, lo + per);
-    for (size_t i = lo + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (size_t)gridDim.x * blockDim.x) {
+    constexpr int U = 4;     // independent 16-byte vectors in flight per thread
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i0 = lo + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < hi; i0 += U * stride) {
         if (MULTICAST) {
-            float4 v;
-            asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];\n"
-                         : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(reinterpret_cast<float4*>(mc) + i) : "memory");
-            asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};\n"
-                         ::"l"(reinterpret_cast<float4*>(mc) + i), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+            float4 v[U];
+#pragma unroll
+            for (int u = 0; u < U; u++)
+                if (i0 + u * stride < hi)
+                    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];\n"
+                                 : "=f"(v[u].x), "=f"(v[u].y), "=f"(v[u].z), "=f"(v[u].w)
+                                 : "l"(reinterpret_cast<float4*>(mc) + i0 + u * stride) : "memory");
+#pragma unroll
+            for (int u = 0; u < U; u++)
+                if (i0 + u * stride < hi)
+                    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};\n"
+                                 ::"l"(reinterpret_cast<float4*>(mc) + i0 + u * stride), "f"(v[u].x), "f"(v[u].y), "f"(v[u].z),
+                                 "f"(v[u].w) : "memory");
         } else {
-            float4 acc = reinterpret_cast<const float4*>(P.buf[0])[i];
+            float4 acc[U];
+#pragma unroll
+            for (int u = 0; u < U; u++)
+                acc[u] = (i0 + u * stride < hi) ? reinterpret_cast<const float4*>(P.buf[0])[i0 + u * stride] : make_float4(0.f, 0.f, 0.f, 0.f);
             for (int r = 1; r < world; r++) {      // fixed rank order: every rank computes bit-identical sums
-                const float4 v = reinterpret_cast<const float4*>(P.buf[r])[i];
-                acc.x += v.x;
-                acc.y += v.y;
-                acc.z += v.z;
-                acc.w += v.w;
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    if (i0 + u * stride < hi) {
+                        const float4 v = reinterpret_cast<const float4*>(P.buf[r])[i0 + u * stride];
+                        acc[u].x += v.x;
+                        acc[u].y += v.y;
+                        acc[u].z += v.z;
+                        acc[u].w += v.w;
+                    }
+                }
             }
-            for (int r = 0; r < world; r++) reinterpret_cast<float4*>(P.buf[r])[i] = acc;
+            for (int r = 0; r < world; r++) {
+#pragma unroll
+                for (int u = 0; u < U; u++)
+                    if (i0 + u * stride < hi) reinterpret_cast<float4*>(P.buf[r])[i0 + u * stride] = acc[u];
+            }
         }
     }
     rank_barrier(P, rank, world, epoch + 1);
@@ -108,7 +130,7 @@ int launch_allreduce_sum(void* multicast_ptr, void* const* peer_bufs, void* cons
         P.pad[r] = r < world ? (uint32_t*)peer_pads[r] : nullptr;
         P.buf[r] = (r < world && peer_bufs != nullptr) ? (float*)peer_bufs[r] : nullptr;
     }
-    if (blocks <= 0) blocks = 64;
+    if (blocks <= 0) blocks = 128;
     if (multicast_ptr != nullptr)
         allreduce_sum_kernel<true><<<blocks, 512, 0, stream>>>(P, (float*)multicast_ptr, rank, world, n / 4, epoch);
     else

@@ -174,10 +174,14 @@ class SymmetricAllReduce:
                 ("NVSwitch multicast (multimem.ld_reduce + multimem.st)" if self.multicast_ptr else "peer loads / stores (two-shot)"))
 
 
-def enable_symmetric_allreduce(params: FlatParams, group=None, blocks: int = 64, multicast: bool = True):
+def enable_symmetric_allreduce(params: FlatParams, group=None, blocks: int = 64, multicast: Optional[bool] = None):
     """Switches `allreduce_gradients(params)` to this library's NVLink kernel.  Returns the SymmetricAllReduce object, or
-    None (with the reason in `.symm_error`) when symmetric memory cannot be set up -- NCCL's all_reduce is used then."""
+    None (with the reason in `.symm_error`) when symmetric memory cannot be set up -- NCCL's all_reduce is used then.
+    multicast None = by world size: measured on 8 x B200 (tools/allreduce_bench.py, 48 MB): NVSwitch multicast 0.139 ms vs
+    peer loads / stores 0.166 ms vs NCCL 0.223 ms; on 2 GPUs peer 0.095 ms vs multicast 0.144 ms vs NCCL 0.115 ms."""
     try:
+        if multicast is None:
+            multicast = dist.get_world_size(group) > 2
         params._symm = SymmetricAllReduce(params, group, blocks, multicast)
     except Exception as ex:          # no NVLink peer access / no fabric support: keep the NCCL collective
         params._symm = None
