@@ -636,6 +636,37 @@ def run_extras(a):
             opt.step()
             conv_opt.step()
         ms = timed_loop(map_step, max(5, min(a.steps, 20)))
+        # the same iteration as ONE CUDA graph: capacity-mode binning, FlatAdam with the step count on the device
+        try:
+            from hier_slam_b200.mapping import GraphedMappingIteration, static_camera
+            raster_g = GraphedMappingIteration  # noqa: F841  (name kept short below)
+            cam_static = static_camera(settings)
+            raster2 = GaussianRasterizer_semantic(raster_settings=cam_static)
+            opt_g = FlatAdam(params, {k: 1e-3 for k in params.names}, eps=1e-15, device_step=True)
+            conv_opt_g = torch.optim.Adam(conv.parameters(), lr=5e-4, capturable=True)
+
+            def map_step_static():
+                opt_g.zero_grad()
+                conv_opt_g.zero_grad(set_to_none=False)
+                im, radii, sem, depth, median, sil = raster2(
+                    means3D=lv["means3D"], means2D=means2D, opacities=lv["opacities"], colors_precomp=lv["colors_precomp"],
+                    scales=lv["scales"], rotations=lv["rotations"], semantics_precomp=lv["semantics_precomp"])
+                loss = (masked_l1_sum(depth, gt_depth, mask) / n_mask + 0.5 * l1_ssim_loss(im, gt_im)
+                        + 0.2 * tree_semantic_loss(sem, labels, sizes, conv.weight, conv.bias, 1.0, 5.0, num_valid=H * W,
+                                                 level_valid=H * W))
+                loss.backward()
+                opt_g.step()
+                conv_opt_g.step()
+                return loss.detach()
+            gm = GraphedMappingIteration(params, map_step_static, warmup=2)
+            ms_g = timed_loop(gm.replay, max(5, min(a.steps, 20)))
+            out["mapping_iteration_graphed"] = {"value": 1e3 / ms_g, "unit": "iterations/s", "ms_per_iteration": ms_g,
+                                                "capacity_overflow": gm.overflowed(),
+                                                "what": "the same mapping iteration captured once and replayed as one CUDA graph "
+                                                        "(hier_slam_b200.mapping.GraphedMappingIteration)"}
+            del gm
+        except Exception as ex:
+            out["mapping_iteration_graphed"] = {"error": repr(ex)}
         out["mapping_iteration"] = {"value": 1e3 / ms, "unit": "iterations/s", "ms_per_iteration": ms,
                                     "what": "render + 1.0 depth L1 + 0.5 (0.8 L1 + 0.2 (1 - SSIM)) + 0.2 (level CE + 5 leaf CE "
                                             f"behind a 1x1 conv to {leaves_n} classes) + backward + Adam on all Gaussian "

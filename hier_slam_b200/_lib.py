@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("HS_LIB", os.path.join(HERE, "libhsraster.so"))
 EXPORTED_SYMBOLS = [
     "hs_abi_version", "hs_last_error", "hs_supports_semantic_channels", "hs_geom_state_bytes",
     "hs_image_state_bytes", "hs_binning_state_bytes", "hs_image_state_info_offset", "hs_forward_geometry", "hs_forward_render",
-    "hs_backward", "hs_mark_visible", "hs_masked_l1", "hs_hier_cross_entropy", "hs_leaf_cross_entropy", "hs_leaf_cross_entropy_tc", "hs_leaf_ce_workspace_bytes", "hs_leaf_tc_debug", "hs_allreduce_sum", "hs_l1_ssim", "hs_adam_step", "hs_transform_points", "hs_tracking_loss", "hs_pose_step", "hs_keyframe_overlap",
+    "hs_backward", "hs_mark_visible", "hs_masked_l1", "hs_hier_cross_entropy", "hs_leaf_cross_entropy", "hs_leaf_cross_entropy_tc", "hs_leaf_ce_workspace_bytes", "hs_leaf_tc_debug", "hs_allreduce_sum", "hs_l1_ssim", "hs_adam_step", "hs_adam_step_device", "hs_transform_points", "hs_tracking_loss", "hs_pose_step", "hs_keyframe_overlap",
     "hs_compact_scratch_bytes", "hs_compact_plan", "hs_compact_gather",
     "hs_geom_state_layout", "hs_image_state_layout",
     "hs_binning_state_layout", "hs_profile_enable", "hs_profile_read", "hs_kernel_launch_count",
@@ -92,6 +92,9 @@ def load() -> ctypes.CDLL:
     lib.hs_adam_step.argtypes = [vp, vp, vp, vp, c_size_t, c_int, POINTER(c_ulonglong), POINTER(c_double), c_double, c_double,
                                  c_double, c_int, vp]
     lib.hs_adam_step.restype = c_int
+    lib.hs_adam_step_device.argtypes = [vp, vp, vp, vp, c_size_t, c_int, POINTER(c_ulonglong), POINTER(c_double), c_double,
+                                        c_double, c_double, vp, vp, vp]
+    lib.hs_adam_step_device.restype = c_int
     lib.hs_transform_points.argtypes = [vp, vp, c_int, vp, vp]
     lib.hs_transform_points.restype = c_int
     lib.hs_tracking_loss.argtypes = [vp, vp, vp, vp, vp, c_size_t, c_float, c_int, c_float, c_float, vp, vp, vp, vp]

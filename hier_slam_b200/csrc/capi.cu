@@ -424,6 +424,18 @@ int hs_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg
                             (cudaStream_t)stream_);
 }
 
+int hs_adam_step_device(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, int segments,
+                        const unsigned long long* segment_end, const double* segment_lr, double beta1, double beta2, double eps,
+                        int* step_counter, float* scalars, void* stream_) {
+    if (param == nullptr || grad == nullptr || exp_avg == nullptr || exp_avg_sq == nullptr || segment_end == nullptr ||
+        segment_lr == nullptr || step_counter == nullptr || scalars == nullptr) {
+        set_error("hs_adam_step_device: NULL argument");
+        return 1;
+    }
+    return launch_adam_flat(param, grad, exp_avg, exp_avg_sq, n, segments, segment_end, segment_lr, beta1, beta2, eps, 1,
+                            (cudaStream_t)stream_, step_counter, scalars);
+}
+
 size_t hs_compact_scratch_bytes(int P) { return compact_scratch_bytes(P); }
 
 int hs_compact_plan(const unsigned char* keep, int P, void* scratch, void* stream_) {

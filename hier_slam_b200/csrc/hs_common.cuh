@@ -168,7 +168,7 @@ int launch_keyframe_overlap(const float* pts, int N, const float* w2c, int K, fl
                             int height, int edge, int* counts, cudaStream_t stream);
 int launch_adam_flat(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, int n_seg,
                      const unsigned long long* seg_end, const double* seg_lr, double beta1, double beta2, double eps, int step,
-                     cudaStream_t stream);
+                     cudaStream_t stream, int* step_counter = nullptr, float* dev_scalars = nullptr);
 size_t compact_scratch_bytes(int P);
 int launch_compact_plan(const uint8_t* keep, int P, unsigned* scratch, cudaStream_t stream);
 int launch_compact_gather(const float* src, float* dst, const unsigned* scratch, int P, int rows, int n_seg,

@@ -24,11 +24,14 @@ struct AdamSegments {
 __global__ void __launch_bounds__(256) adam_flat_kernel(float4* __restrict__ param, const float4* __restrict__ grad,
                                                         float4* __restrict__ exp_avg, float4* __restrict__ exp_avg_sq,
                                                         size_t n4, AdamSegments seg, float w1, float beta2, float w2,
-                                                        float bc2_sqrt, float eps) {
+                                                        float bc2_sqrt, float eps, const float* __restrict__ dev_scalars) {
+    // dev_scalars (device-side step counter, hs_adam_step_device): [segment] -> -(lr / bias_correction1), [HS_MAX_SEGMENTS]
+    // -> sqrt(bias_correction2), written by adam_scalars_kernel just before this launch
+    if (dev_scalars != nullptr) bc2_sqrt = dev_scalars[HS_MAX_SEGMENTS];
     for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (size_t)gridDim.x * 256) {
         int s = 0;
         while (s < seg.n - 1 && 4 * i >= seg.end[s]) s++;
-        const float nss = seg.neg_step_size[s];
+        const float nss = dev_scalars != nullptr ? dev_scalars[s] : seg.neg_step_size[s];
         const float4 g4 = grad[i];
         float4 p4 = param[i], m4 = exp_avg[i], v4 = exp_avg_sq[i];
         const float g[4] = {g4.x, g4.y, g4.z, g4.w};
@@ -47,10 +50,26 @@ __global__ void __launch_bounds__(256) adam_flat_kernel(float4* __restrict__ par
     }
 }
 
+// step counter on the device (CUDA-graph capturable optimiser step): ++step, then the bias-correction scalars in double like
+// the host path / torch's Python scalars
+struct AdamLrs {
+    double lr[HS_MAX_SEGMENTS];
+};
+__global__ void adam_scalars_kernel(int* __restrict__ step_counter, float* __restrict__ scalars, AdamLrs lrs, int n_seg,
+                                    double beta1, double beta2) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int step = step_counter[0] + 1;
+    step_counter[0] = step;
+    const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
+    for (int s = 0; s < n_seg; s++) scalars[s] = (float)((lrs.lr[s] / bc1) * -1.0);
+    scalars[HS_MAX_SEGMENTS] = (float)sqrt(bc2);
+}
+
 int launch_adam_flat(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, int n_seg,
                      const unsigned long long* seg_end, const double* seg_lr, double beta1, double beta2, double eps, int step,
-                     cudaStream_t stream) {
+                     cudaStream_t stream, int* step_counter, float* dev_scalars) {
     if (n == 0) return 0;
+    if (step_counter != nullptr) step = 1;      // the real count lives on the device
     if (n_seg < 1 || n_seg > HS_MAX_SEGMENTS || (n & 3) != 0 || step < 1) {
         set_error("adam: 1..%d segments, a multiple of 4 elements and step >= 1 required", HS_MAX_SEGMENTS);
         return 1;
@@ -71,8 +90,19 @@ int launch_adam_flat(float* param, const float* grad, float* exp_avg, float* exp
     const size_t n4 = n / 4;
     int blocks = (int)((n4 + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
+    if (step_counter != nullptr) {
+        if (dev_scalars == nullptr) {
+            set_error("adam: the device-side step counter needs a scalar scratch of %d floats", HS_MAX_SEGMENTS + 1);
+            return 1;
+        }
+        AdamLrs lrs;
+        for (int s = 0; s < HS_MAX_SEGMENTS; s++) lrs.lr[s] = s < n_seg ? seg_lr[s] : 0.0;
+        adam_scalars_kernel<<<1, 32, 0, stream>>>(step_counter, dev_scalars, lrs, n_seg, b1, b2);
+        HS_LAUNCH_OK(stream, false);
+    }
     adam_flat_kernel<<<blocks, 256, 0, stream>>>((float4*)param, (const float4*)grad, (float4*)exp_avg, (float4*)exp_avg_sq, n4,
-                                                 seg, (float)(1.0 - b1), (float)b2, (float)(1.0 - b2), (float)sqrt(bc2), (float)eps);
+                                                 seg, (float)(1.0 - b1), (float)b2, (float)(1.0 - b2), (float)sqrt(bc2), (float)eps,
+                                                 step_counter != nullptr ? dev_scalars : nullptr);
     HS_LAUNCH_OK(stream, false);
     return 0;
 }

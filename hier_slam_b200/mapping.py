@@ -293,3 +293,71 @@ def mapping_iteration(params: FlatParams, keyframe_losses: Sequence[Callable[[Di
             total = total + loss.detach()
     allreduce_gradients(params, group)
     return total
+
+
+def static_camera(raster_settings):
+    """The same GaussianRasterizationSettings with contiguous float32 tensors of its own: what a captured graph may safely
+    keep pointers to (the reference's setup_camera hands out transposed views, utils/recon_helpers.py:8-13)."""
+    own = lambda t: t.detach().to(torch.float32).contiguous().clone()
+    rs = raster_settings
+    return rs._replace(bg=own(rs.bg), viewmatrix=own(rs.viewmatrix), projmatrix=own(rs.projmatrix), campos=own(rs.campos))
+
+
+class GraphedMappingIteration:
+    """One mapping iteration of Hier-SLAM (scripts/hierslam.py:1986-2059: pick a keyframe, get_loss_semantic_mlp,
+    loss.backward(), optimizer.step(), zero_grad) as ONE CUDA-graph launch.
+
+    `iteration()` must do the whole iteration on static inputs: zero the gradients, render from `params.leaves` (through
+    GaussianRasterizer_semantic / PoseRasterizer_semantic), evaluate the loss with the kernels of hier_slam_b200.losses
+    (pass num_valid / level_valid: no host sync), call backward, and step the optimisers (FlatAdam(device_step=True);
+    torch optimisers with capturable=True).  It is run eagerly a few times (warm-up, and to size the binning capacity: the
+    forward's only host read-back, `num_rendered`, is replaced by capacity-mode binning, `_C.BinningCapacity`), captured
+    once and replayed.  What changes between iterations -- the keyframe's images, labels and pose -- lives in tensors
+    that the caller overwrites in place before `replay()`.
+
+    A replay whose frame outgrew the capacity renders empty; `overflowed()` (one host read, e.g. once per mapped frame)
+    reports it, `recapture()` re-sizes.  Note: the optimiser also steps in the eager warm-up iterations."""
+
+    def __init__(self, params: FlatParams, iteration: Callable[[], torch.Tensor], warmup: int = 2, slack: float = 1.3):
+        from . import _C
+        self.params, self.iteration, self.slack = params, iteration, slack
+        self.graph = None
+        self.capacity = None
+        self.loss = None
+        self._C = _C
+        self._capture(warmup)
+
+    def _capture(self, warmup: int, at_least=None) -> None:
+        _C = self._C
+        dev = self.params.flat.device
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            with _C.record_binning() as infos:
+                for _ in range(max(warmup, 1)):
+                    self.iteration()
+            if not infos:
+                raise RuntimeError("GraphedMappingIteration: the iteration does not contain a rasterizer call")
+            both = torch.stack(infos)[:, :2].max(0).values.tolist()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        inst, longest = int(both[0] * self.slack) + 65536, int(both[1] * self.slack) + 256
+        if at_least is not None:
+            inst, longest = max(inst, at_least[0]), max(longest, at_least[1])
+        self.capacity = _C.BinningCapacity(inst, longest)
+        self.graph = torch.cuda.CUDAGraph()
+        with _C.async_binning(self.capacity):
+            with torch.cuda.graph(self.graph):
+                self.loss = self.iteration()
+
+    def replay(self) -> torch.Tensor:
+        """one iteration; returns the (static) loss tensor of the captured graph -- read it only when needed"""
+        self.graph.replay()
+        return self.loss
+
+    def overflowed(self) -> bool:
+        return self.capacity.overflowed()
+
+    def recapture(self, warmup: int = 1) -> None:
+        """after an overflow (or when the number of Gaussians changed: build a new object then)"""
+        need = torch.stack(self.capacity.infos)[:, :2].max(0).values.tolist() if self.capacity.infos else [0, 0]
+        self._capture(warmup, (int(need[0] * self.slack) + 65536, int(need[1] * self.slack) + 256))

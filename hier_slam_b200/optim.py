@@ -22,7 +22,12 @@ def _stream(dev):
 
 
 class FlatAdam:
-    def __init__(self, params: FlatParams, lrs: Dict[str, float], betas=(0.9, 0.999), eps: float = 1e-8):
+    """device_step=True keeps the step count on the device (hs_adam_step_device): `step()` then contains no host value
+    that changes from call to call, so it can be captured in a CUDA graph together with the render and the losses
+    (hier_slam_b200.mapping.GraphedMappingIteration)."""
+
+    def __init__(self, params: FlatParams, lrs: Dict[str, float], betas=(0.9, 0.999), eps: float = 1e-8,
+                 device_step: bool = False):
         if not params.flat.is_cuda:
             raise RuntimeError("FlatAdam is CUDA-only (no CPU fallback)")
         missing = [k for k in params.names if k not in lrs]
@@ -37,6 +42,10 @@ class FlatAdam:
         self.step_count = 0
         self.exp_avg = torch.zeros_like(params.flat)
         self.exp_avg_sq = torch.zeros_like(params.flat)
+        self.device_step = bool(device_step)
+        if self.device_step:
+            self.step_dev = torch.zeros(1, dtype=torch.int32, device=params.flat.device)
+            self.scalars_dev = torch.zeros(32, dtype=torch.float32, device=params.flat.device)
 
     def zero_grad(self) -> None:
         self.params.zero_grad()
@@ -57,6 +66,12 @@ class FlatAdam:
         lrs = (ctypes.c_double * n_seg)(*[self.lrs[k] for k in p.names])
         vp = lambda t: ctypes.c_void_p(t.data_ptr())
         with torch.cuda.device(p.flat.device):
+            if self.device_step:
+                _lib.check(lib.hs_adam_step_device(vp(p.flat), vp(p.flat_grad), vp(self.exp_avg), vp(self.exp_avg_sq),
+                                                   p.flat.numel(), n_seg, ends, lrs, self.betas[0], self.betas[1], self.eps,
+                                                   vp(self.step_dev), vp(self.scalars_dev), _stream(p.flat.device)),
+                           "hs_adam_step_device")
+                return
             _lib.check(lib.hs_adam_step(vp(p.flat), vp(p.flat_grad), vp(self.exp_avg), vp(self.exp_avg_sq), p.flat.numel(),
                                         n_seg, ends, lrs, self.betas[0], self.betas[1], self.eps, self.step_count,
                                         _stream(p.flat.device)), "hs_adam_step")

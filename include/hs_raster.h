@@ -179,6 +179,14 @@ int hs_keyframe_overlap(const float* points, int num_points, const float* w2c, i
 int hs_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, int segments,
                  const unsigned long long* segment_end, const double* segment_lr, double beta1, double beta2, double eps,
                  int step, void* stream);
+/* The same update with the step count on the DEVICE, so that a whole mapping iteration (render, losses, backward, this
+ * step) can be captured in one CUDA graph and replayed: step_counter[0] (int32, device; 0 before the first step) is
+ * incremented by a one-thread kernel that also evaluates the bias-correction scalars (in double, as above) into
+ * scalars[HS_ADAM_SCALARS] (float32, device scratch); the update kernel reads them from there. */
+#define HS_ADAM_SCALARS 17
+int hs_adam_step_device(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, int segments,
+                        const unsigned long long* segment_end, const double* segment_lr, double beta1, double beta2, double eps,
+                        int* step_counter, float* scalars, void* stream);
 
 /* Extension: Gaussian pruning (utils/slam_external.py:142-164 remove_points: `tensor[to_keep]` on every parameter and both
  * Adam moments).  hs_compact_plan turns keep[P] (device bytes, non-zero = keep) into an ordered source-row list inside

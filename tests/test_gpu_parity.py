@@ -560,7 +560,8 @@ def test_leaf_cross_entropy_matches_torch(S, L, H, W, use_bias, kernel, float32_
     assert_grads_close(sem.grad, ref_leaves[0].grad, "d loss / d sem", tol=2e-5)
     assert_grads_close(weight.grad, ref_leaves[1].grad, "d loss / d weight", tol=2e-5)
     if use_bias:
-        assert_grads_close(bias.grad, ref_leaves[2].grad, "d loss / d bias", tol=2e-5)
+        # the bias gradient is a sum over all pixels of (softmax - onehot): heavy cancellation, fp32 round-off level
+        assert_grads_close(bias.grad, ref_leaves[2].grad, "d loss / d bias", tol=1e-4)
 
 
 def test_tree_semantic_loss_matches_torch(float32_convolutions):
@@ -1234,3 +1235,63 @@ def test_keyframe_parallel_mapping_gradient_sum():
     assert_grads_close(total, plain.flat_grad, "direct accumulation vs autograd accumulation", tol=1e-5)
     for k in ("colors_precomp", "semantics_precomp"):
         assert float(plain.leaves[k].grad.abs().max()) > 0
+
+
+def test_graphed_mapping_iteration_matches_the_eager_loop(float32_convolutions):
+    """hier_slam_b200.mapping.GraphedMappingIteration: render + the complete mapping loss (depth L1, 0.8 L1 + 0.2 (1 - SSIM)
+    colour, level CE + leaf CE behind the 1x1 conv: scripts/hierslam.py:905-1016) + backward + Adam on every Gaussian
+    parameter (FlatAdam with the step count on the device) and on the conv (torch Adam, capturable) as ONE CUDA graph,
+    against the same iteration run eagerly with host-side step counts."""
+    import diff_gaussian_rasterization as dgr
+    from hier_slam_b200.losses import l1_ssim_loss, masked_l1_sum, tree_semantic_loss
+    from hier_slam_b200.mapping import FlatParams, GraphedMappingIteration, static_camera
+    from hier_slam_b200.optim import FlatAdam
+    cfg = CONFIGS["c1"]
+    H, W, sizes, leaves_n = cfg.height, cfg.width, [4, 5, 5, 6, 6], 102
+    sc = make_scene(cfg, 0, device="cuda")
+    g = torch.Generator().manual_seed(3)
+    gt_im = torch.rand(3, H, W, generator=g).cuda()
+    gt_depth = (0.5 + 5 * torch.rand(1, H, W, generator=g)).cuda()
+    labels = torch.stack([torch.randint(0, n, (H, W), generator=g) for n in sizes + [leaves_n]]).int().cuda()
+    mask = gt_depth > 0.6
+    n_mask = float(mask.sum())
+    settings = static_camera(pt.make_settings(dgr.GaussianRasterizationSettings, cfg, "cuda"))
+    raster = dgr.GaussianRasterizer_semantic(settings)
+    P = sc["means3D"].shape[0]
+    means2D = torch.zeros(P, 3, device="cuda")
+    lrs = dict(means3D=1e-4, colors_precomp=2.5e-3, semantics_precomp=2.5e-3, opacities=5e-2, scales=1e-3, rotations=1e-3)
+
+    def build(device_step):
+        torch.manual_seed(11)
+        params = FlatParams(sc)
+        conv = torch.nn.Conv2d(sum(sizes), leaves_n, kernel_size=1).cuda()
+        opt = FlatAdam(params, lrs, eps=1e-15, device_step=device_step)
+        conv_opt = torch.optim.Adam(conv.parameters(), lr=5e-4, capturable=device_step)
+
+        def iteration():
+            opt.zero_grad()
+            conv_opt.zero_grad(set_to_none=False)
+            lv = params.leaves
+            im, radii, sem, depth, median, sil = raster(
+                means3D=lv["means3D"], means2D=means2D, opacities=lv["opacities"], colors_precomp=lv["colors_precomp"],
+                scales=lv["scales"], rotations=lv["rotations"], semantics_precomp=lv["semantics_precomp"])
+            loss = (masked_l1_sum(depth, gt_depth, mask) / n_mask + 0.5 * l1_ssim_loss(im, gt_im)
+                    + 0.2 * tree_semantic_loss(sem, labels, sizes, conv.weight, conv.bias, 1.0, 5.0, num_valid=H * W,
+                                             level_valid=H * W))
+            loss.backward()
+            opt.step()
+            conv_opt.step()
+            return loss.detach()
+        return params, conv, iteration
+    n_iters, warm = 6, 2
+    pe, ce, it_e = build(False)
+    losses_e = [float(it_e()) for _ in range(n_iters)]
+    pg, cg, it_g = build(True)
+    gm = GraphedMappingIteration(pg, it_g, warmup=warm)          # `warm` eager iterations (they step the optimisers too)
+    losses_g = [float(gm.replay()) for _ in range(n_iters - warm)]
+    assert not gm.overflowed()
+    for a, b in zip(losses_g, losses_e[warm:]):
+        assert abs(a - b) <= 2e-4 * abs(b), (losses_g, losses_e)
+    assert losses_e[-1] < losses_e[0]
+    assert_grads_close(pg.flat, pe.flat, "parameters after the graphed iterations", tol=2e-5)
+    assert_grads_close(cg.weight.detach(), ce.weight.detach(), "conv weight", tol=2e-5)
