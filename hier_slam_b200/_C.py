@@ -190,9 +190,10 @@ _BUILT_S = (16, 26, 32, 48, 64, 74, 102)   # semantic channel counts instantiate
 
 
 def _padded_channels(S: int) -> int:
-    """Kernels are instantiated for the channel counts Hier-SLAM ships (config.h:18: 16 / 26 / 74 / 102).  Any other
-    S <= 102 (another label tree) runs on the next larger instantiation with zero-padded columns: the extra channels
-    blend zeros, receive zero upstream gradients and are sliced away again."""
+    """Kernels are instantiated for the channel counts Hier-SLAM ships (config.h:18: 16 / 26 / 74 / 102) and a few in
+    between.  Any other S <= 102 (another label tree) runs on the next larger instantiation with zero-padded columns: the
+    extra channels blend zeros, receive zero upstream gradients and are sliced away again.  S > 102 is rendered in
+    several passes (`_chunks`)."""
     for b in _BUILT_S:
         if S <= b:
             return b
@@ -200,9 +201,25 @@ def _padded_channels(S: int) -> int:
                        f"other values up to 102 are zero-padded)")
 
 
+_CHUNK = 74     # channels per pass when S exceeds the widest instantiation
+
+
+def _chunks(S: int):
+    """[(first channel, channels, instantiated width)] of the passes that render S > 102 semantic channels (the reference
+    supports any NUM_SEMANTIC by recompiling, cuda_rasterizer/config.h:18; e.g. a flat 550-class map).  Geometry, tile
+    lists, transmittance and n_contrib do not depend on the semantic channels, so every pass blends over the SAME sorted
+    lists (HS_REUSE_BINNING) and the backward -- linear in the upstream gradients -- is the sum of the per-pass backwards."""
+    out, c0 = [], 0
+    while c0 < S:
+        n = min(_CHUNK, S - c0)
+        out.append((c0, n, _padded_channels(n)))
+        c0 += n
+    return out
+
+
 def _forward(background, means3D, colors, semantics, opacity, scales, rotations, scale_modifier, cov3D_precomp,
              viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height, image_width, sh, degree, campos, prefiltered,
-             debug, semantic: bool):
+             debug, semantic: bool, extra_semantic_chunks=()):
     lib = _lib.load()
     if means3D.dim() != 2 or means3D.size(1) != 3:
         raise RuntimeError("means3D must have dimensions (num_points, 3)")   # rasterize_points.cu:266-268
@@ -289,7 +306,22 @@ def _forward(background, means3D, colors, semantics, opacity, scales, rotations,
                                          _ptr(imgBuffer), img_bytes, _ptr(out_color), _ptr(out_sem), _ptr(out_depth),
                                          _ptr(out_median), _ptr(out_opacity), _ptr(out_mask), flags, stream),
                    "hs_forward_render")
+        # more semantic channels than the widest instantiation: further blend passes over the same sorted lists
+        extra_out = []
+        for chunk in extra_semantic_chunks:
+            chunk_c = _f32c(chunk, "semantics_precomp", device)
+            Sc = int(chunk_c.size(1))
+            o_sem = torch.empty(Sc, H, W, **fopt)
+            _lib.check(lib.hs_forward_render(ctypes.byref(cam), P, Sc, num_rendered, int(hint.value), _ptr(colors_c),
+                                             _ptr(chunk_c), _ptr(radii), _ptr(geomBuffer), _ptr(binningBuffer), bin_bytes,
+                                             _ptr(imgBuffer), img_bytes, _ptr(out_color), _ptr(o_sem), _ptr(out_depth),
+                                             _ptr(out_median), _ptr(out_opacity), None, flags | _lib.HS_REUSE_BINNING,
+                                             stream), "hs_forward_render")
+            extra_out.append(o_sem)
         del keep
+    if extra_semantic_chunks:
+        return num_rendered, (out_color, out_sem, out_depth, out_median, out_opacity, out_mask), radii, geomBuffer, \
+            binningBuffer, imgBuffer, extra_out
     return num_rendered, (out_color, out_sem, out_depth, out_median, out_opacity, out_mask), radii, geomBuffer, \
         binningBuffer, imgBuffer
 
@@ -299,6 +331,15 @@ def rasterize_gaussians_semantic(background, means3D, colors, semantics, opacity
                                  image_width, sh, degree, campos, prefiltered, debug):
     """reference: RasterizeGaussiansCUDA_semantic, rasterize_points.cu:240-336."""
     S = int(semantics.size(1)) if (semantics is not None and semantics.dim() == 2 and semantics.numel() > 0) else 0
+    if S > _BUILT_S[-1] and means3D.size(0) > 0:
+        pad = lambda t, w: t if t.size(1) == w else torch.nn.functional.pad(t, (0, w - t.size(1)))
+        parts = [pad(semantics[:, c0:c0 + n], w) for c0, n, w in _chunks(S)]
+        n, o, radii, gb, bb, ib, extra = _forward(background, means3D, colors, parts[0], opacity, scales, rotations,
+                                                  scale_modifier, cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy,
+                                                  image_height, image_width, sh, degree, campos, prefiltered, debug, True,
+                                                  extra_semantic_chunks=parts[1:])
+        sem = torch.cat([img[:nc] for img, (c0, nc, w) in zip([o[1]] + extra, _chunks(S))], 0)
+        return n, o[0], sem, o[2], o[3], o[4], radii, gb, bb, ib
     Sp = _padded_channels(S) if S > 0 else 0
     if Sp != S:
         semantics = torch.nn.functional.pad(semantics, (0, Sp - S))
@@ -415,6 +456,33 @@ def rasterize_gaussians_backward_semantic(background, means3D, radii, colors, se
     H, W = _hw(imageBuffer, (dL_dout_color, dL_dout_semantic, dL_dout_depth, dL_dout_median_depth,
                              dL_dout_final_opacity), image_height, image_width)
     S = int(semantics.size(1)) if (semantics is not None and semantics.dim() == 2 and semantics.numel() > 0) else 0
+    if S > _BUILT_S[-1] and means3D.size(0) > 0:
+        # several passes over the same state (see _chunks): the first carries every non-semantic upstream gradient, the
+        # others only their slice of dL/dout_semantic; geometry gradients add up, dL/dsemantics is concatenated
+        total = None
+        sem_grads = []
+        for i, (c0, nc, w) in enumerate(_chunks(S)):
+            sem_c = semantics[:, c0:c0 + nc]
+            g_c = None if dL_dout_semantic is None else dL_dout_semantic[c0:c0 + nc]
+            if w != nc:
+                sem_c = torch.nn.functional.pad(sem_c, (0, w - nc))
+                if g_c is not None:
+                    g_c = torch.cat((g_c, g_c.new_zeros(w - nc, H, W)), 0)
+            first = i == 0
+            r = _backward(background, means3D, radii, colors, sem_c.contiguous(), scales, rotations, scale_modifier,
+                          cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, dL_dout_color if first else None,
+                          None if g_c is None else g_c.contiguous(), dL_dout_depth if first else None,
+                          dL_dout_median_depth if first else None, dL_dout_final_opacity if first else None, sh, degree,
+                          campos, geomBuffer, R, binningBuffer, imageBuffer, debug, H, W, True, pose_points=pose_points)
+            sem_grads.append(r[2][:, :nc])
+            if total is None:
+                total = list(r)
+            elif g_c is not None:          # without an upstream gradient the pass contributes exact zeros
+                for k in (0, 1, 3, 4, 5, 7, 8) + ((9,) if pose_points is not None else ()):
+                    if total[k] is not None and r[k] is not None:
+                        total[k] = total[k] + r[k]
+        total[2] = torch.cat(sem_grads, 1)
+        return tuple(total)
     Sp = _padded_channels(S) if S > 0 else 0
     if Sp != S:   # zero-padded instantiation (see _padded_channels): the forward state was produced with Sp channels
         semantics = torch.nn.functional.pad(semantics, (0, Sp - S))

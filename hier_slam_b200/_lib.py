@@ -27,6 +27,7 @@ HS_SEM_ALPHA_EXACT = 1
 HS_NO_CULL = 2
 HS_BWD_SIMT = 4
 HS_SORT_GLOBAL = 32
+HS_REUSE_BINNING = 128
 HS_ASYNC_BINNING = 64
 
 

@@ -270,7 +270,9 @@ int hs_forward_render(const hs_camera* c, int P, int S, int R, int binning_hint,
     const bool debug = c->debug != 0;
     int rc = 0;
     const int max_tile = binning_hint & HS_HINT_MASK;
-    if (binning_hint >= 0 && max_tile <= HS_TILE_SORT_MAX) {
+    if (flags & HS_REUSE_BINNING) {
+        // the sorted tile lists of this frame are already in binning_state / image_state
+    } else if (binning_hint >= 0 && max_tile <= HS_TILE_SORT_MAX) {
         rc = launch_tile_binning(P, R, max_tile, (binning_hint & HS_HINT_NO_SMALL) ? 0 : 1, cam, radii, g, b, img, stream,
                                  debug);
     } else {
@@ -282,7 +284,7 @@ int hs_forward_render(const hs_camera* c, int P, int S, int R, int binning_hint,
     }
     if (rc) return rc;
     return launch_blend_forward(S, cam, g, b, img, colors, semantics, out_color, out_semantic, out_depth,
-                                out_median_depth, out_opacity, out_mask, flags, stream, debug);
+                                out_median_depth, out_opacity, out_mask, flags & ~HS_REUSE_BINNING, stream, debug);
 }
 
 int hs_backward(const hs_camera* c, int P, int S, int R, const float* means3D, const int* radii,

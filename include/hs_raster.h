@@ -40,6 +40,9 @@ extern "C" {
                                 feature from a never-written scratch buffer (backward.cu:834, rasterizer_impl.cu:673). */
 #define HS_BWD_SIMT 4        /* backward: use the SIMT (warp-shuffle) blend backward instead of the tensor-core one */
 #define HS_NO_CULL 2         /* forward: disable the conservative per-warp footprint test (results are identical) */
+#define HS_REUSE_BINNING 128 /* hs_forward_render: the binning state already holds this frame's sorted tile lists (an earlier
+                             * hs_forward_render call on the same geometry): only blend.  Used to render more semantic
+                             * channels than the widest instantiation in several passes over the same lists. */
 #define HS_SORT_GLOBAL 32    /* hs_forward_geometry: reference-style binning (offsets scan, key duplication, one global
                                 radix sort) instead of the default per-tile bucket sort; sorted keys, tile lists and
                                 ranges are bit-identical either way */

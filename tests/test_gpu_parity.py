@@ -105,7 +105,9 @@ def test_against_reference_golden(path):
                                             ("small", 74, True), ("tiny", 102, True), ("small", 102, True),
                                             ("small", 0, False),
                                             # channel counts between the reference's four (config.h:18): own instantiations
-                                            ("small", 32, True), ("tiny", 48, True), ("small", 64, True)])
+                                            ("small", 32, True), ("tiny", 48, True), ("small", 64, True),
+                                            # wider than the widest instantiation: several blend passes over the same lists
+                                            ("tiny", 150, True), ("tiny", 550, True)])
 def test_against_cpu_oracle(key, S, semantic):
     C, Settings = new_impl()
     cfg = CONFIGS[key]
@@ -1178,12 +1180,18 @@ def test_public_api_autograd_and_edge_cases():
     assert pt.bits_equal(o5[2], o_ref[2][:5]) == 0
     (o5[2] * o5[2].detach()).sum().backward()
     assert sem5.grad.shape == sem5.shape and float(sem5.grad.abs().max()) > 0
-    # more channels than the largest instantiation is a loud error, not a fallback
-    with pytest.raises(RuntimeError, match="not instantiated"):
-        dgr.GaussianRasterizer_semantic(settings)(means3D=sc["means3D"], means2D=sc["means3D"],
-                                                  opacities=sc["opacities"], colors_precomp=sc["colors_precomp"],
-                                                  scales=sc["scales"], rotations=sc["rotations"],
-                                                  semantics_precomp=torch.rand(sc["means3D"].shape[0], 120, device="cuda"))
+    # more channels than the widest instantiation: rendered in several passes over the same sorted lists (a flat class
+    # map of any width, like rebuilding the reference with another NUM_SEMANTIC, config.h:18); the first 26 planes are
+    # bit-identical to the 26-channel render, and the gradient has the caller's width
+    wide = torch.cat([sc["semantics_precomp"], torch.rand(sc["means3D"].shape[0], 94, device="cuda")], 1).requires_grad_(True)
+    ow = dgr.GaussianRasterizer_semantic(settings)(means3D=sc["means3D"], means2D=sc["means3D"], opacities=sc["opacities"],
+                                                   colors_precomp=sc["colors_precomp"], scales=sc["scales"],
+                                                   rotations=sc["rotations"], semantics_precomp=wide)
+    assert ow[2].shape == (120, cfg.height, cfg.width) and pt.bits_equal(ow[0], o_ref[0]) == 0
+    assert pt.bits_equal(ow[2][:26], o_ref[2]) == 0
+    (ow[2] * ow[2].detach()).sum().backward()
+    assert wide.grad.shape == wide.shape and float(wide.grad[:, 100:].abs().max()) > 0
+
 
 def test_keyframe_parallel_mapping_gradient_sum():
     """SURVEY.md section 8e criterion on one GPU: the flat gradient buffer after a K-keyframe mapping iteration
