@@ -265,7 +265,9 @@ def _forward(background, means3D, colors, semantics, opacity, scales, rotations,
         cov_c = _f32c(cov3D_precomp, "cov3D_precomp", device)
         cam, keep = _camera(background, scale_modifier, viewmatrix, projmatrix, tan_fovx, tan_fovy, H, W, campos,
                             prefiltered, debug)
-        geom_bytes = lib.hs_geom_state_bytes(P)
+        # geometry arrays + the packed per-Gaussian records the blend kernel's TMA gather reads (sized for the widest pass)
+        S_rows = max([S] + [int(c.size(1)) for c in extra_semantic_chunks])
+        geom_bytes = lib.hs_geom_state_bytes_rows(P, S_rows)
         geomBuffer = torch.empty(geom_bytes, **byte)
         img_bytes = lib.hs_image_state_bytes(H, W)
         imgBuffer = torch.empty(img_bytes, **byte)
@@ -302,7 +304,7 @@ def _forward(background, means3D, colors, semantics, opacity, scales, rotations,
         flags = _lib.HS_NO_CULL if NO_CULL else 0
         _lib.check(lib.hs_forward_render(ctypes.byref(cam), P, S, num_rendered, int(hint.value), _ptr(colors_c),
                                          _ptr(sem_c),
-                                         _ptr(radii), _ptr(geomBuffer), _ptr(binningBuffer), bin_bytes,
+                                         _ptr(radii), _ptr(geomBuffer), geom_bytes, _ptr(binningBuffer), bin_bytes,
                                          _ptr(imgBuffer), img_bytes, _ptr(out_color), _ptr(out_sem), _ptr(out_depth),
                                          _ptr(out_median), _ptr(out_opacity), _ptr(out_mask), flags, stream),
                    "hs_forward_render")
@@ -313,7 +315,7 @@ def _forward(background, means3D, colors, semantics, opacity, scales, rotations,
             Sc = int(chunk_c.size(1))
             o_sem = torch.empty(Sc, H, W, **fopt)
             _lib.check(lib.hs_forward_render(ctypes.byref(cam), P, Sc, num_rendered, int(hint.value), _ptr(colors_c),
-                                             _ptr(chunk_c), _ptr(radii), _ptr(geomBuffer), _ptr(binningBuffer), bin_bytes,
+                                             _ptr(chunk_c), _ptr(radii), _ptr(geomBuffer), geom_bytes, _ptr(binningBuffer), bin_bytes,
                                              _ptr(imgBuffer), img_bytes, _ptr(out_color), _ptr(o_sem), _ptr(out_depth),
                                              _ptr(out_median), _ptr(out_opacity), None, flags | _lib.HS_REUSE_BINNING,
                                              stream), "hs_forward_render")

@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("HS_LIB", os.path.join(HERE, "libhsraster.so"))
 
 # every symbol include/hs_raster.h declares (tests check that the library exports all of them)
 EXPORTED_SYMBOLS = [
-    "hs_abi_version", "hs_last_error", "hs_supports_semantic_channels", "hs_geom_state_bytes",
+    "hs_abi_version", "hs_last_error", "hs_supports_semantic_channels", "hs_geom_state_bytes", "hs_geom_state_bytes_rows",
     "hs_image_state_bytes", "hs_binning_state_bytes", "hs_image_state_info_offset", "hs_forward_geometry", "hs_forward_render",
     "hs_backward", "hs_mark_visible", "hs_masked_l1", "hs_hier_cross_entropy", "hs_leaf_cross_entropy", "hs_leaf_cross_entropy_tc", "hs_leaf_ce_workspace_bytes", "hs_leaf_tc_debug", "hs_allreduce_sum", "hs_l1_ssim", "hs_adam_step", "hs_adam_step_device", "hs_transform_points", "hs_tracking_loss", "hs_pose_step", "hs_keyframe_overlap",
     "hs_compact_scratch_bytes", "hs_compact_plan", "hs_compact_gather",
@@ -58,6 +58,8 @@ def load() -> ctypes.CDLL:
     lib.hs_supports_semantic_channels.restype = c_int
     lib.hs_geom_state_bytes.argtypes = [c_int]
     lib.hs_geom_state_bytes.restype = c_size_t
+    lib.hs_geom_state_bytes_rows.argtypes = [c_int, c_int]
+    lib.hs_geom_state_bytes_rows.restype = c_size_t
     lib.hs_image_state_bytes.argtypes = [c_int, c_int]
     lib.hs_image_state_bytes.restype = c_size_t
     lib.hs_binning_state_bytes.argtypes = [c_int]
@@ -67,7 +69,7 @@ def load() -> ctypes.CDLL:
     lib.hs_forward_geometry.argtypes = [POINTER(HsCamera), c_int, vp, vp, vp, vp, vp, vp, c_int, c_int, vp, vp,
                                         c_size_t, vp, c_size_t, c_int, POINTER(c_int), POINTER(c_int), vp]
     lib.hs_forward_geometry.restype = c_int
-    lib.hs_forward_render.argtypes = [POINTER(HsCamera), c_int, c_int, c_int, c_int, vp, vp, vp, vp, vp, c_size_t, vp,
+    lib.hs_forward_render.argtypes = [POINTER(HsCamera), c_int, c_int, c_int, c_int, vp, vp, vp, vp, c_size_t, vp, c_size_t, vp,
                                       c_size_t, vp, vp, vp, vp, vp, vp, c_int, vp]
     lib.hs_forward_render.restype = c_int
     lib.hs_backward.argtypes = ([POINTER(HsCamera), c_int, c_int, c_int] + [vp] * 8 + [c_int, c_int] + [vp] * 21 +
@@ -123,7 +125,7 @@ def load() -> ctypes.CDLL:
     lib.hs_profile_read.argtypes = [POINTER(c_float), POINTER(c_int)]
     lib.hs_kernel_launch_count.restype = ctypes.c_longlong
     lib.hs_library_call_count.restype = ctypes.c_longlong
-    if lib.hs_abi_version() != 4:
+    if lib.hs_abi_version() != 5:
         raise ImportError("libhsraster.so ABI version mismatch; rebuild with `python -m hier_slam_b200.build --force`")
     _lib = lib
     return lib

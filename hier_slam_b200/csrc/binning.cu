@@ -115,6 +115,7 @@ int geom_view(char* base, size_t P, GeomView* v) {
     }
     carve(p, v->scan_temp, v->scan_temp_bytes);
     v->total_bytes = (size_t)(p - base) + HS_ALIGN;
+    v->rows = reinterpret_cast<float*>(base + align_up(v->total_bytes));
     return 0;
 }
 

