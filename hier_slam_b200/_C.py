@@ -9,6 +9,7 @@ from __future__ import annotations
 
 import ctypes
 import os
+import threading
 import weakref
 from typing import Optional, Tuple
 
@@ -24,6 +25,26 @@ SEM_ALPHA_GRAD = os.environ.get("HS_SEM_ALPHA_GRAD", "ref")
 NO_CULL = os.environ.get("HS_NO_CULL", "0") == "1"
 BWD_SIMT = os.environ.get("HS_BWD_SIMT", "0") == "1"   # SIMT blend backward instead of the tensor-core one
 SORT_GLOBAL = os.environ.get("HS_SORT_GLOBAL", "0") == "1"   # reference-style global radix sort instead of tile buckets
+# Speculative binning of the drop-in path: from the second forward at an image size on, the binning buffer and the sort
+# class are sized from the previous frame's counts (+25 %), the whole forward is enqueued without waiting, and the counts
+# are read back while the blend kernel runs; the rare frame that did not fit is repeated synchronously.  `num_rendered`
+# handed to autograd is then the buffer's capacity (it is opaque to callers: reference __init__.py:304-308).  Off: the
+# forward waits for the counts before it sizes the buffer, like the reference (rasterizer_impl.cu:548), and returns the
+# exact count.
+SPECULATIVE = os.environ.get("HS_SPECULATIVE_BINNING", "1") == "1"
+
+
+class exact_num_rendered:
+    """with exact_num_rendered(): forwards of this thread wait for the instance count (no speculation), so that
+    `num_rendered` and the state buffers' layout are the reference's (used by the parity tests that compare them)."""
+
+    def __enter__(self):
+        self.prev = getattr(_tls, "exact", False)
+        _tls.exact = True
+
+    def __exit__(self, *exc):
+        _tls.exact = self.prev
+        return False
 
 _contig_cache: dict = {}   # id(tensor) -> (weakref(tensor), version, contiguous copy)
 
@@ -57,42 +78,47 @@ class BinningCapacity:
         self.infos.clear()
 
 
-_capacity: Optional[BinningCapacity] = None
+# capacity / recorder contexts are per THREAD: two rasterizer users on different threads (and streams) do not see each
+# other's mode
+_tls = threading.local()
+_last_rendered: dict = {}   # (H, W, device) -> num_rendered of the previous forward at that image size (binning-buffer guess)
+
+
+def _current_capacity() -> Optional[BinningCapacity]:
+    return getattr(_tls, "capacity", None)
+
+
+def _current_recorder() -> Optional[list]:
+    return getattr(_tls, "recorder", None)
 
 
 class async_binning:
-    """with async_binning(capacity): every forward inside runs without a host sync (see BinningCapacity)."""
+    """with async_binning(capacity): every forward of THIS THREAD inside runs without a host sync (see BinningCapacity)."""
 
     def __init__(self, capacity: Optional[BinningCapacity]):
         self.capacity = capacity
 
     def __enter__(self):
-        global _capacity
-        self.prev, _capacity = _capacity, self.capacity
+        self.prev, _tls.capacity = _current_capacity(), self.capacity
         return self.capacity
 
     def __exit__(self, *exc):
-        global _capacity
-        _capacity = self.prev
+        _tls.capacity = self.prev
+        if self.capacity is not None and len(self.capacity.infos) > 4096:     # bound what a long-running caller accumulates
+            del self.capacity.infos[:-4096]
         return False
 
 
-_recorder: Optional[list] = None
-_last_rendered: dict = {}   # (H, W, device) -> num_rendered of the previous forward at that image size (binning-buffer guess)
-
-
 class record_binning:
-    """with record_binning() as infos: the int32[4] binning counts of every forward inside are appended to `infos`
-    (used to size a BinningCapacity from synchronous renders)."""
+    """with record_binning() as infos: the int32[4] binning counts of every forward of this thread inside are appended to
+    `infos` (used to size a BinningCapacity from synchronous renders)."""
 
     def __enter__(self):
-        global _recorder
-        self.prev, _recorder = _recorder, []
-        return _recorder
+        self.prev, _tls.recorder = _current_recorder(), []
+        return _tls.recorder
 
     def __exit__(self, *exc):
-        global _recorder
-        _recorder = self.prev
+        _tls.recorder = self.prev
         return False
 
 
@@ -131,6 +157,10 @@ def clear_grad_sinks() -> None:
 
 
 def _sink_for(t: Optional[torch.Tensor]):
+    """The registered gradient buffer if -- and only if -- `t` is the registered parameter itself and autograd will
+    accumulate into exactly that buffer: a leaf that requires grad whose .grad IS the registered view.  Aliases of the
+    parameter's memory (leaf.detach(), a no-grad copy of the leaf, a view) take the normal path, so e.g. tracking renders
+    between two mapping steps cannot leak gradients into the mapping buffer."""
     if t is None or not _grad_sinks or t.numel() == 0 or not t.is_contiguous():
         return None
     hit = _grad_sinks.get(t.data_ptr())
@@ -139,6 +169,8 @@ def _sink_for(t: Optional[torch.Tensor]):
     p = hit[0]()
     if p is None or p.data_ptr() != t.data_ptr() or p.shape != t.shape or hit[1].device != t.device:
         _grad_sinks.pop(t.data_ptr(), None)
+        return None
+    if not (t.requires_grad and t.is_leaf and t.grad is not None and t.grad.data_ptr() == hit[1].data_ptr()):
         return None
     return hit[1]
 
@@ -219,7 +251,7 @@ def _chunks(S: int):
 
 def _forward(background, means3D, colors, semantics, opacity, scales, rotations, scale_modifier, cov3D_precomp,
              viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height, image_width, sh, degree, campos, prefiltered,
-             debug, semantic: bool, extra_semantic_chunks=()):
+             debug, semantic: bool, extra_semantic_chunks=(), _speculate: bool = True):
     lib = _lib.load()
     if means3D.dim() != 2 or means3D.size(1) != 3:
         raise RuntimeError("means3D must have dimensions (num_points, 3)")   # rasterize_points.cu:266-268
@@ -271,7 +303,8 @@ def _forward(background, means3D, colors, semantics, opacity, scales, rotations,
         geomBuffer = torch.empty(geom_bytes, **byte)
         img_bytes = lib.hs_image_state_bytes(H, W)
         imgBuffer = torch.empty(img_bytes, **byte)
-        cap = None if SORT_GLOBAL else _capacity
+        cap = None if SORT_GLOBAL else _current_capacity()
+        _recorder = _current_recorder()
         # Everything that does not depend on num_rendered is allocated BEFORE the read-back, and the binning buffer is
         # sized from the previous frame at this image size (+25 %; the map grows slowly from frame to frame), so the GPU idles only for the copy and two launches
         # between hs_forward_geometry's sync and the first kernel of hs_forward_render.
@@ -281,11 +314,20 @@ def _forward(background, means3D, colors, semantics, opacity, scales, rotations,
         out_median = torch.empty(1, H, W, **fopt)
         out_opacity = torch.empty(1, H, W, **fopt)
         out_mask = None if semantic else torch.empty(1, H, W, **fopt)
-        guess = cap.instances if cap is not None else _last_rendered.get((H, W, device.index), 0) * 5 // 4
+        key = (H, W, device.index)
+        prev = _last_rendered.get(key)             # (instances, longest tile list) of the previous forward at this size
+        spec = (cap is None and prev is not None and SPECULATIVE and _speculate and not SORT_GLOBAL and not debug
+                and not getattr(_tls, "exact", False) and prev[1] * 5 // 4 + 64 <= 16384
+                and not torch.cuda.is_current_stream_capturing())
+        if spec:     # capacities from the previous frame: nothing below waits for the device
+            cap_inst, cap_tile = prev[0] * 5 // 4 + 4096, min(prev[1] * 5 // 4 + 64, 16384)
+        guess = cap.instances if cap is not None else (cap_inst if spec else (prev[0] * 5 // 4 if prev else 0))
         binningBuffer = torch.empty(lib.hs_binning_state_bytes(guess), **byte) if guess > 0 else None
-        R = ctypes.c_int(cap.instances if cap is not None else 0)
-        hint = ctypes.c_int(cap.longest_tile if cap is not None else 0)
+        R = ctypes.c_int(cap.instances if cap is not None else (cap_inst if spec else 0))
+        hint = ctypes.c_int(cap.longest_tile if cap is not None else (cap_tile if spec else 0))
         gflags = _lib.HS_SORT_GLOBAL if SORT_GLOBAL else (_lib.HS_ASYNC_BINNING if cap is not None else 0)
+        if spec:
+            gflags = _lib.HS_ASYNC_BINNING | _lib.HS_DEFER_READBACK
         _lib.check(lib.hs_forward_geometry(ctypes.byref(cam), P, _ptr(means3D_c), _ptr(opac_c), _ptr(scales_c),
                                            _ptr(rot_c), _ptr(cov_c), _ptr(sh_c), int(degree), M, _ptr(radii),
                                            _ptr(geomBuffer), geom_bytes,
@@ -294,8 +336,9 @@ def _forward(background, means3D, colors, semantics, opacity, scales, rotations,
         num_rendered = int(R.value)          # capacity mode: the capacity (the counts stay on the device)
         if cap is not None:
             cap.infos.append(binning_info(imgBuffer, H, W))
-        else:
-            _last_rendered[(H, W, device.index)] = num_rendered
+        elif not spec and not SORT_GLOBAL:
+            # the synchronous call returned the instance count and (in the low bits of the hint) the longest tile list
+            _last_rendered[key] = (num_rendered, int(hint.value) & 0x0fffffff)
         if _recorder is not None and not SORT_GLOBAL:
             _recorder.append(binning_info(imgBuffer, H, W))
         if binningBuffer is None or num_rendered > guess:
@@ -308,6 +351,16 @@ def _forward(background, means3D, colors, semantics, opacity, scales, rotations,
                                          _ptr(imgBuffer), img_bytes, _ptr(out_color), _ptr(out_sem), _ptr(out_depth),
                                          _ptr(out_median), _ptr(out_opacity), _ptr(out_mask), flags, stream),
                    "hs_forward_render")
+        if spec:
+            # the counts have been on their way since the tile scan; by now the blend kernel is queued behind them
+            counts = (ctypes.c_int * 4)()
+            _lib.check(lib.hs_forward_readback(counts), "hs_forward_readback")
+            _last_rendered[key] = (int(counts[0]), int(counts[1]))
+            if counts[3] != 0:       # did not fit the guessed capacity (rendered empty): once more, synchronously
+                del keep
+                return _forward(background, means3D, colors, semantics, opacity, scales, rotations, scale_modifier,
+                                cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height, image_width, sh,
+                                degree, campos, prefiltered, debug, semantic, extra_semantic_chunks, _speculate=False)
         # more semantic channels than the widest instantiation: further blend passes over the same sorted lists
         extra_out = []
         for chunk in extra_semantic_chunks:

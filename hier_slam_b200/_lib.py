@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("HS_LIB", os.path.join(HERE, "libhsraster.so"))
 
 # every symbol include/hs_raster.h declares (tests check that the library exports all of them)
 EXPORTED_SYMBOLS = [
-    "hs_abi_version", "hs_last_error", "hs_supports_semantic_channels", "hs_geom_state_bytes", "hs_geom_state_bytes_rows",
+    "hs_abi_version", "hs_last_error", "hs_supports_semantic_channels", "hs_geom_state_bytes", "hs_geom_state_bytes_rows", "hs_forward_readback",
     "hs_image_state_bytes", "hs_binning_state_bytes", "hs_image_state_info_offset", "hs_forward_geometry", "hs_forward_render",
     "hs_backward", "hs_mark_visible", "hs_masked_l1", "hs_hier_cross_entropy", "hs_leaf_cross_entropy", "hs_leaf_cross_entropy_tc", "hs_leaf_ce_workspace_bytes", "hs_leaf_tc_debug", "hs_allreduce_sum", "hs_l1_ssim", "hs_adam_step", "hs_adam_step_device", "hs_transform_points", "hs_tracking_loss", "hs_pose_step", "hs_keyframe_overlap",
     "hs_compact_scratch_bytes", "hs_compact_plan", "hs_compact_gather",
@@ -28,6 +28,7 @@ HS_NO_CULL = 2
 HS_BWD_SIMT = 4
 HS_SORT_GLOBAL = 32
 HS_REUSE_BINNING = 128
+HS_DEFER_READBACK = 256
 HS_ASYNC_BINNING = 64
 
 
@@ -60,6 +61,8 @@ def load() -> ctypes.CDLL:
     lib.hs_geom_state_bytes.restype = c_size_t
     lib.hs_geom_state_bytes_rows.argtypes = [c_int, c_int]
     lib.hs_geom_state_bytes_rows.restype = c_size_t
+    lib.hs_forward_readback.argtypes = [POINTER(c_int)]
+    lib.hs_forward_readback.restype = c_int
     lib.hs_image_state_bytes.argtypes = [c_int, c_int]
     lib.hs_image_state_bytes.restype = c_size_t
     lib.hs_binning_state_bytes.argtypes = [c_int]

@@ -48,6 +48,23 @@ static int* pinned_int() {
     return p;
 }
 
+// deferred read-back of the binning counts (HS_DEFER_READBACK): pinned words + the event that marks their arrival
+struct Readback {
+    int* host = nullptr;
+    cudaEvent_t ev = nullptr;
+};
+static Readback* readback_slot() {
+    static thread_local Readback rb;
+    if (rb.host == nullptr) {
+        if (cudaHostAlloc((void**)&rb.host, 64, cudaHostAllocDefault) != cudaSuccess) {
+            rb.host = nullptr;
+            return nullptr;
+        }
+        if (cudaEventCreateWithFlags(&rb.ev, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    }
+    return &rb;
+}
+
 extern "C" {
 
 int hs_abi_version(void) { return HS_RASTER_ABI_VERSION; }
@@ -210,6 +227,16 @@ int hs_forward_geometry(const hs_camera* c, int P, const float* means3D, const f
     if (async) {
         *num_rendered = cap_instances;
         *binning_hint = tile_cap;   // both sort classes may be needed; nothing is read back, nothing synchronises
+        if (flags & HS_DEFER_READBACK) {
+            // the counts travel to the host while the render kernels that the caller enqueues next are running
+            Readback* rb = readback_slot();
+            if (rb == nullptr) {
+                set_error("HS_DEFER_READBACK: cannot allocate the pinned read-back slot");
+                return 2;
+            }
+            HS_CUDA_OK(cudaMemcpyAsync(rb->host, img.info, 4 * sizeof(int), cudaMemcpyDeviceToHost, stream));
+            HS_CUDA_OK(cudaEventRecord(rb->ev, stream));
+        }
         return 0;
     }
     HS_CUDA_OK(cudaMemcpyAsync(host, img.info, 3 * sizeof(int), cudaMemcpyDeviceToHost, stream));
@@ -217,6 +244,17 @@ int hs_forward_geometry(const hs_camera* c, int P, const float* means3D, const f
     *num_rendered = host[0];
     // longest tile list, and whether any tile falls in the small sort class
     *binning_hint = (host[1] > HS_HINT_MASK ? HS_HINT_MASK : host[1]) | (host[2] == 0 ? HS_HINT_NO_SMALL : 0);
+    return 0;
+}
+
+int hs_forward_readback(int counts[4]) {
+    Readback* rb = readback_slot();
+    if (rb == nullptr || counts == nullptr) {
+        set_error("hs_forward_readback: no read-back pending on this thread");
+        return 1;
+    }
+    HS_CUDA_OK(cudaEventSynchronize(rb->ev));
+    for (int i = 0; i < 4; i++) counts[i] = rb->host[i];
     return 0;
 }
 

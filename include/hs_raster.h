@@ -40,6 +40,11 @@ extern "C" {
                                 feature from a never-written scratch buffer (backward.cu:834, rasterizer_impl.cu:673). */
 #define HS_BWD_SIMT 4        /* backward: use the SIMT (warp-shuffle) blend backward instead of the tensor-core one */
 #define HS_NO_CULL 2         /* forward: disable the conservative per-warp footprint test (results are identical) */
+#define HS_DEFER_READBACK 256 /* hs_forward_geometry, with HS_ASYNC_BINNING: additionally copy the binning counts to pinned host
+                              * memory WITHOUT waiting; hs_forward_readback() waits for them later -- after the caller has
+                              * enqueued hs_forward_render, so the GPU never idles behind the read-back.  The drop-in Python
+                              * path uses this with capacities guessed from the previous frame and repeats the (rare) frame
+                              * that did not fit synchronously. */
 #define HS_REUSE_BINNING 128 /* hs_forward_render: the binning state already holds this frame's sorted tile lists (an earlier
                              * hs_forward_render call on the same geometry): only blend.  Used to render more semantic
                              * channels than the widest instantiation in several passes over the same lists. */
@@ -98,6 +103,10 @@ int hs_forward_geometry(const hs_camera* cam, int P, const float* means3D, const
                         int sh_degree, int sh_coeffs, int* radii, void* geom_state, size_t geom_state_bytes,
                         void* image_state, size_t image_state_bytes, int flags, int* num_rendered, int* binning_hint,
                         void* stream);
+
+/* Waits for the counts a hs_forward_geometry(HS_ASYNC_BINNING | HS_DEFER_READBACK) call of THIS THREAD sent to the host:
+ * counts = {num_rendered, longest tile list, tiles in the small sort class, overflow flag}. */
+int hs_forward_readback(int counts[4]);
 
 /* Stage 2 of the forward: instance scatter + per-tile sort (or key duplication, global sort and range
  * identification), alpha compositing.  num_rendered and binning_hint are the values stage 1 returned; image_state

@@ -25,7 +25,15 @@ def make_settings(SettingsCls, cfg, device="cuda", w2c=None, debug=False):
 
 
 def run_forward(C, settings, scene: Dict[str, torch.Tensor], semantic=True):
-    """C = a `_C`-compatible module (hier_slam_b200._C or the reference's).  Returns a dict."""
+    """C = a `_C`-compatible module (hier_slam_b200._C or the reference's).  Returns a dict.  This repository's module
+    is run with the exact instance count (`exact_num_rendered`: no speculative binning), so that `R` and the state
+    buffers can be compared with the reference's; the public-API tests exercise the speculative default."""
+    import contextlib
+    with (C.exact_num_rendered() if hasattr(C, "exact_num_rendered") else contextlib.nullcontext()):
+        return _run_forward(C, settings, scene, semantic)
+
+
+def _run_forward(C, settings, scene: Dict[str, torch.Tensor], semantic=True):
     e = torch.Tensor([])
     rs = settings
     if semantic:

@@ -1244,6 +1244,19 @@ def test_keyframe_parallel_mapping_gradient_sum():
     assert_grads_close(total, plain.flat_grad, "direct accumulation vs autograd accumulation", tol=1e-5)
     for k in ("colors_precomp", "semantics_precomp"):
         assert float(plain.leaves[k].grad.abs().max()) > 0
+    # an ALIAS of a registered parameter (leaf.detach(): same memory, no autograd) must not be redirected into the flat
+    # gradient buffer -- e.g. a tracking render between two mapping steps
+    sinked = FlatParams(sc)
+    lv = sinked.leaves
+    settings = pt.make_settings(dgr.GaussianRasterizationSettings, cfg, "cuda", w2c=poses[0])
+    out = dgr.GaussianRasterizer_semantic(settings)(
+        means3D=lv["means3D"], means2D=torch.zeros_like(lv["means3D"]), opacities=lv["opacities"],
+        colors_precomp=lv["colors_precomp"].detach(), scales=lv["scales"], rotations=lv["rotations"],
+        semantics_precomp=lv["semantics_precomp"].detach())
+    ((out[0] * ug["color"]).sum() + (out[2] * ug["semantic"]).sum()).backward()
+    assert float(lv["means3D"].grad.abs().max()) > 0
+    assert float(lv["colors_precomp"].grad.abs().max()) == 0 and float(lv["semantics_precomp"].grad.abs().max()) == 0
+    sinked.release()
 
 
 def test_graphed_mapping_iteration_matches_the_eager_loop(float32_convolutions):
