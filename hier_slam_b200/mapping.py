@@ -291,7 +291,8 @@ def mapping_iteration(params: FlatParams, keyframe_losses: Sequence[Callable[[Di
             loss = keyframe_losses[k](params.leaves)
             loss.backward()
             total = total + loss.detach()
-    allreduce_gradients(params, group)
+    if world_size > 1:      # a single-rank iteration inside a larger job (e.g. a serial re-render for verification) must not
+        allreduce_gradients(params, group)      # enter a collective that the other ranks do not call
     return total
 
 

@@ -48,6 +48,13 @@ def _worker(rank, world, port, out):
     params = FlatParams(_scene())
     loss = mapping_iteration(params, _loss_fns(), rank, world)
     out[rank] = (params.flat_grad.clone(), float(loss))
+    # a single-rank iteration INSIDE the 2-rank job (bench.py's serial verification re-render on rank 0) must not enter a
+    # collective: it would wait for ranks that never call it (this hung an 8-GPU run in round 2)
+    if rank == 0:
+        solo = FlatParams(_scene())
+        mapping_iteration(solo, _loss_fns()[:2], 0, 1)
+        out["solo"] = solo.flat_grad.clone()
+    dist.barrier()
     dist.destroy_process_group()
 
 
@@ -83,3 +90,15 @@ def test_allreduced_gradient_equals_sum_of_keyframe_gradients():
     for r in range(world):
         assert torch.allclose(res[r][0], single.flat_grad, rtol=1e-5, atol=1e-6)     # every rank holds the full sum
     assert abs(sum(res[r][1] for r in range(world)) - float(total)) < 1e-3 * abs(float(total))
+
+
+def test_single_rank_iteration_inside_a_larger_job_calls_no_collective():
+    world = 2
+    port = _free_port()
+    with mp.Manager() as m:
+        out = m.dict()
+        mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)      # would hang (and time out) on a stray collective
+        solo = out["solo"]
+    ref = FlatParams(_scene())
+    mapping_iteration(ref, _loss_fns()[:2], 0, 1)
+    assert torch.allclose(solo, ref.flat_grad, rtol=1e-5, atol=1e-6)
