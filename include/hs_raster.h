@@ -259,7 +259,7 @@ int hs_leaf_cross_entropy_tc(const float* sem, const int* labels, const float* w
  * rank over NVLink peer memory (hier_slam_b200/csrc/allreduce.cu).  peer_buffers[r] / peer_signal_pads[r] (HOST arrays of
  * world_size device pointers): rank r's buffer and signal pad as mapped into THIS process; multicast_ptr: the NVSwitch
  * multicast mapping of the buffer (multimem.ld_reduce / multimem.st do the reduction and the broadcast in the switch) or
- * NULL (peer loads / stores instead).  The signal pad needs 2 * blocks * world_size 32-bit words, zeroed once; `epoch`
+ * NULL (peer loads / stores instead).  The signal pad needs blocks * world_size 32-bit words (word [block][rank]), zeroed once; `epoch`
  * must grow by 2 from call to call, starting at 1, identically on every rank.  All ranks must call it in the same order.
  * Waits are bounded (4 s): a missing peer raises a CUDA error instead of hanging. */
 int hs_allreduce_sum(void* multicast_ptr, void* const* peer_buffers, void* const* peer_signal_pads, int rank, int world_size,

@@ -9,7 +9,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from hier_slam_b200.mapping import FlatParams, keyframes_of_rank, mapping_iteration
+from hier_slam_b200.mapping import FlatParams, enable_symmetric_allreduce, keyframes_of_rank, mapping_iteration
 
 K = 5
 
@@ -58,6 +58,18 @@ def _worker(rank, world, port, out):
     dist.destroy_process_group()
 
 
+def _worker_symm_fallback(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    params = FlatParams(_scene())
+    symm = enable_symmetric_allreduce(params)          # CPU tensors / gloo: no NVLink symmetric memory here
+    loss = mapping_iteration(params, _loss_fns(), rank, world)
+    out[rank] = (symm is None, params.symm_error, params.flat_grad.clone(), float(loss))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
 def test_partition_is_round_robin():
     assert keyframes_of_rank(8, 0, 1) == list(range(8))
     assert keyframes_of_rank(8, 1, 2) == [1, 3, 5, 7]
@@ -102,3 +114,20 @@ def test_single_rank_iteration_inside_a_larger_job_calls_no_collective():
     ref = FlatParams(_scene())
     mapping_iteration(ref, _loss_fns()[:2], 0, 1)
     assert torch.allclose(solo, ref.flat_grad, rtol=1e-5, atol=1e-6)
+
+
+def test_symmetric_allreduce_falls_back_to_the_process_group_and_says_why():
+    """enable_symmetric_allreduce on a job without NVLink symmetric memory (here: CPU tensors, gloo) must not raise, must
+    record the reason, and the iteration must still produce the full gradient sum through torch.distributed."""
+    world = 2
+    port = _free_port()
+    with mp.Manager() as m:
+        out = m.dict()
+        mp.spawn(_worker_symm_fallback, args=(world, port, out), nprocs=world, join=True)
+        res = {r: out[r] for r in range(world)}
+    single = FlatParams(_scene())
+    mapping_iteration(single, _loss_fns(), 0, 1)
+    for r in range(world):
+        fell_back, why, grad, _ = res[r]
+        assert fell_back and isinstance(why, str) and len(why) > 0
+        assert torch.allclose(grad, single.flat_grad, rtol=1e-5, atol=1e-6)
