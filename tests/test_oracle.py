@@ -267,3 +267,40 @@ def test_sh_colour_backward_matches_autograd(deg):
     assert torch.allclose(dmean, m.grad if m.grad is not None else torch.zeros_like(dmean), atol=1e-10)
     n = (deg + 1) ** 2
     assert float(dsh[:, n:].abs().max()) == 0 if n < M else True
+
+
+@pytest.mark.parametrize("mode", ["ref", "exact"])
+def test_channel_passes_add_up_to_the_single_pass_backward(mode):
+    """The claim behind hier_slam_b200._C._chunks (S beyond the widest kernel instantiation is rendered in passes over the
+    same sorted lists): geometry / T / n_contrib do not depend on the semantic channels, the forward planes of a pass are
+    the corresponding planes of the full render, and the backward is linear in the upstream gradients, so
+    backward(all grads, all channels) == backward(non-semantic grads + first slice) + sum_k backward(slice k only) with
+    dL/dsemantics concatenated.  Checked on the oracle in float64, in both Q1 modes."""
+    cfg = CONFIGS["tiny"]
+    S, step = 10, 4
+    sc = {k: v.double() for k, v in make_scene(cfg, 3).items()}
+    g0 = torch.Generator().manual_seed(5)
+    sc["semantics_precomp"] = torch.rand(sc["means3D"].shape[0], S, generator=g0, dtype=torch.float64)
+    ug = {k: v.double() for k, v in upstream_grads(cfg, 2).items()}
+    ug["semantic"] = torch.randn(S, cfg.height, cfg.width, generator=g0, dtype=torch.float64)
+    st, cam = oracle_forward(cfg, sc, torch.float64)
+    full = oracle_backward(cfg, sc, st, cam, ug, mode, torch.float64)
+    total, sem_parts = None, []
+    for i, c0 in enumerate(range(0, S, step)):
+        part = dict(sc, semantics_precomp=sc["semantics_precomp"][:, c0:c0 + step].contiguous())
+        st_c, _ = oracle_forward(cfg, part, torch.float64)
+        assert torch.equal(st_c["n_contrib"], st["n_contrib"]) and torch.equal(st_c["final_T"], st["final_T"])
+        assert torch.equal(st_c["semantic"], st["semantic"][c0:c0 + step]) and torch.equal(st_c["color"], st["color"])
+        g_c = dict(semantic=ug["semantic"][c0:c0 + step]) if i > 0 else dict(ug, semantic=ug["semantic"][c0:c0 + step])
+        r = oracle_backward(cfg, part, st_c, cam, g_c, mode, torch.float64)
+        sem_parts.append(r["dL_dsemantics"])
+        if total is None:
+            total = {k: v.clone() for k, v in r.items() if k != "dL_dsemantics" and torch.is_tensor(v)}
+        else:
+            for k in total:
+                total[k] = total[k] + r[k]
+    assert (torch.cat(sem_parts, 1) - full["dL_dsemantics"]).abs().max() < 1e-12
+    for k, v in total.items():
+        if v.dtype.is_floating_point:
+            scale = float(full[k].abs().max()) + 1e-30
+            assert float((v - full[k]).abs().max()) <= 1e-11 * scale + 1e-14, k
