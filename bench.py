@@ -380,12 +380,8 @@ def run_ours(a, rank, world, local):
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": "f32", "data": "synthetic",
-               "config": {"workload": cfg.name, "gaussians": P, "visible": V, "image": [cfg.width, cfg.height],
-                          "semantic_channels": S, "keyframes_per_rank_per_step": 1,
-                          "parallelism": f"keyframe-dp{world}" if world > 1 else "single-gpu",
-                          "upstream_grads": "raster-only: N(0,1)/N on all five outputs",
-                          "l2": "per-step working set ~350 MB (inputs+grad planes+outputs) > 126 MB L2; no explicit flush",
-                          "sem_alpha_grad": _C.SEM_ALPHA_GRAD},
+               "config": workload_config(cfg, P, world, _C.SEM_ALPHA_GRAD),
+               "workload_stats": {"visible": V},
                "wall_ms_per_step": wall_ms / a.steps,
                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                        "ms_per_step": ms_e2e / n_e2e, "steps": n_e2e,
@@ -512,6 +508,17 @@ def run_mapping_k8(a, rank, world, local):
                             "bus_bandwidth_GBps": 2 * (world - 1) / world * params.grad_bytes() / (ar_ms * 1e-3) / 1e9}
         out["verify"] = verify
     return out
+
+
+def workload_config(cfg, gaussians, world, sem_alpha_grad):
+    """`config` of the headline line -- ONE definition for the default arm and for --impl reference, so that both arms
+    name the workload with the same keys and values."""
+    return {"workload": cfg.name, "gaussians": int(gaussians), "image": [cfg.width, cfg.height],
+            "semantic_channels": cfg.num_semantic, "keyframes_per_rank_per_step": 1,
+            "parallelism": f"keyframe-dp{world}" if world > 1 else "single-gpu",
+            "upstream_grads": "raster-only: N(0,1)/N on all five outputs",
+            "l2": "per-step working set ~350 MB (inputs+grad planes+outputs) > 126 MB L2; no explicit flush",
+            "sem_alpha_grad": sem_alpha_grad}
 
 
 def timed_loop(fn, n, warm=3):
@@ -854,8 +861,9 @@ def main():
                 "ms_per_step": 1e3 * r["sample_step_s"], "ms_per_full_keyframe": 1e3 / r["value"],
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
-                "config": {"workload": cfg.name, "gaussians": cfg.num_gaussians, "image": [cfg.width, cfg.height],
-                           "semantic_channels": cfg.num_semantic},
+                # the same config object as the default arm prints (same workload, same keys)
+                "config": workload_config(cfg, cfg.num_gaussians, int(os.environ.get("WORLD_SIZE", "1")),
+                                          os.environ.get("HS_SEM_ALPHA_GRAD", "ref")),
                 "cpu_baseline": r,
                 "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "note": "the reference rasterizer is CUDA-only; this arm is the CPU restatement of its algorithm "
