@@ -172,3 +172,14 @@ def test_python_host_has_no_undefined_names():
         missing = {n.id for n in ast.walk(tree) if isinstance(n, ast.Name) and isinstance(n.ctx, ast.Load)
                    and n.id not in defined}
         assert not missing, f"{os.path.basename(path)}: undefined names {sorted(missing)}"
+
+
+def test_channel_passes_cover_every_channel_once():
+    """S beyond the widest instantiation is rendered in passes (hier_slam_b200._C._chunks): the passes tile [0, S) without
+    gaps or overlap, each on an instantiated width that holds it."""
+    assert _C._chunks(150) == [(0, 74, 74), (74, 74, 74), (148, 2, 16)]
+    for S in (103, 148, 149, 550, 1000):
+        parts = _C._chunks(S)
+        assert parts[0][0] == 0 and sum(n for _, n, _ in parts) == S
+        for (c0, n, w), nxt in zip(parts, parts[1:] + [(S, 0, 0)]):
+            assert c0 + n == nxt[0] and 0 < n <= w and w in _C._BUILT_S
