@@ -177,6 +177,7 @@ def test_python_host_has_no_undefined_names():
 def test_channel_passes_cover_every_channel_once():
     """S beyond the widest instantiation is rendered in passes (hier_slam_b200._C._chunks): the passes tile [0, S) without
     gaps or overlap, each on an instantiated width that holds it."""
+    from hier_slam_b200 import _C
     assert _C._chunks(150) == [(0, 74, 74), (74, 74, 74), (148, 2, 16)]
     for S in (103, 148, 149, 550, 1000):
         parts = _C._chunks(S)
