@@ -249,8 +249,8 @@ def mapping_iteration(params: FlatParams, keyframe_losses: Sequence[Callable[[Di
             total = mapping_iteration(params, keyframe_losses, rank, world_size, group, streams, None)
         flag = torch.stack([i[3] for i in capacity.infos]).max().to(torch.int32) if capacity.infos else \
             torch.zeros((), dtype=torch.int32, device=params.flat.device)
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-            dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+        if world_size > 1 and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)      # a single-rank iteration calls no collective
         if int(flag) == 0:                    # the iteration's one host sync, behind all of its GPU work
             return total
         return mapping_iteration(params, keyframe_losses, rank, world_size, group, streams, None)
